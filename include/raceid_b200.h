@@ -1,0 +1,103 @@
+/*
+ * raceid_b200.h — C ABI of libraceid_b200.so: the B200-native replacement for RaceID's clustering hot path.
+ *
+ * This is the drop-in boundary.  The reference reaches native code through Rcpp-generated
+ * `.Call` stubs (reference src/RcppExports.cpp:15-24, registration table :154-172, R stubs
+ * R/RcppExports.R:4-46); the functions below are what an equivalent `.Call` shim binds when the bodies of
+ * `dist.gen` (R/RaceID_utils.R:9-15), `clustfun` (R/RaceID_utils.R:102-148) and `compmedoids`
+ * (R/RaceID.R:1298-1316) are replaced.  INTEGRATION.md shows the Rcpp stub for each entry point.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, <0 on error (rid_last_error() gives the text,
+ *     the R stub turns it into Rcpp::stop => an R condition, like BEGIN_RCPP/END_RCPP does upstream);
+ *   - inputs are borrowed and read-only; outputs are caller-allocated host buffers;
+ *   - matrices follow R: column-major; cell/medoid indices crossing this ABI are 0-based, cluster labels 1-based;
+ *   - the library draws no random numbers: bootstrap index vectors come from the caller (R's sample()).
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is usable.
+ */
+#ifndef RACEID_B200_H
+#define RACEID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rid_ctx rid_ctx;   /* one GPU (one rank of a row-sharded job)            */
+typedef struct rid_dmat rid_dmat; /* device-resident distance matrix, row-block sharded */
+
+enum { RID_PEARSON = 0, RID_SPEARMAN = 1, RID_LOGPEARSON = 2, RID_EUCLIDEAN = 3 };
+
+enum {
+    RID_OK = 0,
+    RID_ERR_ARG = -1,     /* bad argument (k outside {1..n-1}, unknown metric, ...)                     */
+    RID_ERR_CUDA = -2,    /* CUDA / NCCL runtime failure, or no usable sm_100 device                    */
+    RID_ERR_NA = -3,      /* NAs in the dissimilarity matrix (pam() refuses them upstream)               */
+    RID_ERR_NOMEM = -4,
+    RID_ERR_UNSUPPORTED = -5
+};
+
+const char *rid_last_error(void);
+int rid_version(void);
+
+/* ---- contexts -------------------------------------------------------------------------------------- */
+/* One context per GPU.  world==1: single-GPU.  world>1: this process is rank `rank` of a job that shards the
+ * distance matrix by row blocks; `nccl_uid` is the 128-byte id made by rid_nccl_unique_id()
+ * on rank 0 and shipped to the other ranks by the caller (torch.distributed store, MPI, a file ...). */
+int rid_nccl_unique_id(void *uid128);
+int rid_ctx_create(int device, int rank, int world, const void *nccl_uid, rid_ctx **out);
+int rid_ctx_destroy(rid_ctx *ctx);
+int rid_ctx_sync(rid_ctx *ctx);
+/* Milliseconds the GPU spent in the last compute call of this ctx, from CUDA events on its stream. */
+double rid_ctx_last_ms(const rid_ctx *ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+long long rid_ctx_launches(const rid_ctx *ctx);
+
+/* ---- distance matrix: replaces dist.gen (R/RaceID_utils.R:9-15) as called at R/RaceID.R:769 ---------- */
+/* x: G x N column-major doubles (column c = the G feature values of cell c), i.e. what cor()/dist() see.
+ * x_on_device != 0: x is a device pointer on ctx's GPU (benchmarks with resident inputs).
+ * Every rank passes the full x; rank r keeps rows [row0,row1) of the N x N result.
+ * n_zero_var: number of zero-variance cells (cor() returns NA for them and warns; their rows/cols are NA). */
+int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric, int x_on_device, rid_dmat **out,
+             int *n_zero_var);
+/* Adopt a distance matrix computed elsewhere (clustexp() only needs @distances, R/RaceID.R:903,907).
+ * D: N x N column-major.  Like as.dist() the LOWER triangle is authoritative and is mirrored. */
+int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat **out);
+int rid_dmat_free(rid_dmat *dm);
+/* N, owned row range, the value of one quantisation step (distances are stored as 32-bit fixed point,
+ * see DESIGN.md), 1 if the matrix holds NAs. */
+int rid_dmat_info(const rid_dmat *dm, int *N, int *row0, int *row1, double *step, int *has_na);
+/* as.matrix() on demand: out is m x n column-major, rows ridx (NULL = 0..m-1), columns cidx (NULL = 0..n-1).
+ * Collective when world>1 (every rank calls with the same arguments; every rank receives the block). */
+int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cidx, int n, double *out);
+
+/* ---- cluster::pam(as.dist(x[subset,subset]), k) as called at R/RaceID_utils.R:113,221 ------------------ */
+/* subset: m cell indices (order significant: position = object index inside pam); NULL = all cells.
+ * medoids[k]: id.med, as POSITIONS into subset, in cluster-number order.  labels[m]: `clustering`.
+ * objective[2]: build, swap.  avg_sil: silinfo$avg.width (NULL = skip).  n_swaps: accepted swaps (nullable). */
+int rid_pam(rid_dmat *dm, const int *subset, int m, int k, int *medoids, int *labels, double *objective,
+            double *avg_sil, int *n_swaps);
+
+/* ---- clusGapExt(..., FUNcluster=pam, random=FALSE, diss=TRUE) k-loop, R/RaceID_utils.R:58-61 ----------- */
+int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW);
+
+/* ---- fpc::clusterboot(..., clustermethod=pamkdCBI, k) as called at R/RaceID_utils.R:132-133 ------------ */
+/* samples: the B resamples concatenated (already unique()'d, first-occurrence order); sample_len[B].
+ * partition[N], medoids[k] (cell indices of c1's id.med), bootresult k x B column-major. */
+int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const int *sample_len, int B, int *partition,
+                    int *medoids, double *bootresult);
+
+/* ---- compmedoids (R/RaceID.R:1298-1316) and the final-partition refresh (R/RaceID.R:1044-1054) -------- */
+/* labels[N]: positive cluster numbers, 0 = cell not in `part`.  medoid_idx / cluster_ids sized >= #clusters. */
+int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_idx, int *cluster_ids, int *n_clusters);
+int rid_refresh(rid_dmat *dm, const int *medoid_idx, int k, int *labels);
+
+/* ---- W.k (R/RaceID_utils.R:39-53) for a given partition; used by tests and by callers of clusGapExt ---- */
+int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACEID_B200_H */

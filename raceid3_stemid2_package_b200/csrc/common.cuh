@@ -1,0 +1,74 @@
+// common.cuh — shared declarations for libraceid_b200.so (context, distance-matrix handle, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/raceid_b200.h"
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+// NaN sentinel inside the fixed-point matrix (zero-variance cells: cor() gives NA).
+#define RID_Q_NA 0xFFFFFFFFu
+
+void rid_set_error(const char *fmt, ...);
+
+#define RID_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            rid_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return RID_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define RID_TRY(call)                \
+    do {                             \
+        int rc__ = (call);           \
+        if (rc__ != RID_OK) return rc__; \
+    } while (0)
+
+// ---- NCCL, bound at run time (dlopen) so that single-GPU use needs no NCCL at all -------------------------
+struct NcclApi;
+
+struct rid_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    long long launches = 0;
+    void *comm = nullptr; // ncclComm_t
+    NcclApi *nccl = nullptr;
+};
+
+int rid_allreduce_u64(rid_ctx *ctx, u64 *buf, size_t count);
+int rid_allreduce_i32(rid_ctx *ctx, int *buf, size_t count);
+int rid_allreduce_f64(rid_ctx *ctx, double *buf, size_t count);
+
+struct PamWs; // pam.cu
+
+struct rid_dmat {
+    rid_ctx *ctx = nullptr;
+    int N = 0;
+    int row0 = 0, row1 = 0; // owned rows [row0,row1)
+    size_t ld = 0;          // pitch in elements, multiple of 128
+    u32 *D = nullptr;       // (row1-row0) x ld, fixed point: value = q * step
+    int bits = 28;          // q <= 2^bits  (28: correlation distances, 31: general)
+    double step = 0.0;      // value of one quantisation step
+    int has_na = 0;
+    std::vector<unsigned char> na_cell; // host copy: 1 if the cell's row/col is NA
+    PamWs *ws = nullptr;
+};
+
+static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// timing helpers (CUDA events on the ctx stream)
+int rid_time_begin(rid_ctx *ctx);
+int rid_time_end(rid_ctx *ctx);
+
+void rid_pam_ws_free(PamWs *ws);

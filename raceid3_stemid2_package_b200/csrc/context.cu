@@ -1,0 +1,183 @@
+// context.cu — contexts, error text, NCCL binding (run-time), timing.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void rid_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *rid_last_error(void) { return g_err; }
+extern "C" int rid_version(void) { return 100; }
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // If torch (or anything else) already mapped libnccl.so.2, RTLD_NOLOAD-style reuse happens through the soname.
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.handle = h;
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce) return nullptr;
+    return &api;
+}
+
+#define RID_NCCL(api, call)                                                                            \
+    do {                                                                                               \
+        ncclResult_t r__ = (call);                                                                     \
+        if (r__ != ncclSuccess) {                                                                      \
+            rid_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                           \
+                          (api)->GetErrorString ? (api)->GetErrorString(r__) : "nccl error");          \
+            return RID_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+extern "C" int rid_nccl_unique_id(void *uid128)
+{
+    NcclApi *api = nccl_api();
+    if (!api) {
+        rid_set_error("libnccl.so.2 could not be loaded: %s", dlerror());
+        return RID_ERR_CUDA;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    RID_NCCL(api, api->GetUniqueId(&id));
+    memcpy(uid128, &id, sizeof(id));
+    return RID_OK;
+}
+
+extern "C" int rid_ctx_create(int device, int rank, int world, const void *nccl_uid, rid_ctx **out)
+{
+    if (!out || world < 1 || rank < 0 || rank >= world) {
+        rid_set_error("rid_ctx_create: bad arguments (rank=%d world=%d)", rank, world);
+        return RID_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        rid_set_error("rid_ctx_create: no CUDA device is usable (%s); libraceid_b200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return RID_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        rid_set_error("rid_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+        return RID_ERR_ARG;
+    }
+    RID_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RID_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        rid_set_error("rid_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                      prop.major, prop.minor);
+        return RID_ERR_CUDA;
+    }
+    rid_ctx *ctx = new rid_ctx();
+    ctx->device = device;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->sm_count = prop.multiProcessorCount;
+    RID_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RID_CUDA(cudaEventCreate(&ctx->ev0));
+    RID_CUDA(cudaEventCreate(&ctx->ev1));
+    if (world > 1) {
+        if (!nccl_uid) {
+            rid_set_error("rid_ctx_create: world>1 needs the NCCL unique id");
+            delete ctx;
+            return RID_ERR_ARG;
+        }
+        NcclApi *api = nccl_api();
+        if (!api) {
+            rid_set_error("libnccl.so.2 could not be loaded");
+            delete ctx;
+            return RID_ERR_CUDA;
+        }
+        ncclUniqueId id;
+        memcpy(&id, nccl_uid, sizeof(id));
+        ncclComm_t comm;
+        RID_NCCL(api, api->CommInitRank(&comm, world, id, rank));
+        ctx->comm = comm;
+        ctx->nccl = api;
+    }
+    *out = ctx;
+    return RID_OK;
+}
+
+extern "C" int rid_ctx_destroy(rid_ctx *ctx)
+{
+    if (!ctx) return RID_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RID_OK;
+}
+
+extern "C" int rid_ctx_sync(rid_ctx *ctx)
+{
+    if (!ctx) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RID_OK;
+}
+
+extern "C" double rid_ctx_last_ms(const rid_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
+extern "C" long long rid_ctx_launches(const rid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rid_time_begin(rid_ctx *ctx)
+{
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return RID_OK;
+}
+
+int rid_time_end(rid_ctx *ctx)
+{
+    RID_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    RID_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    RID_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    return RID_OK;
+}
+
+static int allreduce(rid_ctx *ctx, void *buf, size_t count, ncclDataType_t dt)
+{
+    if (ctx->world == 1) return RID_OK;
+    RID_NCCL(ctx->nccl, ctx->nccl->AllReduce(buf, buf, count, dt, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    return RID_OK;
+}
+int rid_allreduce_u64(rid_ctx *ctx, u64 *buf, size_t count) { return allreduce(ctx, buf, count, ncclUint64); }
+int rid_allreduce_i32(rid_ctx *ctx, int *buf, size_t count) { return allreduce(ctx, buf, count, ncclInt32); }
+int rid_allreduce_f64(rid_ctx *ctx, double *buf, size_t count) { return allreduce(ctx, buf, count, ncclFloat64); }

@@ -1,0 +1,566 @@
+// dist.cu — the cell-by-cell distance matrix: replaces dist.gen (reference R/RaceID_utils.R:9-15), i.e.
+// 1 - stats::cor(x, method = pearson|spearman) / 1 - cor(log2(x)) / as.matrix(stats::dist(t(x))), as called from
+// compdist at R/RaceID.R:769 (algorithms: R's cov.c / distance.c, restated in oracle/oracle.c).
+//
+// Pipeline:  x (G x N, one column per cell)  --k_prep-->  Z (N x Gp, one unit-norm centred row per cell, FP64)
+//            --k_gram_dmma-->  r = Z Z^T on the FP64 tensor path (mma.sync m8n8k4 DMMA; tcgen05 has no FP64 kind)
+//            --fused epilogue-->  D = 1 - r (or sqrt(|xi|^2+|xj|^2-2 xi.xj)), clamped, exact-zero diagonal,
+//            quantised to 32-bit fixed point and written once into the row-block shard of the HBM-resident matrix.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                         \
+    do {                                                                  \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->launches++;                                                \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------------------
+// k_prep: one CTA per cell.  transform (identity | log2 | average-tie rank), two-pass mean, L2 normalisation.
+// ----------------------------------------------------------------------------------------------------------
+#define PREP_THREADS 256
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = l < (PREP_THREADS / 32) ? sh[l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (l == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// metric 0 pearson, 1 spearman, 2 logpearson, 3 euclidean.
+// Z row c: unit-norm centred values (correlation metrics) or the raw values (euclidean, with nrm2[c] = |x_c|^2).
+// Spearman: rank2 = 2*rank = 2*#less + #equal + 1 is an exact integer; the centred value 2*rank-(G+1) too.
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prep(const double *__restrict__ x, int G, int N, int Gp, int metric, double *__restrict__ Z,
+       unsigned char *__restrict__ zero_var, double *__restrict__ nrm2)
+{
+    extern __shared__ double sh_keys[]; // spearman only: G keys
+    __shared__ double sh_red[PREP_THREADS / 32];
+    const int c = blockIdx.x;
+    const double *col = x + (size_t)c * G;
+    double *zrow = Z + (size_t)c * Gp;
+
+    if (metric == 3) {
+        double s = 0.0;
+        for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+            double v = col[k];
+            zrow[k] = v;
+            s += v * v;
+        }
+        s = block_sum(s, sh_red);
+        if (threadIdx.x == 0) { nrm2[c] = s; zero_var[c] = 0; }
+        return;
+    }
+    if (metric == 1) {
+        for (int k = threadIdx.x; k < G; k += PREP_THREADS) sh_keys[k] = col[k];
+        __syncthreads();
+        double ss = 0.0;
+        for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+            const double v = sh_keys[k];
+            int less = 0, eq = 0;
+            for (int l = 0; l < G; ++l) {
+                const double u = sh_keys[l];
+                less += (u < v);
+                eq += (u == v);
+            }
+            double cv = (double)(2 * less + eq + 1 - (G + 1)); // 2*(rank - mean rank), exact
+            zrow[k] = cv;
+            ss += cv * cv; // exact: integers below 2^53
+        }
+        ss = block_sum(ss, sh_red);
+        const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+        for (int k = threadIdx.x; k < G; k += PREP_THREADS) zrow[k] *= inv; // same thread wrote it
+        if (threadIdx.x == 0) zero_var[c] = ss > 0.0 ? 0 : 1;
+        return;
+    }
+    // pearson / logpearson: two-pass mean like cov.c, then centred sum of squares
+    double s = 0.0;
+    for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+        double v = col[k];
+        if (metric == 2) v = log2(v);
+        s += v;
+    }
+    double mean = block_sum(s, sh_red) / (double)G;
+    s = 0.0;
+    for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+        double v = col[k];
+        if (metric == 2) v = log2(v);
+        s += v - mean;
+    }
+    mean += block_sum(s, sh_red) / (double)G;
+    double ss = 0.0;
+    for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+        double v = col[k];
+        if (metric == 2) v = log2(v);
+        v -= mean;
+        ss += v * v;
+    }
+    ss = block_sum(ss, sh_red);
+    const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+    for (int k = threadIdx.x; k < G; k += PREP_THREADS) {
+        double v = col[k];
+        if (metric == 2) v = log2(v);
+        zrow[k] = (v - mean) * inv;
+    }
+    if (threadIdx.x == 0) zero_var[c] = ss > 0.0 ? 0 : 1;
+}
+
+__global__ void k_max_f64(const double *__restrict__ x, int n, double *out)
+{
+    __shared__ double sh[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, x[i]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// k_gram_dmma: 128 x 128 tile of Z Z^T per CTA, K in slabs of 16, 3-stage cp.async pipeline, 8 warps (2 x 4),
+// each warp a 64 x 32 sub-tile = 8 x 4 DMMA m8n8k4 accumulators.  Shared-memory rows are padded to 20 doubles so
+// that the half-warp fragment loads (4 rows x 4 k) hit 16 distinct 8-byte bank pairs.
+// ----------------------------------------------------------------------------------------------------------
+#define GM_BM 128
+#define GM_BN 128
+#define GM_BK 16
+#define GM_PITCH 20
+#define GM_STAGES 3
+#define GM_THREADS 256
+#define GM_SMEM (GM_STAGES * 2 * GM_BM * GM_PITCH * 8)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct GramParams {
+    const double *Z;   // Np x Gp (rows beyond N are zero)
+    int Gp, N, row0, nloc;
+    u32 *D;
+    size_t ld;
+    const unsigned char *zero_var;
+    int euclid;
+    const double *nrm2; // euclid
+    const double *xraw; // euclid fallback: == Z
+    int G;
+    double inv_step;    // 1/step
+};
+
+__device__ __forceinline__ u32 quantise_corr(double r, double inv_step)
+{
+    // cor(): clamp to [-1,1]; dist.gen: 1 - r
+    r = fmin(1.0, fmax(-1.0, r));
+    return (u32)__double2ull_rn((1.0 - r) * inv_step);
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;                                   // [stage][128][20]
+    double *Bs = smem + GM_STAGES * GM_BM * GM_PITCH;    // [stage][128][20]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3; // 2 x 4 warps
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    const size_t a_row0 = (size_t)P.row0 + (size_t)bm * GM_BM; // global cell index of the tile's first row
+    const size_t b_row0 = (size_t)bn * GM_BN;
+    const int nslab = P.Gp / GM_BK;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // each stage: A 128 rows x 16 doubles = 1024 16-byte chunks; same for B; 256 threads -> 4 + 4 chunks
+    auto load_stage = [&](int stage, int slab) {
+        double *a = As + (size_t)stage * GM_BM * GM_PITCH;
+        double *b = Bs + (size_t)stage * GM_BN * GM_PITCH;
+        const int k0 = slab * GM_BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ch = tid + i * GM_THREADS; // 0..1023
+            int r = ch >> 3, c2 = (ch & 7) * 2;
+            cp_async16(a + r * GM_PITCH + c2, P.Z + (a_row0 + r) * P.Gp + k0 + c2);
+            cp_async16(b + r * GM_PITCH + c2, P.Z + (b_row0 + r) * P.Gp + k0 + c2);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < GM_STAGES - 1; ++s) {
+        if (s < nslab) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int slab = 0; slab < nslab; ++slab) {
+        cp_async_wait<GM_STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = slab + GM_STAGES - 1;
+            if (nxt < nslab) load_stage(nxt % GM_STAGES, nxt);
+            cp_async_commit();
+        }
+        const double *a = As + (size_t)(slab % GM_STAGES) * GM_BM * GM_PITCH + (wm * 64 + (lane >> 2)) * GM_PITCH + (lane & 3);
+        const double *b = Bs + (size_t)(slab % GM_STAGES) * GM_BN * GM_PITCH + (wn * 32 + (lane >> 2)) * GM_PITCH + (lane & 3);
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a[i * 8 * GM_PITCH + kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b[j * 8 * GM_PITCH + kk];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: c0 -> (row = lane/4, col = 2*(lane%4)), c1 -> col+1
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int lrow = bm * GM_BM + wm * 64 + i * 8 + (lane >> 2);
+        if (lrow >= P.nloc) continue;
+        const int grow = P.row0 + lrow;
+        const bool zr = P.zero_var[grow];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gcol = bn * GM_BN + wn * 32 + j * 8 + 2 * (lane & 3);
+            u32 q[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cc = gcol + e;
+                u32 v;
+                if (cc >= P.N) {
+                    v = 0u;
+                } else if (cc == grow) {
+                    v = zr ? RID_Q_NA : 0u; // diagonal: exactly 0 (1 - 1), NA for a zero-variance cell
+                } else if (!P.euclid) {
+                    v = (zr || P.zero_var[cc]) ? RID_Q_NA : quantise_corr(acc[i][j][e], P.inv_step);
+                } else {
+                    const double s = P.nrm2[grow] + P.nrm2[cc];
+                    double d2 = s - 2.0 * acc[i][j][e];
+                    if (d2 < 1e-9 * s) {
+                        // near-duplicate cells: the Gram form cancels; redo this pair in difference form (dist())
+                        const double *xa = P.xraw + (size_t)grow * P.Gp, *xb = P.xraw + (size_t)cc * P.Gp;
+                        d2 = 0.0;
+                        for (int k = 0; k < P.G; ++k) {
+                            double dv = xa[k] - xb[k];
+                            d2 += dv * dv;
+                        }
+                    }
+                    v = (u32)__double2ull_rn(sqrt(fmax(d2, 0.0)) * P.inv_step);
+                }
+                q[e] = v;
+            }
+            *reinterpret_cast<uint2 *>(P.D + (size_t)lrow * P.ld + gcol) = make_uint2(q[0], q[1]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// import / export
+// ----------------------------------------------------------------------------------------------------------
+// src: N x N column-major doubles (device).  Lower triangle is authoritative (as.dist): D(a,b) = src[max,min].
+__global__ void k_import(const double *__restrict__ src, int N, int row0, int nloc, u32 *__restrict__ D, size_t ld,
+                         double inv_step, int *has_na)
+{
+    size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lrow = blockIdx.y;
+    if (col >= ld || lrow >= nloc) return;
+    int r = row0 + lrow;
+    u32 v = 0u;
+    if (col < (size_t)N && (int)col != r) {
+        int hi = max(r, (int)col), lo = min(r, (int)col);
+        double d = src[(size_t)lo * N + hi];
+        if (isnan(d)) { v = RID_Q_NA; *has_na = 1; }
+        else v = (u32)__double2ull_rn(d * inv_step);
+    }
+    D[(size_t)lrow * ld + col] = v;
+}
+
+// out: m x n column-major doubles; rows ridx (global cells) owned by this rank are filled, others left 0
+__global__ void k_export(const u32 *__restrict__ D, size_t ld, int row0, int row1, const int *__restrict__ ridx, int m,
+                         const int *__restrict__ cidx, int n, double step, double *__restrict__ out)
+{
+    int a = blockIdx.x * blockDim.x + threadIdx.x; // row position (fast index of the column-major output)
+    int b = blockIdx.y;
+    if (a >= m || b >= n) return;
+    int r = ridx ? ridx[a] : a, c = cidx ? cidx[b] : b;
+    if (r < row0 || r >= row1) return;
+    u32 q = D[(size_t)(r - row0) * ld + c];
+    out[(size_t)b * m + a] = q == RID_Q_NA ? __longlong_as_double(0x7ff8000000000000LL) : (double)q * step;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------
+static void shard_rows(int N, int rank, int world, int *r0, int *r1)
+{
+    // contiguous row blocks; block size rounded to 128 rows so GEMM tiles do not straddle shards
+    long long per = ((long long)N + world - 1) / world;
+    per = (per + 127) / 128 * 128;
+    long long a = std::min<long long>((long long)rank * per, N), b = std::min<long long>(a + per, N);
+    *r0 = (int)a;
+    *r1 = (int)b;
+}
+
+static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
+{
+    rid_dmat *dm = new rid_dmat();
+    dm->ctx = ctx;
+    dm->N = N;
+    shard_rows(N, ctx->rank, ctx->world, &dm->row0, &dm->row1);
+    dm->ld = round_up((size_t)N, 128);
+    size_t nloc = (size_t)(dm->row1 - dm->row0);
+    cudaError_t e = cudaMalloc(&dm->D, std::max<size_t>(nloc, 1) * dm->ld * sizeof(u32));
+    if (e != cudaSuccess) {
+        rid_set_error("cannot allocate %.2f GB for the distance-matrix shard (%zu x %zu): %s",
+                      (double)nloc * dm->ld * 4 / 1e9, nloc, dm->ld, cudaGetErrorString(e));
+        delete dm;
+        return RID_ERR_NOMEM;
+    }
+    *out = dm;
+    return RID_OK;
+}
+
+extern "C" int rid_dmat_free(rid_dmat *dm)
+{
+    if (!dm) return RID_OK;
+    cudaSetDevice(dm->ctx->device);
+    cudaStreamSynchronize(dm->ctx->stream);
+    rid_pam_ws_free(dm->ws);
+    cudaFree(dm->D);
+    delete dm;
+    return RID_OK;
+}
+
+extern "C" int rid_dmat_info(const rid_dmat *dm, int *N, int *row0, int *row1, double *step, int *has_na)
+{
+    if (!dm) { rid_set_error("null distance matrix"); return RID_ERR_ARG; }
+    if (N) *N = dm->N;
+    if (row0) *row0 = dm->row0;
+    if (row1) *row1 = dm->row1;
+    if (step) *step = dm->step;
+    if (has_na) *has_na = dm->has_na;
+    return RID_OK;
+}
+
+extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric, int x_on_device, rid_dmat **out,
+                        int *n_zero_var)
+{
+    if (!ctx || !x || !out || G < 2 || N < 2) { rid_set_error("rid_dist: bad arguments"); return RID_ERR_ARG; }
+    if (metric < 0 || metric > 3) {
+        rid_set_error("metric has to be one of the following: spearman, pearson, logpearson, euclidean (kendall is not "
+                      "implemented on the GPU path)");
+        return RID_ERR_ARG;
+    }
+    RID_CUDA(cudaSetDevice(ctx->device));
+    if (metric == RID_SPEARMAN && (size_t)G * 8 > 200 * 1024) {
+        rid_set_error("spearman: G=%d features exceed the shared-memory rank kernel's limit (25600)", G);
+        return RID_ERR_UNSUPPORTED;
+    }
+    rid_dmat *dm = nullptr;
+    RID_TRY(dmat_alloc(ctx, N, &dm));
+    const int Gp = (int)round_up((size_t)G, GM_BK);
+    const size_t Np = round_up((size_t)N, 128);
+    double *xd = nullptr, *Z = nullptr, *nrm2 = nullptr, *dmax = nullptr;
+    unsigned char *zv = nullptr;
+    int rc = RID_OK;
+    auto fail = [&](int code) {
+        cudaFree(Z); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+        if (!x_on_device) cudaFree(xd);
+        rid_dmat_free(dm);
+        return code;
+    };
+#define DCHK(call)                                                                                         \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            rid_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+            return fail(RID_ERR_CUDA);                                                                     \
+        }                                                                                                  \
+    } while (0)
+    DCHK(cudaMalloc(&Z, Np * (size_t)Gp * sizeof(double)));
+    DCHK(cudaMalloc(&nrm2, Np * sizeof(double)));
+    DCHK(cudaMalloc(&zv, Np));
+    DCHK(cudaMalloc(&dmax, sizeof(double)));
+    if ((rc = rid_time_begin(ctx)) != RID_OK) return fail(rc);
+    if (x_on_device) {
+        xd = const_cast<double *>(x);
+    } else {
+        DCHK(cudaMalloc(&xd, (size_t)G * N * sizeof(double)));
+        DCHK(cudaMemcpyAsync(xd, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DCHK(cudaMemsetAsync(Z, 0, Np * (size_t)Gp * sizeof(double), ctx->stream));
+    DCHK(cudaMemsetAsync(nrm2, 0, Np * sizeof(double), ctx->stream));
+    DCHK(cudaMemsetAsync(zv, 0, Np, ctx->stream));
+    size_t prep_smem = metric == RID_SPEARMAN ? (size_t)G * sizeof(double) : 0;
+    if (prep_smem > 48 * 1024)
+        DCHK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
+    DCHK(cudaGetLastError());
+
+    if (metric == RID_EUCLIDEAN) {
+        // d(i,j) <= |x_i| + |x_j| <= 2 max|x|: pick the power-of-two step so that every q fits 31 bits
+        LAUNCH(ctx, k_max_f64, 1, 256, 0, nrm2, N, dmax);
+        double h = 0.0;
+        DCHK(cudaMemcpyAsync(&h, dmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DCHK(cudaStreamSynchronize(ctx->stream));
+        double bound = 2.0 * sqrt(h);
+        int e = 0;
+        frexp(bound > 0 ? bound : 1.0, &e); // bound < 2^e
+        dm->bits = 31;
+        dm->step = ldexp(1.0, e - 31);
+    } else {
+        dm->bits = 28;
+        dm->step = ldexp(1.0, -27); // D in [0,2] -> q in [0, 2^28]
+    }
+    {
+        GramParams P;
+        P.Z = Z; P.Gp = Gp; P.N = N; P.row0 = dm->row0; P.nloc = dm->row1 - dm->row0; P.D = dm->D; P.ld = dm->ld;
+        P.zero_var = zv; P.euclid = metric == RID_EUCLIDEAN; P.nrm2 = nrm2; P.xraw = Z; P.G = G;
+        P.inv_step = 1.0 / dm->step;
+        if (P.nloc > 0) {
+            DCHK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
+            dim3 grid((unsigned)(Np / GM_BN), (unsigned)((P.nloc + GM_BM - 1) / GM_BM));
+            LAUNCH(ctx, k_gram_dmma, grid, GM_THREADS, GM_SMEM, P);
+            DCHK(cudaGetLastError());
+        }
+    }
+    // zero-variance cells (cor(): NA + warning "the standard deviation is zero")
+    dm->na_cell.assign(N, 0);
+    DCHK(cudaMemcpyAsync(dm->na_cell.data(), zv, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = rid_time_end(ctx)) != RID_OK) return fail(rc);
+    int nz = 0;
+    for (int i = 0; i < N; ++i) nz += dm->na_cell[i];
+    dm->has_na = nz > 0;
+    if (n_zero_var) *n_zero_var = nz;
+    cudaFree(Z); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+    if (!x_on_device) cudaFree(xd);
+    *out = dm;
+    return RID_OK;
+#undef DCHK
+}
+
+extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat **out)
+{
+    if (!ctx || !D || !out || N < 2) { rid_set_error("rid_dmat_from_host: bad arguments"); return RID_ERR_ARG; }
+    RID_CUDA(cudaSetDevice(ctx->device));
+    // range of the lower triangle decides the fixed-point step
+    double mx = 0.0;
+    bool neg = false;
+    for (int c = 0; c < N; ++c)
+        for (int r = c + 1; r < N; ++r) {
+            double d = D[(size_t)c * N + r];
+            if (d < 0) neg = true;
+            if (d > mx) mx = d;
+        }
+    if (neg) { rid_set_error("negative dissimilarities are not supported"); return RID_ERR_ARG; }
+    rid_dmat *dm = nullptr;
+    RID_TRY(dmat_alloc(ctx, N, &dm));
+    if (mx <= 2.0) {
+        dm->bits = 28;
+        dm->step = ldexp(1.0, -27);
+    } else {
+        int e = 0;
+        frexp(mx, &e); // mx < 2^e (or == 2^(e-1))
+        dm->bits = 31;
+        dm->step = ldexp(1.0, e - 31);
+    }
+    double *src = nullptr;
+    int *flag = nullptr;
+    if (cudaMalloc(&src, (size_t)N * N * sizeof(double)) != cudaSuccess || cudaMalloc(&flag, sizeof(int)) != cudaSuccess) {
+        rid_set_error("cannot stage the %d x %d host matrix on the device", N, N);
+        cudaFree(src); rid_dmat_free(dm);
+        return RID_ERR_NOMEM;
+    }
+    int rc = rid_time_begin(ctx);
+    cudaMemcpyAsync(src, D, (size_t)N * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
+    int nloc = dm->row1 - dm->row0;
+    if (nloc > 0) {
+        dim3 grid((unsigned)((dm->ld + 255) / 256), (unsigned)nloc);
+        LAUNCH(ctx, k_import, grid, 256, 0, src, N, dm->row0, nloc, dm->D, dm->ld, 1.0 / dm->step, flag);
+    }
+    int h = 0;
+    cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == RID_OK) rc = rid_time_end(ctx);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(src); cudaFree(flag);
+    if (rc != RID_OK || e != cudaSuccess) {
+        if (e != cudaSuccess) rid_set_error("rid_dmat_from_host: %s", cudaGetErrorString(e));
+        rid_dmat_free(dm);
+        return RID_ERR_CUDA;
+    }
+    // NA anywhere: every rank must agree, so look at the host copy
+    for (int c = 0; c < N && !h; ++c)
+        for (int r = c + 1; r < N; ++r)
+            if (D[(size_t)c * N + r] != D[(size_t)c * N + r]) { h = 1; break; }
+    dm->has_na = h;
+    *out = dm;
+    return RID_OK;
+}
+
+extern "C" int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cidx, int n, double *out)
+{
+    if (!dm || !out || m < 1 || n < 1) { rid_set_error("rid_dmat_sub: bad arguments"); return RID_ERR_ARG; }
+    rid_ctx *ctx = dm->ctx;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    if ((!ridx && m > dm->N) || (!cidx && n > dm->N)) { rid_set_error("rid_dmat_sub: block exceeds the matrix"); return RID_ERR_ARG; }
+    for (int i = 0; ridx && i < m; ++i) if (ridx[i] < 0 || ridx[i] >= dm->N) { rid_set_error("row index out of range"); return RID_ERR_ARG; }
+    for (int i = 0; cidx && i < n; ++i) if (cidx[i] < 0 || cidx[i] >= dm->N) { rid_set_error("column index out of range"); return RID_ERR_ARG; }
+    double *d_out = nullptr;
+    int *d_r = nullptr, *d_c = nullptr;
+    // export in column panels to bound the staging buffer
+    const int panel = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / ((size_t)m * 8)));
+    RID_CUDA(cudaMalloc(&d_out, (size_t)m * panel * sizeof(double)));
+    if (ridx) { RID_CUDA(cudaMalloc(&d_r, (size_t)m * sizeof(int))); RID_CUDA(cudaMemcpy(d_r, ridx, (size_t)m * sizeof(int), cudaMemcpyHostToDevice)); }
+    if (cidx) { RID_CUDA(cudaMalloc(&d_c, (size_t)n * sizeof(int))); RID_CUDA(cudaMemcpy(d_c, cidx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice)); }
+    int rc = RID_OK;
+    for (int c0 = 0; c0 < n && rc == RID_OK; c0 += panel) {
+        int nc = std::min(panel, n - c0);
+        cudaMemsetAsync(d_out, 0, (size_t)m * nc * sizeof(double), ctx->stream);
+        dim3 grid((unsigned)((m + 127) / 128), (unsigned)nc);
+        // without a column list the panel's columns are c0.. ; shift through a pointer offset on the matrix
+        if (d_c)
+            LAUNCH(ctx, k_export, grid, 128, 0, dm->D, dm->ld, dm->row0, dm->row1, d_r, m, d_c + c0, nc, dm->step, d_out);
+        else
+            LAUNCH(ctx, k_export, grid, 128, 0, dm->D + c0, dm->ld, dm->row0, dm->row1, d_r, m, (const int *)nullptr, nc, dm->step, d_out);
+        rc = rid_allreduce_f64(ctx, d_out, (size_t)m * nc);
+        if (rc == RID_OK && cudaMemcpyAsync(out + (size_t)c0 * m, d_out, (size_t)m * nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
+        if (rc == RID_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
+    }
+    if (rc != RID_OK && rc != RID_ERR_CUDA) {}
+    else if (rc == RID_ERR_CUDA) rid_set_error("rid_dmat_sub: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_out); cudaFree(d_r); cudaFree(d_c);
+    return rc;
+}

@@ -1,0 +1,1132 @@
+// pam.cu — k-medoids (PAM BUILD / SWAP), within-cluster dispersion, medoid refresh, silhouette and the
+// clusterboot Jaccard table on a row-block-sharded, fixed-point distance matrix resident in HBM.
+//
+// Replaces cluster::pam as called at reference R/RaceID_utils.R:113,221 (algorithm: cluster/src/pam.c
+// bswap()+cstat()+dark(), restated in oracle/oracle.c), W.k R/RaceID_utils.R:39-53, fpc::clusterboot as called
+// at R/RaceID_utils.R:132-133, compmedoids R/RaceID.R:1298-1316 and the refresh R/RaceID.R:1044-1054.
+//
+// Formulation.  The matrix is symmetric, so the cost of opening candidate h while closing
+// medoid slot c,
+//        TD'(h,c) = sum_j min( D[j][h], c == nearest(j) ? dsecond(j) : dnearest(j) ),
+// is a column sum over point rows j with a per-row cap.  One streaming pass over the owned rows gives, for all
+// columns h at once,  SP[h] = sum_j min(D[j][h], dnearest_j)  and, with rows grouped by nearest medoid,
+// AQ[c][h] = sum_{j in c} (min(D[j][h], dsecond_j) - min(D[j][h], dnearest_j));  TD'(h,c) = SP[h] + AQ[c][h].
+// BUILD's gain is TD - SP[h].  Distances are 32-bit fixed point, all sums are exact 64-bit integers, so the
+// result does not depend on summation order, tiling or the number of GPUs, and ties are exact ties resolved
+// with the upstream rules (BUILD: largest index; SWAP: first (h, then medoid) in index order).
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------------------------------------
+struct PamState {
+    u64 td;       // total deviation at the last SWAP decision (fixed point)
+    u64 td_build; // total deviation after BUILD
+    u64 best_val;
+    int best_h, best_slot;
+    int done;
+    int nswaps;
+    int nmed;
+    unsigned int ticket;
+    int pad;
+};
+
+struct Cand {
+    u64 val;
+    int p, mp, slot;
+};
+
+struct PamWs {
+    int N = 0;
+    size_t ld = 0;
+    int nloc = 0; // owned rows
+    int kcap = 0;
+    // per subset position / per cell
+    int *subset = nullptr;         // [N] cell index by position
+    int *pos_of = nullptr;         // [N] position by cell or -1
+    unsigned char *is_med = nullptr; // [N] by cell
+    int *lab_pos = nullptr;        // [N] group by position
+    // owned subset rows
+    int *rows = nullptr, *rows_pos = nullptr;     // [nloc]
+    u32 *capP = nullptr, *capQ = nullptr;         // [nloc]
+    int *grp = nullptr;                           // [nloc]
+    int *s_row = nullptr, *s_grp = nullptr;       // sorted by group
+    u32 *s_capP = nullptr, *s_capQ = nullptr;
+    // per group
+    int *med = nullptr, *medpos = nullptr; // [kcap]
+    int *hist = nullptr;                   // [3*kcap]: hist, base, cursor
+    u64 *grp_sum = nullptr;                // [kcap] T_c
+    int *grp_cnt = nullptr;                // [kcap]
+    u64 *grp_min = nullptr;                // [kcap]
+    int *grp_arg = nullptr;                // [kcap]
+    // accumulators: hdr[4] | SP[ld] | AQ[kcap][ld]
+    u64 *acc = nullptr;
+    Cand *blockbest = nullptr; // [maxblocks]
+    int maxblocks = 0;
+    double *sil = nullptr; // [N]
+    double *dscratch = nullptr; // [8]
+    PamState *state = nullptr;
+    // host mirrors for the current subset
+    int m = 0, nls = 0;
+    std::vector<int> h_subset, h_rows, h_rows_pos, h_pos_of;
+};
+
+static void ws_free_groups(PamWs *w)
+{
+    cudaFree(w->med); cudaFree(w->medpos); cudaFree(w->hist); cudaFree(w->grp_sum); cudaFree(w->grp_cnt);
+    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc);
+    w->med = w->medpos = w->hist = w->grp_cnt = w->grp_arg = nullptr;
+    w->grp_sum = w->grp_min = w->acc = nullptr;
+}
+
+void rid_pam_ws_free(PamWs *w)
+{
+    if (!w) return;
+    cudaFree(w->subset); cudaFree(w->pos_of); cudaFree(w->is_med); cudaFree(w->lab_pos);
+    cudaFree(w->rows); cudaFree(w->rows_pos); cudaFree(w->capP); cudaFree(w->capQ); cudaFree(w->grp);
+    cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
+    cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state);
+    ws_free_groups(w);
+    delete w;
+}
+
+static int ws_get(rid_dmat *dm, int k, PamWs **out)
+{
+    PamWs *w = dm->ws;
+    RID_CUDA(cudaSetDevice(dm->ctx->device));
+    if (!w) {
+        w = new PamWs();
+        dm->ws = w;
+        w->N = dm->N;
+        w->ld = dm->ld;
+        w->nloc = dm->row1 - dm->row0;
+        size_t N = (size_t)dm->N, nl = (size_t)std::max(w->nloc, 1);
+        RID_CUDA(cudaMalloc(&w->subset, N * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->pos_of, N * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->is_med, N));
+        RID_CUDA(cudaMalloc(&w->lab_pos, N * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->rows, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->rows_pos, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->capP, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->capQ, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->grp, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->s_row, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->s_grp, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->s_capP, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->s_capQ, nl * sizeof(u32)));
+        w->maxblocks = (int)((N + 255) / 256);
+        RID_CUDA(cudaMalloc(&w->blockbest, (size_t)w->maxblocks * sizeof(Cand)));
+        RID_CUDA(cudaMalloc(&w->sil, N * sizeof(double)));
+        RID_CUDA(cudaMalloc(&w->dscratch, 8 * sizeof(double)));
+        RID_CUDA(cudaMalloc(&w->state, sizeof(PamState)));
+    }
+    if (k > w->kcap) {
+        ws_free_groups(w);
+        int kc = std::max(k, 32);
+        RID_CUDA(cudaMalloc(&w->med, kc * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->medpos, kc * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->hist, 3 * (size_t)kc * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->grp_sum, kc * sizeof(u64)));
+        RID_CUDA(cudaMalloc(&w->grp_cnt, kc * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->grp_min, kc * sizeof(u64)));
+        RID_CUDA(cudaMalloc(&w->grp_arg, kc * sizeof(int)));
+        cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * w->ld) * sizeof(u64));
+        if (e != cudaSuccess) {
+            rid_set_error("out of device memory for %d group accumulators", kc);
+            return RID_ERR_NOMEM;
+        }
+        w->kcap = kc;
+    }
+    *out = w;
+    return RID_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// kernels
+// ----------------------------------------------------------------------------------------------------------
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                         \
+    do {                                                                  \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+        (ctx)->launches++;                                                \
+    } while (0)
+
+__global__ void k_fill_u32(u32 *p, u32 v, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_zero(u64 *acc, size_t n_acc, int *hist, int n_hist, const PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = i; t < n_acc; t += stride) acc[t] = 0ull;
+    if (i < (size_t)n_hist) hist[i] = 0;
+}
+
+__global__ void k_state_init(PamState *st)
+{
+    st->td = 0; st->td_build = 0; st->best_val = 0; st->best_h = -1; st->best_slot = -1;
+    st->done = 0; st->nswaps = 0; st->nmed = 0; st->ticket = 0u;
+}
+
+// medoids := given cells (slots 0..k-1); used to start SWAP(k) from the shared BUILD prefix
+__global__ void k_set_medoids(const int *cells, int k, int *med, int *medpos, const int *pos_of,
+                              unsigned char *is_med, PamState *st)
+{
+    int c = threadIdx.x;
+    if (c < k) {
+        int h = cells[c];
+        med[c] = h;
+        medpos[c] = pos_of[h];
+        is_med[h] = 1;
+    }
+    if (c == 0) { st->nmed = k; st->done = 0; st->nswaps = 0; st->ticket = 0u; }
+}
+
+// The streaming pass.  Thread = 4 consecutive columns (one 128-bit load per row), CTA = 512 columns x a chunk
+// of the (group-sorted) row list.  32-bit partial sums are promoted to 64 bits every FLUSH rows
+// (q <= 2^28: 8 rows; q <= 2^31: 2 rows), and pushed to SP / AQ with 64-bit integer reductions.
+#define SCAN_THREADS 128
+#define SCAN_MAXROWS 512
+
+__device__ __forceinline__ uint4 ld_stream(const u32 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void red_add_u64(u64 *p, u64 v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool WITH_Q, int FLUSH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ s_row,
+       const u32 *__restrict__ s_capP, const u32 *__restrict__ s_capQ, const int *__restrict__ s_grp, int nrows,
+       int rows_per_cta, u64 *__restrict__ SP, u64 *__restrict__ AQ, const PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    __shared__ int sh_row[SCAN_MAXROWS];
+    __shared__ u32 sh_cp[SCAN_MAXROWS];
+    __shared__ u32 sh_cq[SCAN_MAXROWS];
+    __shared__ int sh_g[SCAN_MAXROWS];
+
+    const int r_begin = blockIdx.y * rows_per_cta;
+    const int nr = min(nrows - r_begin, rows_per_cta);
+    if (nr <= 0) return;
+    const int nr8 = (nr + 7) & ~7;
+    for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
+        bool ok = i < nr;
+        int src = r_begin + (ok ? i : nr - 1);
+        sh_row[i] = ok ? s_row[src] - row0 : -1;
+        sh_cp[i] = ok ? s_capP[src] : 0u;
+        if (WITH_Q) {
+            sh_cq[i] = ok ? s_capQ[src] : 0u;
+            sh_g[i] = s_grp[src];
+        }
+    }
+    __syncthreads();
+    const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    if (col >= ld) return;
+    const u32 *base = D + col;
+
+    u64 accP[4] = {0, 0, 0, 0}, accQ[4] = {0, 0, 0, 0};
+    u32 p32[4] = {0, 0, 0, 0}, q32[4] = {0, 0, 0, 0};
+    int cur_g = WITH_Q ? sh_g[0] : 0;
+
+    for (int r = 0; r < nr8; r += 8) {
+        uint4 d[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int lr = sh_row[r + u];
+            d[u] = lr >= 0 ? ld_stream(base + (size_t)lr * ld) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const u32 cp = sh_cp[r + u];
+            if (WITH_Q) {
+                const int g = sh_g[r + u];
+                if (g != cur_g) { // uniform across the CTA
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        accP[c] += p32[c]; p32[c] = 0;
+                        accQ[c] += q32[c]; q32[c] = 0;
+                        red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
+                        accQ[c] = 0;
+                    }
+                    cur_g = g;
+                }
+                const u32 cq = sh_cq[r + u];
+                u32 p, q;
+                p = min(d[u].x, cp); q = min(d[u].x, cq); p32[0] += p; q32[0] += q - p;
+                p = min(d[u].y, cp); q = min(d[u].y, cq); p32[1] += p; q32[1] += q - p;
+                p = min(d[u].z, cp); q = min(d[u].z, cq); p32[2] += p; q32[2] += q - p;
+                p = min(d[u].w, cp); q = min(d[u].w, cq); p32[3] += p; q32[3] += q - p;
+            } else {
+                p32[0] += min(d[u].x, cp);
+                p32[1] += min(d[u].y, cp);
+                p32[2] += min(d[u].z, cp);
+                p32[3] += min(d[u].w, cp);
+            }
+            if ((u % FLUSH) == FLUSH - 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    accP[c] += p32[c]; p32[c] = 0;
+                    if (WITH_Q) { accQ[c] += q32[c]; q32[c] = 0; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        red_add_u64(SP + col + c, accP[c]);
+        if (WITH_Q) red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
+    }
+}
+
+// nearest / second-nearest medoid of every owned subset row (cstat + the dysma/dysmb refresh of bswap):
+// strict '<' with medoids visited in index (position) order => the lowest-position medoid wins ties.
+__global__ void k_assign(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ rows, int nls,
+                         const int *__restrict__ med, const int *__restrict__ medpos, int k, u32 *capP, u32 *capQ,
+                         int *grp, int *hist, u64 *td, const PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    extern __shared__ int sh[];
+    int *sh_med = sh, *sh_mp = sh + k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) { sh_med[i] = med[i]; sh_mp[i] = medpos[i]; }
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 mine = 0;
+    if (t < nls) {
+        const u32 *row = D + (size_t)(rows[t] - row0) * ld;
+        u32 d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu;
+        int g = -1, gp = INT_MAX;
+        for (int c = 0; c < k; ++c) {
+            u32 d = row[sh_med[c]];
+            int mp = sh_mp[c];
+            if (d < d1 || (d == d1 && mp < gp)) {
+                d2 = d1; d1 = d; g = c; gp = mp;
+            } else if (d < d2) {
+                d2 = d;
+            }
+        }
+        capP[t] = d1;
+        capQ[t] = d2;
+        grp[t] = g;
+        atomicAdd(&hist[g], 1);
+        mine = d1;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(td, mine);
+}
+
+// groups given per position (W.k, compmedoids, silhouette): plain grouped column sums (capP=0, capQ=inf)
+__global__ void k_groups_from_labels(const int *__restrict__ rows_pos, int nls, const int *__restrict__ lab_pos,
+                                     u32 *capP, u32 *capQ, int *grp, int *hist)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) {
+        int g = lab_pos[rows_pos[t]];
+        capP[t] = 0u;
+        capQ[t] = 0xFFFFFFFFu;
+        grp[t] = g;
+        atomicAdd(&hist[g], 1);
+    }
+}
+
+__global__ void k_prefix(int *hist, int k, const PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < k; ++c) {
+            hist[k + c] = run;   // base
+            hist[2 * k + c] = 0; // cursor
+            run += hist[c];
+        }
+    }
+}
+
+__global__ void k_scatter(const int *__restrict__ rows, const u32 *__restrict__ capP, const u32 *__restrict__ capQ,
+                          const int *__restrict__ grp, int nls, int *hist, int k, int *s_row, u32 *s_capP,
+                          u32 *s_capQ, int *s_grp, const PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) {
+        int g = grp[t];
+        int dst = hist[k + g] + atomicAdd(&hist[2 * k + g], 1);
+        s_row[dst] = rows[t];
+        s_capP[dst] = capP[t];
+        s_capQ[dst] = capQ[t];
+        s_grp[dst] = g;
+    }
+}
+
+__device__ __forceinline__ bool cand_better_swap(const Cand &a, const Cand &b)
+{
+    if (a.val != b.val) return a.val < b.val;
+    if (a.p != b.p) return a.p < b.p;
+    return a.mp < b.mp;
+}
+__device__ __forceinline__ bool cand_better_build(const Cand &a, const Cand &b)
+{
+    if (a.val != b.val) return a.val < b.val;
+    return a.p > b.p; // upstream BUILD: `if (ammax <= beter[i])` => the largest index wins ties
+}
+
+template <bool BUILD>
+__device__ __forceinline__ Cand cand_reduce_block(Cand c, Cand *sh)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand b;
+        b.val = __shfl_down_sync(0xffffffffu, c.val, o);
+        b.p = __shfl_down_sync(0xffffffffu, c.p, o);
+        b.mp = __shfl_down_sync(0xffffffffu, c.mp, o);
+        b.slot = __shfl_down_sync(0xffffffffu, c.slot, o);
+        if (BUILD ? cand_better_build(b, c) : cand_better_swap(b, c)) c = b;
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (l == 0) sh[w] = c;
+    __syncthreads();
+    if (w == 0) {
+        Cand e;
+        e.val = ~0ull; e.p = BUILD ? -1 : INT_MAX; e.mp = INT_MAX; e.slot = -1;
+        c = l < nw ? sh[l] : e;
+        for (int o = 16; o > 0; o >>= 1) {
+            Cand b;
+            b.val = __shfl_down_sync(0xffffffffu, c.val, o);
+            b.p = __shfl_down_sync(0xffffffffu, c.p, o);
+            b.mp = __shfl_down_sync(0xffffffffu, c.mp, o);
+            b.slot = __shfl_down_sync(0xffffffffu, c.slot, o);
+            if (BUILD ? cand_better_build(b, c) : cand_better_swap(b, c)) c = b;
+        }
+    }
+    __syncthreads();
+    return c; // valid in thread 0
+}
+
+// Candidate selection.  SWAP: argmin over (h non-medoid, medoid slot c) of SP[h]+AQ[c][h], first (h, medoid) in
+// position order on ties; accepted iff it lowers TD (upstream: dzsky < -16*DBL_EPSILON*|sky|, which on exact
+// fixed-point sums is dz < 0).  BUILD: argmin SP[h], largest position on ties.
+template <bool BUILD>
+__global__ void __launch_bounds__(256)
+k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
+         const u64 *__restrict__ acc, size_t ld, int k, int *med, int *medpos, unsigned char *is_med,
+         Cand *blockbest, PamState *st, int check_done)
+{
+    if (check_done && st->done) return;
+    __shared__ Cand sh[32];
+    __shared__ int sh_mp[1024];
+    __shared__ bool is_last;
+    const u64 *SP = acc + 4;
+    const u64 *AQ = SP + ld;
+    if (!BUILD)
+        for (int i = threadIdx.x; i < k && i < 1024; i += blockDim.x) sh_mp[i] = medpos[i];
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    Cand best;
+    best.val = ~0ull; best.p = BUILD ? -1 : INT_MAX; best.mp = INT_MAX; best.slot = -1;
+    if (p < m) {
+        int h = subset[p];
+        if (!is_med_c[h]) {
+            u64 sp = SP[h];
+            if (BUILD) {
+                best.val = sp; best.p = p; best.mp = 0; best.slot = 0;
+            } else {
+                for (int c = 0; c < k; ++c) {
+                    Cand x;
+                    x.val = sp + AQ[(size_t)c * ld + h];
+                    x.p = p;
+                    x.mp = c < 1024 ? sh_mp[c] : medpos[c];
+                    x.slot = c;
+                    if (cand_better_swap(x, best)) best = x;
+                }
+            }
+        }
+    }
+    best = cand_reduce_block<BUILD>(best, sh);
+    if (threadIdx.x == 0) {
+        blockbest[blockIdx.x] = best;
+        __threadfence();
+        unsigned int t = atomicAdd(&st->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Cand c;
+    c.val = ~0ull; c.p = BUILD ? -1 : INT_MAX; c.mp = INT_MAX; c.slot = -1;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        Cand b = blockbest[i];
+        if (BUILD ? cand_better_build(b, c) : cand_better_swap(b, c)) c = b;
+    }
+    c = cand_reduce_block<BUILD>(c, sh);
+    if (threadIdx.x == 0) {
+        st->ticket = 0u;
+        u64 td = acc[0];
+        if (BUILD) {
+            int h = subset[c.p];
+            int s = st->nmed;
+            med[s] = h;
+            medpos[s] = c.p;
+            is_med[h] = 1;
+            st->nmed = s + 1;
+            st->best_h = h; st->best_slot = s; st->best_val = c.val;
+        } else {
+            st->td = td;
+            st->best_val = c.val;
+            if (c.slot >= 0 && c.val < td) {
+                int h = subset[c.p];
+                is_med[med[c.slot]] = 0;
+                is_med[h] = 1;
+                med[c.slot] = h;
+                medpos[c.slot] = c.p;
+                st->best_h = h; st->best_slot = c.slot;
+                st->nswaps += 1;
+            } else {
+                st->done = 1;
+            }
+        }
+    }
+}
+
+// after BUILD picked medoid `best_h`: dnearest_j = min(dnearest_j, D[j][best_h])
+__global__ void k_build_update(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ rows,
+                               int nls, u32 *capP, const PamState *st)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) {
+        u32 d = D[(size_t)(rows[t] - row0) * ld + st->best_h];
+        if (d < capP[t]) capP[t] = d;
+    }
+}
+
+__global__ void k_capture_td_build(PamState *st, const u64 *acc) { st->td_build = acc[0]; }
+
+__global__ void k_labels_to_pos(const int *__restrict__ rows_pos, const int *__restrict__ grp, int nls, int *lab_pos)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) lab_pos[rows_pos[t]] = grp[t];
+}
+
+// T_c = sum_{h in c} S_h with S_h = AQ[c][h]; n_c
+__global__ void k_wdisp(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
+                        const u64 *__restrict__ AQ, size_t ld, u64 *grp_sum, int *grp_cnt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        int c = lab_pos[p];
+        atomicAdd(&grp_sum[c], AQ[(size_t)c * ld + subset[p]]);
+        atomicAdd(&grp_cnt[c], 1);
+    }
+}
+
+// compmedoids: first argmin of S_h within each cluster (two passes of integer atomicMin)
+__global__ void k_medoid_min(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
+                             const u64 *__restrict__ AQ, size_t ld, u64 *grp_min, int *grp_arg, int pass)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        int c = lab_pos[p];
+        u64 s = AQ[(size_t)c * ld + subset[p]];
+        if (pass == 0) atomicMin(&grp_min[c], s);
+        else if (s == grp_min[c]) atomicMin(&grp_arg[c], p);
+    }
+}
+
+// silhouette width of every subset position (pam.c dark())
+__global__ void k_silhouette(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m, int k,
+                             const u64 *__restrict__ AQ, size_t ld, const int *__restrict__ grp_cnt, double *sil)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        int h = subset[p], cj = lab_pos[p];
+        double sw = 0.0;
+        int nj = grp_cnt[cj];
+        if (nj > 1) {
+            double a = (double)AQ[(size_t)cj * ld + h] / (double)(nj - 1);
+            double b = INFINITY;
+            for (int c = 0; c < k; ++c)
+                if (c != cj && grp_cnt[c] > 0) {
+                    double v = (double)AQ[(size_t)c * ld + h] / (double)grp_cnt[c];
+                    if (v < b) b = v;
+                }
+            double mx = a > b ? a : b;
+            sw = mx > 0.0 ? (b - a) / mx : 0.0;
+        }
+        sil[p] = sw;
+    }
+}
+
+// deterministic sum of n doubles (fixed order) -> out[0]
+__global__ void k_sum_f64(const double *__restrict__ x, int n, double *out)
+{
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// the final-partition refresh (RaceID.R:1049-1052): nearest of the given medoid columns, first minimum
+__global__ void k_refresh(const u32 *__restrict__ D, size_t ld, int row0, int nloc, const int *__restrict__ med,
+                          int k, int *labels)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nloc) {
+        const u32 *row = D + (size_t)t * ld;
+        u32 best = row[med[0]];
+        int g = 0;
+        for (int c = 1; c < k; ++c) {
+            u32 d = row[med[c]];
+            if (d < best) { best = d; g = c; }
+        }
+        labels[row0 + t] = g + 1;
+    }
+}
+
+// clusterboot: k x k contingency table of (c1 label of the resampled cell, bootstrap label)
+__global__ void k_contingency(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
+                              const int *__restrict__ part_slot /* [N] c1 group by cell */, int k, int *tab)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) atomicAdd(&tab[part_slot[subset[p]] * k + lab_pos[p]], 1);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host orchestration
+// ----------------------------------------------------------------------------------------------------------
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+static int pam_check_na(rid_dmat *dm, const int *subset, int m)
+{
+    if (!dm->has_na) return RID_OK;
+    if (dm->na_cell.empty()) {
+        rid_set_error("No clustering performed, NAs in the computed dissimilarity matrix.");
+        return RID_ERR_NA;
+    }
+    for (int p = 0; p < m; ++p) {
+        int h = subset ? subset[p] : p;
+        if (dm->na_cell[h]) {
+            rid_set_error("No clustering performed, NAs in the computed dissimilarity matrix.");
+            return RID_ERR_NA;
+        }
+    }
+    return RID_OK;
+}
+
+// install the subset (positions -> cells) and the list of owned subset rows
+static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
+{
+    rid_ctx *ctx = dm->ctx;
+    int N = dm->N;
+    if (m < 1 || m > N) {
+        rid_set_error("subset size %d out of range", m);
+        return RID_ERR_ARG;
+    }
+    w->h_subset.resize(m);
+    w->h_pos_of.assign(N, -1);
+    for (int p = 0; p < m; ++p) {
+        int h = subset ? subset[p] : p;
+        if (h < 0 || h >= N) {
+            rid_set_error("subset index %d out of range", h);
+            return RID_ERR_ARG;
+        }
+        if (w->h_pos_of[h] != -1) {
+            rid_set_error("subset holds cell %d twice", h);
+            return RID_ERR_ARG;
+        }
+        w->h_subset[p] = h;
+        w->h_pos_of[h] = p;
+    }
+    w->h_rows.clear();
+    w->h_rows_pos.clear();
+    // owned rows in cell order (any order works: all sums are exact integers)
+    for (int h = dm->row0; h < dm->row1; ++h)
+        if (w->h_pos_of[h] >= 0) {
+            w->h_rows.push_back(h);
+            w->h_rows_pos.push_back(w->h_pos_of[h]);
+        }
+    w->m = m;
+    w->nls = (int)w->h_rows.size();
+    RID_CUDA(cudaMemcpyAsync(w->subset, w->h_subset.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->pos_of, w->h_pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (w->nls) {
+        RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // the host vectors are reused by the next call; make sure the copies are done
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RID_OK;
+}
+
+template <bool WITH_Q>
+static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP, const u32 *capQ, const int *grp,
+                       int check_done)
+{
+    rid_ctx *ctx = dm->ctx;
+    if (w->nls == 0) return RID_OK;
+    int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
+    int want_ctas = ctx->sm_count * 16;
+    int chunks_needed = std::max(1, (want_ctas + strips - 1) / strips);
+    int rpc = (w->nls + chunks_needed - 1) / chunks_needed;
+    rpc = (rpc + 7) & ~7;
+    rpc = std::min(std::max(rpc, 8), SCAN_MAXROWS);
+    int chunks = (w->nls + rpc - 1) / rpc;
+    dim3 grid(strips, chunks);
+    u64 *SP = w->acc + 4, *AQ = SP + w->ld;
+    auto scan8 = k_scan<WITH_Q, 8>;
+    auto scan2 = k_scan<WITH_Q, 2>;
+    if (dm->bits <= 28)
+        LAUNCH(ctx, scan8, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, w->nls, rpc, SP, AQ,
+               w->state, check_done);
+    else
+        LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, w->nls, rpc, SP, AQ,
+               w->state, check_done);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+static int zero_acc(rid_dmat *dm, PamWs *w, int ngroups, int check_done)
+{
+    size_t n = 4 + (size_t)(1 + ngroups) * w->ld;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)dm->ctx->sm_count * 8);
+    blocks = std::max(blocks, nblk(3 * w->kcap, 256));
+    LAUNCH(dm->ctx, k_zero, blocks, 256, 0, w->acc, n, w->hist, 3 * w->kcap, w->state, check_done);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+// BUILD: add medoids until `k` are chosen (continues from state.nmed; caps must be current)
+static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
+{
+    rid_ctx *ctx = dm->ctx;
+    for (int s = k_from; s < k_to; ++s) {
+        RID_TRY(zero_acc(dm, w, 0, 0));
+        RID_TRY((launch_scan<false>(dm, w, w->rows, w->capP, nullptr, nullptr, 0)));
+        RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
+        auto sel_build = k_select<true>;
+        LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med,
+               w->medpos, w->is_med, w->blockbest, w->state, 0);
+        if (w->nls)
+            LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, dm->D, dm->ld, dm->row0, w->rows, w->nls, w->capP,
+                   w->state);
+        RID_CUDA(cudaGetLastError());
+    }
+    return RID_OK;
+}
+
+static int pam_begin(rid_dmat *dm, PamWs *w)
+{
+    rid_ctx *ctx = dm->ctx;
+    LAUNCH(ctx, k_state_init, 1, 1, 0, w->state);
+    RID_CUDA(cudaMemsetAsync(w->is_med, 0, (size_t)dm->N, ctx->stream));
+    if (w->nls) LAUNCH(ctx, k_fill_u32, nblk(w->nls, 256), 256, 0, w->capP, 0xFFFFFFFFu, w->nls);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+// one assign pass: caps, groups, TD -> acc[0] (all-reduced).  ngroups = k accumulators are zeroed too.
+static int pam_assign(rid_dmat *dm, PamWs *w, int k, int check_done)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(zero_acc(dm, w, k, check_done));
+    if (w->nls)
+        LAUNCH(ctx, k_assign, nblk(w->nls, 128), 128, 2 * k * sizeof(int), dm->D, dm->ld, dm->row0, w->rows, w->nls,
+               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, w->acc, w->state, check_done);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+static int sort_rows_by_group(rid_dmat *dm, PamWs *w, int k, int check_done)
+{
+    rid_ctx *ctx = dm->ctx;
+    LAUNCH(ctx, k_prefix, 1, 32, 0, w->hist, w->kcap, w->state, check_done);
+    if (w->nls)
+        LAUNCH(ctx, k_scatter, nblk(w->nls, 256), 256, 0, w->rows, w->capP, w->capQ, w->grp, w->nls, w->hist, w->kcap,
+               w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->state, check_done);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+// SWAP until no improving swap is left.  Medoids (k of them) must be installed in w->med / is_med.
+// On return: state.td_build = TD before the first swap, state.td = final TD, w->grp / capP / capQ describe the
+// final medoids for the owned rows.
+static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
+{
+    rid_ctx *ctx = dm->ctx;
+    // how many iterations to enqueue between host checks: per-iteration work is ~ nls*ld*4 bytes
+    double bytes = (double)w->nls * (double)w->ld * 4.0;
+    int batch = bytes > 2.0e9 ? 1 : (bytes > 2.0e8 ? 2 : 8);
+    bool first = true;
+    for (;;) {
+        for (int b = 0; b < batch; ++b) {
+            int chk = first ? 0 : 1;
+            RID_TRY(pam_assign(dm, w, k, chk));
+            if (first) {
+                // objective["build"]: TD of the BUILD medoids
+                if (ctx->world > 1) RID_TRY(rid_allreduce_u64(ctx, w->acc, 4));
+                LAUNCH(ctx, k_capture_td_build, 1, 1, 0, w->state, w->acc);
+                if (ctx->world > 1) {
+                    // acc[0] now holds the global TD on every rank; the big all-reduce below would add it world
+                    // times, so keep only this rank's share: rank 0 keeps it, the others restart from zero.
+                    if (ctx->rank != 0) RID_CUDA(cudaMemsetAsync(w->acc, 0, sizeof(u64), ctx->stream));
+                }
+                first = false;
+            }
+            if (k < 2) break;
+            {
+                RID_TRY(sort_rows_by_group(dm, w, k, chk));
+                RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, chk)));
+                RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
+                auto sel_swap = k_select<false>;
+                LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
+                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk);
+                RID_CUDA(cudaGetLastError());
+            }
+        }
+        RID_CUDA(cudaMemcpyAsync(h_state, w->state, sizeof(PamState), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (k < 2) {
+            h_state->td = h_state->td_build;
+            break;
+        }
+        if (h_state->done) break;
+    }
+    return RID_OK;
+}
+
+// labels by position for the current medoids -> w->lab_pos (device, all ranks) and host copy
+static int pam_collect_labels(rid_dmat *dm, PamWs *w, std::vector<int> &h_lab)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_CUDA(cudaMemsetAsync(w->lab_pos, 0, (size_t)w->m * sizeof(int), ctx->stream));
+    if (w->nls) LAUNCH(ctx, k_labels_to_pos, nblk(w->nls, 256), 256, 0, w->rows_pos, w->grp, w->nls, w->lab_pos);
+    RID_CUDA(cudaGetLastError());
+    RID_TRY(rid_allreduce_i32(ctx, w->lab_pos, (size_t)w->m));
+    h_lab.resize(w->m);
+    RID_CUDA(cudaMemcpyAsync(h_lab.data(), w->lab_pos, (size_t)w->m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RID_OK;
+}
+
+// grouped column sums for the groups in w->lab_pos (0..k-1 by position): AQ[c][h] = sum_{j in c} D[j][h]
+static int grouped_colsums(rid_dmat *dm, PamWs *w, int k)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(zero_acc(dm, w, k, 0));
+    if (w->nls)
+        LAUNCH(ctx, k_groups_from_labels, nblk(w->nls, 256), 256, 0, w->rows_pos, w->nls, w->lab_pos, w->capP, w->capQ,
+               w->grp, w->hist);
+    RID_TRY(sort_rows_by_group(dm, w, k, 0));
+    RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, 0)));
+    RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
+    return RID_OK;
+}
+
+// W.k from w->lab_pos
+static int within_disp(rid_dmat *dm, PamWs *w, int k, double *W, std::vector<int> *counts)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(grouped_colsums(dm, w, k));
+    RID_CUDA(cudaMemsetAsync(w->grp_sum, 0, (size_t)k * sizeof(u64), ctx->stream));
+    RID_CUDA(cudaMemsetAsync(w->grp_cnt, 0, (size_t)k * sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_wdisp, nblk(w->m, 256), 256, 0, w->subset, w->lab_pos, w->m, w->acc + 4 + w->ld, w->ld, w->grp_sum,
+           w->grp_cnt);
+    RID_CUDA(cudaGetLastError());
+    std::vector<u64> hs(k);
+    std::vector<int> hc(k);
+    RID_CUDA(cudaMemcpyAsync(hs.data(), w->grp_sum, (size_t)k * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(hc.data(), w->grp_cnt, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    long double tot = 0.0L;
+    for (int c = 0; c < k; ++c)
+        if (hc[c] > 0) tot += (long double)((double)((long double)hs[c] * (long double)dm->step / (long double)hc[c]));
+    *W = 0.5 * (double)tot;
+    if (counts) *counts = hc;
+    return RID_OK;
+}
+
+// cstat numbering: clusters numbered by first appearance scanning positions 0..m-1
+static void number_clusters(const std::vector<int> &slot_by_pos, int k, const std::vector<int> &medpos_by_slot,
+                            int *labels, int *medoids)
+{
+    std::vector<int> num(k, 0);
+    int next = 0;
+    for (size_t p = 0; p < slot_by_pos.size(); ++p) {
+        int s = slot_by_pos[p];
+        if (!num[s]) {
+            num[s] = ++next;
+            if (medoids) medoids[next - 1] = medpos_by_slot[s];
+        }
+        if (labels) labels[p] = num[s];
+    }
+}
+
+static int pam_run(rid_dmat *dm, const int *subset, int m, int k, int *medoids, int *labels, double *objective,
+                   double *avg_sil, int *n_swaps)
+{
+    if (!dm) { rid_set_error("null distance matrix"); return RID_ERR_ARG; }
+    if (subset == nullptr) m = dm->N;
+    if (k < 1 || k >= m) {
+        rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}");
+        return RID_ERR_ARG;
+    }
+    RID_TRY(pam_check_na(dm, subset, m));
+    PamWs *w;
+    RID_TRY(ws_get(dm, k, &w));
+    RID_TRY(pam_set_subset(dm, w, subset, m));
+    RID_TRY(pam_begin(dm, w));
+    RID_TRY(pam_build(dm, w, 0, k));
+    PamState hs;
+    RID_TRY(pam_swap(dm, w, k, &hs));
+    std::vector<int> slot;
+    RID_TRY(pam_collect_labels(dm, w, slot));
+    std::vector<int> h_medpos(k);
+    RID_CUDA(cudaMemcpy(h_medpos.data(), w->medpos, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    number_clusters(slot, k, h_medpos, labels, medoids);
+    if (objective) {
+        objective[0] = (double)hs.td_build * dm->step / (double)m;
+        objective[1] = (double)hs.td * dm->step / (double)m;
+    }
+    if (n_swaps) *n_swaps = hs.nswaps;
+    if (avg_sil) {
+        if (k == 1) {
+            *avg_sil = 0.0;
+        } else {
+            rid_ctx *ctx = dm->ctx;
+            RID_TRY(grouped_colsums(dm, w, k));
+            RID_CUDA(cudaMemsetAsync(w->grp_sum, 0, (size_t)k * sizeof(u64), ctx->stream));
+            RID_CUDA(cudaMemsetAsync(w->grp_cnt, 0, (size_t)k * sizeof(int), ctx->stream));
+            LAUNCH(ctx, k_wdisp, nblk(w->m, 256), 256, 0, w->subset, w->lab_pos, w->m, w->acc + 4 + w->ld, w->ld,
+                   w->grp_sum, w->grp_cnt);
+            LAUNCH(ctx, k_silhouette, nblk(w->m, 256), 256, 0, w->subset, w->lab_pos, w->m, k, w->acc + 4 + w->ld, w->ld,
+                   w->grp_cnt, w->sil);
+            LAUNCH(ctx, k_sum_f64, 1, 1024, 0, w->sil, w->m, w->dscratch);
+            RID_CUDA(cudaGetLastError());
+            double s = 0.0;
+            RID_CUDA(cudaMemcpyAsync(&s, w->dscratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            RID_CUDA(cudaStreamSynchronize(ctx->stream));
+            *avg_sil = s / (double)m;
+        }
+    }
+    return RID_OK;
+}
+
+extern "C" int rid_pam(rid_dmat *dm, const int *subset, int m, int k, int *medoids, int *labels, double *objective,
+                       double *avg_sil, int *n_swaps)
+{
+    if (!dm) { rid_set_error("null distance matrix"); return RID_ERR_ARG; }
+    RID_TRY(rid_time_begin(dm->ctx));
+    int rc = pam_run(dm, subset, m, k, medoids, labels, objective, avg_sil, n_swaps);
+    if (rc == RID_OK) rc = rid_time_end(dm->ctx);
+    return rc;
+}
+
+extern "C" int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W)
+{
+    if (!dm || !labels || !W || k < 1) { rid_set_error("rid_within_disp: bad arguments"); return RID_ERR_ARG; }
+    if (subset == nullptr) m = dm->N;
+    RID_TRY(pam_check_na(dm, subset, m));
+    PamWs *w;
+    RID_TRY(ws_get(dm, k, &w));
+    RID_TRY(pam_set_subset(dm, w, subset, m));
+    std::vector<int> g(m);
+    for (int p = 0; p < m; ++p) {
+        if (labels[p] < 1 || labels[p] > k) { rid_set_error("label %d out of 1..%d", labels[p], k); return RID_ERR_ARG; }
+        g[p] = labels[p] - 1;
+    }
+    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    RID_TRY(rid_time_begin(dm->ctx));
+    RID_TRY(within_disp(dm, w, k, W, nullptr));
+    return rid_time_end(dm->ctx);
+}
+
+// clusGapExt's k loop.  BUILD is greedy and does not depend on k, so BUILD(k) is the first k picks of
+// BUILD(Kmax): run it once and start SWAP(k) from the k-prefix (identical results, Kmax instead of
+// Kmax(Kmax+1)/2 BUILD passes).
+extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW)
+{
+    if (!dm || !logW || Kmax < 1) { rid_set_error("rid_gap_sweep: bad arguments"); return RID_ERR_ARG; }
+    if (subset == nullptr) m = dm->N;
+    if (Kmax >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); return RID_ERR_ARG; }
+    RID_TRY(pam_check_na(dm, subset, m));
+    rid_ctx *ctx = dm->ctx;
+    PamWs *w;
+    RID_TRY(ws_get(dm, Kmax, &w));
+    RID_TRY(pam_set_subset(dm, w, subset, m));
+    RID_TRY(rid_time_begin(ctx));
+    RID_TRY(pam_begin(dm, w));
+    RID_TRY(pam_build(dm, w, 0, Kmax));
+    std::vector<int> order(Kmax);
+    RID_CUDA(cudaMemcpyAsync(order.data(), w->med, (size_t)Kmax * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    int *d_order = nullptr;
+    RID_CUDA(cudaMalloc(&d_order, (size_t)Kmax * sizeof(int)));
+    RID_CUDA(cudaMemcpy(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice));
+    int rc = RID_OK;
+    for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
+        double W = 0.0;
+        if (k == 1) {
+            rc = cudaMemsetAsync(w->lab_pos, 0, (size_t)m * sizeof(int), ctx->stream) == cudaSuccess ? RID_OK : RID_ERR_CUDA;
+        } else {
+            cudaMemsetAsync(w->is_med, 0, (size_t)dm->N, ctx->stream);
+            LAUNCH(ctx, k_set_medoids, 1, std::max(32, (k + 31) / 32 * 32), 0, d_order, k, w->med, w->medpos, w->pos_of,
+                   w->is_med, w->state);
+            PamState hs;
+            rc = pam_swap(dm, w, k, &hs);
+            std::vector<int> slot;
+            if (rc == RID_OK) rc = pam_collect_labels(dm, w, slot);
+        }
+        if (rc == RID_OK) rc = within_disp(dm, w, k, &W, nullptr);
+        logW[k - 1] = log(W);
+    }
+    cudaFree(d_order);
+    if (rc != RID_OK) return rc;
+    return rid_time_end(ctx);
+}
+
+extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const int *sample_len, int B, int *partition,
+                               int *medoids, double *bootresult)
+{
+    if (!dm || !partition || (B > 0 && (!samples || !sample_len || !bootresult))) {
+        rid_set_error("rid_clusterboot: bad arguments");
+        return RID_ERR_ARG;
+    }
+    rid_ctx *ctx = dm->ctx;
+    int N = dm->N;
+    RID_TRY(rid_time_begin(ctx));
+    std::vector<int> med_pos(k);
+    RID_TRY(pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr));
+    if (medoids) for (int c = 0; c < k; ++c) medoids[c] = med_pos[c]; // positions == cells for the full set
+    // c1 labels by cell (0-based) on the device
+    int *d_part = nullptr, *d_tab = nullptr;
+    RID_CUDA(cudaMalloc(&d_part, (size_t)N * sizeof(int)));
+    RID_CUDA(cudaMalloc(&d_tab, (size_t)k * k * sizeof(int)));
+    std::vector<int> p0(N);
+    for (int i = 0; i < N; ++i) p0[i] = partition[i] - 1;
+    RID_CUDA(cudaMemcpy(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    PamWs *w = dm->ws;
+    std::vector<int> tab((size_t)k * k), blab, bmed(k);
+    const int *sp = samples;
+    int rc = RID_OK;
+    for (int b = 0; b < B && rc == RID_OK; ++b) {
+        int m = sample_len[b];
+        blab.resize(m);
+        rc = pam_run(dm, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr);
+        if (rc != RID_OK) break;
+        // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
+        cudaMemsetAsync(d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
+        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, d_part, k, d_tab);
+        if (cudaMemcpyAsync(tab.data(), d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rid_set_error("rid_clusterboot: contingency table copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = RID_ERR_CUDA;
+            break;
+        }
+        std::vector<long long> ca(k, 0), cb(k, 0);
+        for (int a = 0; a < k; ++a)
+            for (int c = 0; c < k; ++c) { ca[a] += tab[(size_t)a * k + c]; cb[c] += tab[(size_t)a * k + c]; }
+        for (int j = 0; j < k; ++j) {
+            double best = 0.0;
+            for (int c = 0; c < k; ++c) {
+                long long inter = tab[(size_t)j * k + c], uni = ca[j] + cb[c] - inter;
+                double cj = uni == 0 ? 0.0 : (double)inter / (double)uni; // clujaccard(zerobyzero=0)
+                if (cj > best) best = cj;
+            }
+            bootresult[(size_t)b * k + j] = best;
+        }
+        sp += m;
+    }
+    cudaFree(d_part);
+    cudaFree(d_tab);
+    if (rc != RID_OK) return rc;
+    return rid_time_end(ctx);
+}
+
+extern "C" int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_idx, int *cluster_ids, int *n_clusters)
+{
+    if (!dm || !labels || !medoid_idx || N != dm->N) { rid_set_error("rid_medoids: bad arguments"); return RID_ERR_ARG; }
+    rid_ctx *ctx = dm->ctx;
+    // sort(unique(part)) and the member list in cell order
+    std::vector<int> ids;
+    for (int i = 0; i < N; ++i) if (labels[i] > 0) ids.push_back(labels[i]);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    int k = (int)ids.size();
+    if (n_clusters) *n_clusters = k;
+    if (k == 0) return RID_OK;
+    std::vector<int> sub, g;
+    for (int i = 0; i < N; ++i)
+        if (labels[i] > 0) {
+            sub.push_back(i);
+            g.push_back((int)(std::lower_bound(ids.begin(), ids.end(), labels[i]) - ids.begin()));
+        }
+    int m = (int)sub.size();
+    RID_TRY(pam_check_na(dm, sub.data(), m));
+    PamWs *w;
+    RID_TRY(ws_get(dm, k, &w));
+    RID_TRY(pam_set_subset(dm, w, sub.data(), m));
+    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    RID_TRY(rid_time_begin(ctx));
+    RID_TRY(grouped_colsums(dm, w, k));
+    RID_CUDA(cudaMemsetAsync(w->grp_min, 0xFF, (size_t)k * sizeof(u64), ctx->stream));
+    RID_CUDA(cudaMemsetAsync(w->grp_arg, 0x7F, (size_t)k * sizeof(int), ctx->stream));
+    for (int pass = 0; pass < 2; ++pass)
+        LAUNCH(ctx, k_medoid_min, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, w->acc + 4 + w->ld, w->ld, w->grp_min,
+               w->grp_arg, pass);
+    RID_CUDA(cudaGetLastError());
+    std::vector<int> arg(k);
+    RID_CUDA(cudaMemcpyAsync(arg.data(), w->grp_arg, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_TRY(rid_time_end(ctx));
+    for (int c = 0; c < k; ++c) {
+        medoid_idx[c] = sub[arg[c]];
+        if (cluster_ids) cluster_ids[c] = ids[c];
+    }
+    return RID_OK;
+}
+
+extern "C" int rid_refresh(rid_dmat *dm, const int *medoid_idx, int k, int *labels)
+{
+    if (!dm || !medoid_idx || !labels || k < 1) { rid_set_error("rid_refresh: bad arguments"); return RID_ERR_ARG; }
+    rid_ctx *ctx = dm->ctx;
+    int N = dm->N;
+    for (int c = 0; c < k; ++c)
+        if (medoid_idx[c] < 0 || medoid_idx[c] >= N) { rid_set_error("medoid index out of range"); return RID_ERR_ARG; }
+    RID_TRY(pam_check_na(dm, nullptr, N));
+    PamWs *w;
+    RID_TRY(ws_get(dm, k, &w));
+    RID_TRY(rid_time_begin(ctx));
+    RID_CUDA(cudaMemcpyAsync(w->med, medoid_idx, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemsetAsync(w->lab_pos, 0, (size_t)N * sizeof(int), ctx->stream));
+    int nloc = dm->row1 - dm->row0;
+    if (nloc) LAUNCH(ctx, k_refresh, nblk(nloc, 128), 128, 0, dm->D, dm->ld, dm->row0, nloc, w->med, k, w->lab_pos);
+    RID_CUDA(cudaGetLastError());
+    RID_TRY(rid_allreduce_i32(ctx, w->lab_pos, (size_t)N));
+    RID_CUDA(cudaMemcpyAsync(labels, w->lab_pos, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_TRY(rid_time_end(ctx));
+    // for (i in max(cpart):1) if (sum(cpart==i)==0) cpart[cpart>i] <- cpart[cpart>i]-1
+    std::vector<int> cnt(k + 1, 0), remap(k + 1, 0);
+    for (int i = 0; i < N; ++i) cnt[labels[i]]++;
+    int next = 0;
+    for (int c = 1; c <= k; ++c) if (cnt[c]) remap[c] = ++next;
+    for (int i = 0; i < N; ++i) labels[i] = remap[labels[i]];
+    return RID_OK;
+}

@@ -1,0 +1,249 @@
+"""ctypes binding of libraceid_b200.so (C ABI declared in include/raceid_b200.h).
+
+This is the only way the Python host layer reaches compute.  There is NO CPU fallback: if the shared library is
+missing, or no sm_100 device is usable, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libraceid_b200.so")
+
+METRIC_CODES = {"pearson": 0, "spearman": 1, "logpearson": 2, "euclidean": 3}
+
+# every symbol include/raceid_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
+    "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
+    "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp",
+]
+
+
+class RaceIDError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libraceid_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C raceid3_stemid2_package_b200/csrc).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, ip, dp = C.c_void_p, C.c_void_p, C.c_void_p
+    L.rid_last_error.restype = C.c_char_p
+    L.rid_version.restype = C.c_int
+    L.rid_nccl_unique_id.argtypes = [vp]
+    L.rid_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.rid_ctx_destroy.argtypes = [vp]
+    L.rid_ctx_sync.argtypes = [vp]
+    L.rid_ctx_last_ms.argtypes = [vp]
+    L.rid_ctx_last_ms.restype = C.c_double
+    L.rid_ctx_launches.argtypes = [vp]
+    L.rid_ctx_launches.restype = C.c_longlong
+    L.rid_dist.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.rid_dmat_from_host.argtypes = [vp, dp, C.c_int, C.POINTER(vp)]
+    L.rid_dmat_free.argtypes = [vp]
+    L.rid_dmat_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.rid_dmat_sub.argtypes = [vp, ip, C.c_int, ip, C.c_int, dp]
+    L.rid_pam.argtypes = [vp, ip, C.c_int, C.c_int, ip, ip, dp, dp, ip]
+    L.rid_gap_sweep.argtypes = [vp, ip, C.c_int, C.c_int, dp]
+    L.rid_clusterboot.argtypes = [vp, C.c_int, ip, ip, C.c_int, ip, ip, dp]
+    L.rid_medoids.argtypes = [vp, ip, C.c_int, ip, ip, ip]
+    L.rid_refresh.argtypes = [vp, ip, C.c_int, ip]
+    L.rid_within_disp.argtypes = [vp, ip, C.c_int, ip, C.c_int, dp]
+    for name in SYMBOLS:
+        getattr(L, name)  # AttributeError here = the library does not export what include/raceid_b200.h declares
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RaceIDError(rc, load().rid_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load().rid_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Context:
+    """One GPU (one rank of a row-sharded job).  Mirrors rid_ctx."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, nccl_uid: bytes | None = None):
+        self._h = C.c_void_p()
+        self.rank, self.world, self.device = rank, world, device
+        uid = C.create_string_buffer(nccl_uid, 128) if nccl_uid is not None else None
+        _check(load().rid_ctx_create(device, rank, world, uid, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load().rid_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(load().rid_ctx_sync(self._h))
+
+    @property
+    def last_ms(self) -> float:
+        return load().rid_ctx_last_ms(self._h)
+
+    @property
+    def launches(self) -> int:
+        return int(load().rid_ctx_launches(self._h))
+
+    # ---- distance matrices ----
+    def dist(self, x_gn, metric: str = "pearson") -> "DistMatrix":
+        """x_gn: G x N numpy array (genes x cells), or a (device_ptr, G, N) tuple for device-resident input laid
+        out cell-major (each cell's G doubles contiguous)."""
+        if metric not in METRIC_CODES:
+            raise ValueError("metric has to be one of the following: spearman, pearson, logpearson, euclidean")
+        h = C.c_void_p()
+        nz = C.c_int(0)
+        if isinstance(x_gn, tuple):
+            ptr, G, N = x_gn
+            _check(load().rid_dist(self._h, C.c_void_p(ptr), G, N, METRIC_CODES[metric], 1, C.byref(h), C.byref(nz)))
+        else:
+            x = np.asarray(x_gn, dtype=np.float64)
+            G, N = x.shape
+            buf = np.ascontiguousarray(x.T)  # == G x N column-major
+            _check(load().rid_dist(self._h, _p(buf), G, N, METRIC_CODES[metric], 0, C.byref(h), C.byref(nz)))
+        return DistMatrix(self, h, nz.value)
+
+    def dist_cellmajor(self, x_ng: np.ndarray, metric: str = "pearson") -> "DistMatrix":
+        """x_ng: N x G C-contiguous float64 host array (one row per cell) — no transpose copy."""
+        x = np.ascontiguousarray(x_ng, dtype=np.float64)
+        N, G = x.shape
+        h = C.c_void_p()
+        nz = C.c_int(0)
+        _check(load().rid_dist(self._h, _p(x), G, N, METRIC_CODES[metric], 0, C.byref(h), C.byref(nz)))
+        return DistMatrix(self, h, nz.value)
+
+    def from_matrix(self, D: np.ndarray) -> "DistMatrix":
+        D = np.asarray(D, dtype=np.float64)
+        if D.ndim != 2 or D.shape[0] != D.shape[1]:
+            raise ValueError("distance matrix must be square")
+        buf = np.ascontiguousarray(D.T)  # column-major
+        h = C.c_void_p()
+        _check(load().rid_dmat_from_host(self._h, _p(buf), D.shape[0], C.byref(h)))
+        return DistMatrix(self, h, 0)
+
+
+class DistMatrix:
+    """Device-resident, row-block-sharded distance matrix (rid_dmat).  Plays the role of `sc@distances`."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p, n_zero_var: int):
+        self.ctx = ctx
+        self._h = handle
+        self.n_zero_var = n_zero_var
+        n, r0, r1, has_na = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        step = C.c_double()
+        _check(load().rid_dmat_info(self._h, C.byref(n), C.byref(r0), C.byref(r1), C.byref(step), C.byref(has_na)))
+        self.N, self.row0, self.row1, self.step, self.has_na = n.value, r0.value, r1.value, step.value, bool(has_na.value)
+
+    def free(self):
+        if self._h:
+            load().rid_dmat_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return (self.N, self.N)
+
+    def sub(self, rows=None, cols=None) -> np.ndarray:
+        r, c = _i32(rows), _i32(cols)
+        m = self.N if r is None else len(r)
+        n = self.N if c is None else len(c)
+        out = np.empty((n, m), dtype=np.float64)  # column-major m x n
+        _check(load().rid_dmat_sub(self._h, _p(r), m, _p(c), n, _p(out)))
+        return out.T
+
+    def as_matrix(self) -> np.ndarray:
+        return np.ascontiguousarray(self.sub())
+
+    def pam(self, k: int, subset=None, want_sil: bool = False):
+        s = _i32(subset)
+        m = self.N if s is None else len(s)
+        med = np.zeros(max(k, 1), dtype=np.int32)
+        lab = np.zeros(m, dtype=np.int32)
+        obj = np.zeros(2)
+        sil = np.zeros(1)
+        nsw = np.zeros(1, dtype=np.int32)
+        _check(load().rid_pam(self._h, _p(s), m, k, _p(med), _p(lab), _p(obj), _p(sil) if want_sil else None, _p(nsw)))
+        return {"id_med": med[:k], "clustering": lab, "objective": obj, "avg_sil": float(sil[0]) if want_sil else None,
+                "n_swaps": int(nsw[0])}
+
+    def gap_sweep(self, kmax: int, subset=None) -> np.ndarray:
+        s = _i32(subset)
+        m = self.N if s is None else len(s)
+        out = np.zeros(kmax)
+        _check(load().rid_gap_sweep(self._h, _p(s), m, kmax, _p(out)))
+        return out
+
+    def clusterboot(self, k: int, samples):
+        B = len(samples)
+        cat = _i32(np.concatenate(samples)) if B else np.zeros(1, dtype=np.int32)
+        lens = _i32([len(s) for s in samples]) if B else np.zeros(1, dtype=np.int32)
+        part = np.zeros(self.N, dtype=np.int32)
+        med = np.zeros(k, dtype=np.int32)
+        br = np.zeros((max(B, 1), k))
+        _check(load().rid_clusterboot(self._h, k, _p(cat), _p(lens), B, _p(part), _p(med), _p(br)))
+        br = br[:B]
+        return {"partition": part, "id_med": med, "bootresult": br.T.copy(),
+                "bootmean": br.mean(axis=0) if B else np.ones(k)}
+
+    def medoids(self, labels):
+        lab = _i32(labels)
+        out = np.zeros(self.N, dtype=np.int32)
+        ids = np.zeros(self.N, dtype=np.int32)
+        nc = C.c_int(0)
+        _check(load().rid_medoids(self._h, _p(lab), len(lab), _p(out), _p(ids), C.byref(nc)))
+        return out[:nc.value].copy(), ids[:nc.value].copy()
+
+    def refresh(self, medoid_idx) -> np.ndarray:
+        md = _i32(medoid_idx)
+        lab = np.zeros(self.N, dtype=np.int32)
+        _check(load().rid_refresh(self._h, _p(md), len(md), _p(lab)))
+        return lab
+
+    def within_disp(self, labels, k: int, subset=None) -> float:
+        s = _i32(subset)
+        lab = _i32(labels)
+        W = np.zeros(1)
+        _check(load().rid_within_disp(self._h, _p(s), len(lab), _p(lab), k, _p(W)))
+        return float(W[0])
