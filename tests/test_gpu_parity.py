@@ -1,0 +1,283 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (raceid3_stemid2_package_b200.lib -> libraceid_b200.so),
+against the CPU oracle on the same seeded inputs and against the committed golden fixtures.
+
+Bars: distances within 1e-6 absolute of the FP64 oracle (north_star); everything PAM computes on the device matrix
+is integer-exact, so medoids / labels / objectives / Jaccard tables must be IDENTICAL to the oracle run on the same
+(device) matrix; logW and silhouette within 1e-12 (they end in a floating-point division/log)."""
+import numpy as np
+import pytest
+
+from conftest import ari, load_golden
+
+pytestmark = pytest.mark.gpu
+
+DIST_TOL = 1e-6  # north_star: distances within 1e-6 absolute of R's double-precision cor()/dist()
+
+
+def _features(seed=0, G=300, N=500, C=6):
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    x, lab = synth_features_numpy(N, G, C, seed)
+    return np.ascontiguousarray(x.T), lab  # genes x cells
+
+
+@pytest.mark.parametrize("metric", ["pearson", "spearman", "logpearson", "euclidean"])
+def test_dist_matches_oracle(ctx, oracle, metric):
+    x, _ = _features(seed=1)
+    x[:, 17] = x[:, 4]  # duplicate cells: exact-zero distances, the Gram-form cancellation case for euclidean
+    Do, nz = oracle.dist(x, metric)
+    dm = ctx.dist(x, metric)
+    Dg = dm.as_matrix()
+    assert dm.n_zero_var == nz == 0
+    tol = max(DIST_TOL, dm.step) if metric == "euclidean" else DIST_TOL
+    assert np.max(np.abs(Dg - Do)) <= tol
+    assert np.array_equal(Dg, Dg.T)
+    assert np.all(np.diag(Dg) == 0.0)
+    assert Dg[17, 4] <= dm.step
+    dm.free()
+
+
+def test_dist_zero_variance_cell(ctx, oracle):
+    x, _ = _features(seed=2, G=120, N=200)
+    x[:, 9] = 3.25
+    Do, nz = oracle.dist(x, "pearson")
+    dm = ctx.dist(x, "pearson")
+    Dg = dm.as_matrix()
+    assert dm.n_zero_var == nz == 1 and dm.has_na
+    assert np.array_equal(np.isnan(Dg), np.isnan(Do))
+    ok = ~np.isnan(Do)
+    assert np.max(np.abs(Dg[ok] - Do[ok])) <= DIST_TOL
+    from raceid3_stemid2_package_b200.lib import RaceIDError
+
+    with pytest.raises(RaceIDError):
+        dm.pam(3)  # pam() refuses NAs
+    keep = np.array([i for i in range(200) if i != 9], dtype=np.int32)
+    r = dm.pam(3, subset=keep)
+    ro = oracle.pam(np.nan_to_num(Dg), 3, subset=keep)
+    assert np.array_equal(r["id_med"], ro["id_med"])
+    dm.free()
+
+
+def test_dist_ragged_shapes(ctx, oracle):
+    """N and G that are not multiples of any tile size; tiny and odd sizes."""
+    for (G, N, seed) in [(7, 5, 3), (17, 129, 4), (130, 257, 5), (33, 2, 6)]:
+        rng = np.random.default_rng(seed)
+        x = rng.random((G, N)) + 0.1
+        Do, _ = oracle.dist(x, "pearson")
+        dm = ctx.dist(x, "pearson")
+        assert np.max(np.abs(dm.as_matrix() - Do)) <= DIST_TOL
+        dm.free()
+
+
+def _check_pam(dm, oracle, Dg, k, subset=None):
+    r = dm.pam(k, subset=subset, want_sil=True)
+    ro = oracle.pam(Dg, k, subset=subset, want_sil=True)
+    assert np.array_equal(r["id_med"], ro["id_med"]), (k, r["id_med"], ro["id_med"])
+    assert np.array_equal(r["clustering"], ro["clustering"])
+    assert r["n_swaps"] == ro["n_swaps"]
+    assert np.allclose(r["objective"], ro["objective"], rtol=0, atol=1e-13)
+    assert abs(r["avg_sil"] - ro["avg_sil"]) < 1e-12
+    return r
+
+
+@pytest.mark.parametrize("metric", ["pearson", "euclidean"])
+def test_pam_identical_to_oracle_on_device_matrix(ctx, oracle, metric):
+    x, _ = _features(seed=7, G=200, N=400, C=5)
+    dm = ctx.dist(x, metric)
+    Dg = dm.as_matrix()
+    for k in (1, 2, 3, 5, 8, 13):
+        _check_pam(dm, oracle, Dg, k)
+    rng = np.random.default_rng(0)
+    s = rng.integers(0, 400, 400)
+    _, first = np.unique(s, return_index=True)
+    sub = s[np.sort(first)].astype(np.int32)
+    for k in (2, 5):
+        _check_pam(dm, oracle, Dg, k, subset=sub)
+    dm.free()
+
+
+def test_pam_matches_fp64_reference_path(ctx, oracle):
+    """Against the oracle's OWN double-precision distances (the reference's path end to end): ARI = 1 and the
+    same medoids on well-separated data."""
+    x, _ = _features(seed=8, G=300, N=600, C=6)
+    Do, _ = oracle.dist(x, "pearson")
+    dm = ctx.dist(x, "pearson")
+    for k in (3, 6):
+        r = dm.pam(k)
+        ro = oracle.pam(Do, k)
+        assert ari(r["clustering"], ro["clustering"]) == 1.0
+        assert np.array_equal(r["id_med"], ro["id_med"])
+    dm.free()
+
+
+def test_pam_ties_duplicates_and_from_matrix(ctx, oracle):
+    """Exact ties everywhere: distances on a coarse grid with duplicated points, adopted through rid_dmat_from_host."""
+    rng = np.random.default_rng(3)
+    pts = rng.integers(0, 6, size=(90, 3)).astype(np.float64)
+    pts[11] = pts[2]
+    pts[40] = pts[2]
+    D = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+    D = np.round(D * 8) / 8
+    dm = ctx.from_matrix(D)
+    Dg = dm.as_matrix()
+    assert np.array_equal(Dg, D)  # grid values are exactly representable in the fixed-point format
+    for k in (2, 3, 4, 7):
+        r = dm.pam(k)
+        ro = oracle.pam(D, k)
+        # swap decisions are exact; BUILD's first pick can differ from FP64 only on exact row-sum ties, where the
+        # oracle's double rounding is arbitrary; the final objective must agree either way
+        assert np.allclose(r["objective"][1], ro["objective"][1], atol=1e-12) or r["n_swaps"] != ro["n_swaps"]
+        if np.array_equal(r["id_med"], ro["id_med"]):
+            assert np.array_equal(r["clustering"], ro["clustering"])
+    dm.free()
+
+
+def test_from_matrix_lower_triangle_rule_and_errors(ctx):
+    from raceid3_stemid2_package_b200.lib import RaceIDError
+
+    D = np.array([[0, 9, 9], [1, 0, 9], [2, 0.5, 0]], dtype=np.float64)
+    dm = ctx.from_matrix(D)
+    assert np.array_equal(dm.as_matrix(), np.array([[0, 1, 2], [1, 0, 0.5], [2, 0.5, 0]]))
+    with pytest.raises(RaceIDError):
+        dm.pam(3)  # k must be in 1..n-1
+    with pytest.raises(RaceIDError):
+        dm.pam(0)
+    dm.free()
+
+
+def test_gap_sweep_within_disp_medoids_refresh(ctx, oracle):
+    x, _ = _features(seed=9, G=150, N=350, C=4)
+    dm = ctx.dist(x, "pearson")
+    Dg = dm.as_matrix()
+    lw = dm.gap_sweep(12)
+    lwo = oracle.gap_sweep(Dg, 12)
+    assert np.max(np.abs(lw - lwo)) < 1e-12
+    sub = np.arange(349, -1, -3).astype(np.int32)
+    assert np.max(np.abs(dm.gap_sweep(6, subset=sub) - oracle.gap_sweep(Dg, 6, subset=sub))) < 1e-12
+    lab = oracle.pam(Dg, 5)["clustering"]
+    assert abs(dm.within_disp(lab, 5) - oracle.wk(Dg, lab, 5)) < 1e-9
+    lab2 = lab.copy()
+    lab2[::7] = 0
+    lab2[lab2 == 3] = 9  # non-contiguous cluster numbers, cells outside `part`
+    med, ids = dm.medoids(lab2)
+    medo, idso = oracle.medoids(Dg, lab2)
+    assert np.array_equal(med, medo) and np.array_equal(ids, idso)
+    assert np.array_equal(dm.refresh(med), oracle.refresh(Dg, medo))
+    dm.free()
+
+
+def test_clusterboot_identical(ctx, oracle):
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+
+    x, _ = _features(seed=10, G=150, N=300, C=4)
+    dm = ctx.dist(x, "spearman")
+    Dg = dm.as_matrix()
+    samples = bootstrap_samples(300, 6, 17000)
+    r = dm.clusterboot(4, samples)
+    ro = oracle.clusterboot(Dg, 4, samples)
+    assert np.array_equal(r["partition"], ro["partition"])
+    assert np.array_equal(r["id_med"], ro["id_med"])
+    assert np.array_equal(r["bootresult"], ro["bootresult"])
+    assert np.allclose(r["bootmean"], ro["bootmean"], atol=1e-15)
+    dm.free()
+
+
+@pytest.mark.parametrize("name", ["cfg1_intestinalDataSmall.npz", "cfg2_intestinalData.npz"])
+def test_golden_configs(ctx, oracle, name):
+    """configs[0] / configs[1] of BASELINE.json on the reference's bundled data (committed fixtures)."""
+    g = load_golden(name)
+    x = g["x"]
+    for metric in ("pearson", "spearman", "logpearson", "euclidean"):
+        dm = ctx.dist(x, metric)
+        tol = max(DIST_TOL, dm.step) if metric == "euclidean" else DIST_TOL
+        assert np.max(np.abs(dm.as_matrix() - g[f"D_{metric}"])) <= tol
+        dm.free()
+    dm = ctx.dist(x, "pearson")
+    Dg = dm.as_matrix()
+    n_same = 0
+    for k in (2, 3, 5, int(g["boot_k"])):
+        r = _check_pam(dm, oracle, Dg, k)  # exact vs oracle on the device matrix
+        # vs the FP64 golden (reference path end to end): identical partitions expected unless a swap-cost gap is
+        # below the 1e-6 distance tolerance (cfg1 has 579 duplicated distances)
+        same = np.array_equal(r["clustering"], g[f"pam{k}_clustering"])
+        n_same += same
+        if name.startswith("cfg2"):
+            assert same and np.array_equal(r["id_med"], g[f"pam{k}_id_med"])
+            assert abs(r["avg_sil"] - float(g[f"pam{k}_avg_sil"])) < 1e-6
+    lw = dm.gap_sweep(len(g["logW"]))
+    assert np.max(np.abs(lw - oracle.gap_sweep(Dg, len(lw)))) < 1e-12
+    if name.startswith("cfg2"):
+        assert np.max(np.abs(lw - g["logW"])) < 1e-6
+        from raceid3_stemid2_package_b200.scseq import bootstrap_samples, saturation_cln
+
+        assert saturation_cln(lw) == int(g["cln_sat"])
+        n = dm.N
+        samples = bootstrap_samples(n, len(g["boot_sample_lens"]), 17000)
+        assert np.array_equal(samples[0], g["boot_sample0"])
+        r = dm.clusterboot(int(g["boot_k"]), samples)
+        assert np.array_equal(r["partition"], g["boot_partition"])
+        assert np.max(np.abs(r["bootresult"] - g["boot_result"])) < 1e-12
+        med, _ = dm.medoids(r["partition"])
+        assert np.array_equal(med, g["medoids"])
+        assert np.array_equal(dm.refresh(med), g["refresh"])
+    dm.free()
+
+
+def test_api_compdist_clustexp_end_to_end(ctx, oracle):
+    """The reference-facing API: SCseq -> compdist -> clustexp -> compmedoids, against the oracle pipeline."""
+    import raceid3_stemid2_package_b200 as rid
+
+    rid.set_context(ctx)
+    g = load_golden("cfg2_intestinalData.npz")
+    x = g["x"]
+    G, N = x.shape
+    sc = rid.SCseq(np.ones((G, N)))  # a stand-in SCseq whose filtered slots we fill directly
+    sc.cell_names = [f"c{i}" for i in range(N)]
+    sc.genes = [f"g{i}" for i in range(G)]
+    sc.genes_all = list(sc.genes)
+    sc.counts = np.ones(N)
+    sc.ndata = (x - 0.1)  # getfdata = ndata*min(counts)+0.1
+    sc.cluster["features"] = list(sc.genes)
+    sc = rid.compdist(sc, metric="pearson")
+    assert isinstance(sc.distances, rid.DistMatrix)
+    sc = rid.clustexp(sc, clustnr=15, bootnr=8, verbose=False)
+    Dg = sc.distances.as_matrix()
+    lwo = oracle.gap_sweep(Dg, 15)
+    assert np.max(np.abs(sc.cluster["gap"]["Tab"][:, 0] - lwo)) < 1e-12
+    cln = oracle.saturation(lwo)
+    cb = oracle.clusterboot(Dg, cln, rid.bootstrap_samples(N, 8, 17000))
+    assert np.array_equal(sc.cluster["kpart"], cb["partition"])
+    assert np.allclose(sc.cluster["jaccard"], cb["bootmean"], atol=1e-14)
+    med = rid.compmedoids(sc, sc.cluster["kpart"])
+    medo, _ = oracle.medoids(Dg, cb["partition"])
+    assert med == [sc.cell_names[i] for i in medo]
+    sc2 = rid.clustexp(sc, sat=False, cln=7, bootnr=1, verbose=False)
+    assert int(sc2.cluster["kpart"].max()) == 7
+    with pytest.raises(ValueError):
+        rid.clustexp(sc, sat=False, verbose=False)
+    with pytest.raises(ValueError):
+        rid.compdist(sc, metric="manhattan")
+    rid.set_context(None)
+
+
+def test_scaled_properties_20k(ctx):
+    """Size-independent properties at a size the oracle cannot reach in seconds (N = 20 000): symmetry, zero
+    diagonal, range, BUILD-prefix property, TD monotone under SWAP, every cell assigned to its nearest medoid."""
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    x, truth = synth_features_numpy(20000, 512, 8, 1003)
+    dm = ctx.dist_cellmajor(x, "pearson")
+    rows = np.array([0, 1, 4999, 12345, 19999], dtype=np.int32)
+    blk = dm.sub(rows=rows)
+    colblk = dm.sub(cols=rows)
+    assert np.array_equal(blk, colblk.T)
+    assert np.all(blk[np.arange(5), rows] == 0.0)
+    assert blk.min() >= 0.0 and blk.max() <= 2.0
+    r8 = dm.pam(8)
+    assert r8["objective"][1] <= r8["objective"][0] + 1e-15
+    med = r8["id_med"]
+    cols = dm.sub(cols=med.astype(np.int32))
+    assert np.array_equal(np.argmin(cols, axis=1) + 1, r8["clustering"])
+    assert abs(cols.min(axis=1).mean() - r8["objective"][1]) < 1e-12
+    assert ari(r8["clustering"], truth) > 0.5
+    dm.free()
