@@ -55,6 +55,15 @@ double rid_ctx_last_ms(const rid_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 long long rid_ctx_launches(const rid_ctx *ctx);
 
+/* Measurement hooks (bench.py): per-kernel CUDA-event timing on the library's own stream.
+ * kind: 0 Gram/DMMA distance kernel (work = flops), 1 SWAP scan, 2 BUILD scan, 3 grouped column sums (W.k, medoids,
+ * silhouette), 4 prep (work = algorithmic bytes; traffic = bytes requested from memory). */
+int rid_ctx_profile(rid_ctx *ctx, int enable);
+int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, double *ms, double *work, double *traffic);
+/* user events on the library's stream, slots 0..7 */
+int rid_ctx_event_record(rid_ctx *ctx, int slot);
+int rid_ctx_event_elapsed_ms(rid_ctx *ctx, int slot_a, int slot_b, double *ms);
+
 /* ---- distance matrix: replaces dist.gen (R/RaceID_utils.R:9-15) as called at R/RaceID.R:769 ---------- */
 /* x: G x N column-major doubles (column c = the G feature values of cell c), i.e. what cor()/dist() see.
  * x_on_device != 0: x is a device pointer on ctx's GPU (benchmarks with resident inputs).

@@ -234,14 +234,21 @@ int orc_pam(const double *dmat, int n_full, const int *subset, int m, int k, int
         for (int kk = 0; kk < k; ++kk) {
             int nmax = -1;
             double ammax = 0.;
+            /* beter[i] for every non-representative (independent per i; OpenMP only in the _omp build) */
+#pragma omp parallel for schedule(static)
             for (int i = 0; i < n; ++i) {
                 if (nrepr[i] == 0) {
-                    beter[i] = 0.;
+                    double b = 0.;
                     for (int j = 0; j < n; ++j) {
                         double dij = (i == j) ? 0. : dys_at(dmat, ld, idx, i, j);
                         double cmd = dysma[j] - dij;
-                        if (cmd > 0.) beter[i] += cmd;
+                        if (cmd > 0.) b += cmd;
                     }
+                    beter[i] = b;
+                }
+            }
+            for (int i = 0; i < n; ++i) {
+                if (nrepr[i] == 0) {
                     if (ammax <= beter[i]) { /* upstream: ties go to the LARGEST index */
                         ammax = beter[i];
                         nmax = i;
@@ -281,28 +288,46 @@ int orc_pam(const double *dmat, int n_full, const int *subset, int m, int k, int
             }
             double dzsky = 1.;
             int hbest = -1, nbest = -1;
-            for (int h = 0; h < n; ++h) {
-                if (nrepr[h]) continue;
-                for (int i = 0; i < n; ++i) {
-                    if (!nrepr[i]) continue;
-                    double dz = 0.;
-                    for (int j = 0; j < n; ++j) {
-                        double dhj = (h == j) ? 0. : dys_at(dmat, ld, idx, h, j);
-                        double dij = (i == j) ? 0. : dys_at(dmat, ld, idx, i, j);
-                        if (dij == dysma[j]) {
-                            double small = dysmb[j] > dhj ? dhj : dysmb[j];
-                            dz += (-dysma[j] + small);
-                        } else if (dhj < dysma[j]) {
-                            dz += (-dysma[j] + dhj);
+            /* h-loop split into contiguous chunks (one per thread in the _omp build, one chunk otherwise); chunks
+             * are merged in increasing-h order with the same strict '>' so the first (h,i) still wins ties. */
+            enum { ORC_MAXT = 256 };
+            double cdz[ORC_MAXT];
+            int ch[ORC_MAXT], ci[ORC_MAXT], nchunks = 1;
+#ifdef _OPENMP
+            nchunks = omp_get_max_threads();
+            if (nchunks > ORC_MAXT) nchunks = ORC_MAXT;
+#endif
+#pragma omp parallel for schedule(static, 1)
+            for (int t = 0; t < nchunks; ++t) {
+                int h0 = (int)((long long)n * t / nchunks), h1 = (int)((long long)n * (t + 1) / nchunks);
+                double ldz = 1.;
+                int lh = -1, li = -1;
+                for (int h = h0; h < h1; ++h) {
+                    if (nrepr[h]) continue;
+                    for (int i = 0; i < n; ++i) {
+                        if (!nrepr[i]) continue;
+                        double dz = 0.;
+                        for (int j = 0; j < n; ++j) {
+                            double dhj = (h == j) ? 0. : dys_at(dmat, ld, idx, h, j);
+                            double dij = (i == j) ? 0. : dys_at(dmat, ld, idx, i, j);
+                            if (dij == dysma[j]) {
+                                double small = dysmb[j] > dhj ? dhj : dysmb[j];
+                                dz += (-dysma[j] + small);
+                            } else if (dhj < dysma[j]) {
+                                dz += (-dysma[j] + dhj);
+                            }
+                        }
+                        if (ldz > dz) { /* upstream: first (h,i) wins ties */
+                            ldz = dz;
+                            lh = h;
+                            li = i;
                         }
                     }
-                    if (dzsky > dz) { /* upstream: first (h,i) wins ties */
-                        dzsky = dz;
-                        hbest = h;
-                        nbest = i;
-                    }
                 }
+                cdz[t] = ldz; ch[t] = lh; ci[t] = li;
             }
+            for (int t = 0; t < nchunks; ++t)
+                if (dzsky > cdz[t]) { dzsky = cdz[t]; hbest = ch[t]; nbest = ci[t]; }
             if (dzsky < -16 * DBL_EPSILON * fabs(sky)) {
                 nrepr[hbest] = 1;
                 nrepr[nbest] = 0;

@@ -44,7 +44,21 @@ struct rid_ctx {
     long long launches = 0;
     void *comm = nullptr; // ncclComm_t
     NcclApi *nccl = nullptr;
+    // optional per-kernel profiling (rid_ctx_profile): CUDA-event pairs around the hot kernels, on `stream`
+    int prof_on = 0;
+    struct ProfRec { int kind; cudaEvent_t a, b; double work; double traffic; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> prof_pool;
+    cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// kinds for rid_ctx_profile_get
+enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,
+       RID_PROF_NKINDS = 5 };
+
+// RAII-less helpers: call prof_begin right before the launch and prof_end right after it.
+cudaEvent_t rid_prof_begin(rid_ctx *ctx);
+void rid_prof_end(rid_ctx *ctx, cudaEvent_t a, int kind, double work, double traffic);
 
 int rid_allreduce_u64(rid_ctx *ctx, u64 *buf, size_t count);
 int rid_allreduce_i32(rid_ctx *ctx, int *buf, size_t count);

@@ -172,6 +172,93 @@ int rid_time_end(rid_ctx *ctx)
     return RID_OK;
 }
 
+// ---- per-kernel profiling -------------------------------------------------------------------------------
+static cudaEvent_t prof_event(rid_ctx *ctx)
+{
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+cudaEvent_t rid_prof_begin(rid_ctx *ctx)
+{
+    if (!ctx->prof_on) return nullptr;
+    cudaEvent_t a = prof_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+    return a;
+}
+
+void rid_prof_end(rid_ctx *ctx, cudaEvent_t a, int kind, double work, double traffic)
+{
+    if (!ctx->prof_on || !a) return;
+    cudaEvent_t b = prof_event(ctx);
+    cudaEventRecord(b, ctx->stream);
+    ctx->prof.push_back({kind, a, b, work, traffic});
+}
+
+// enable != 0: start collecting (clears what was collected); enable == 0: stop
+extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
+{
+    if (!ctx) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->prof_on = enable ? 1 : 0;
+    return RID_OK;
+}
+
+// totals for one kernel kind since profiling was enabled: launches, summed device ms, summed algorithmic work
+// (bytes for the scans, flops for the Gram kernel) and summed bytes actually requested from memory
+extern "C" int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, double *ms, double *work,
+                                   double *traffic)
+{
+    if (!ctx || kind < 0 || kind >= RID_PROF_NKINDS) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    long long n = 0;
+    double t = 0, w = 0, tr = 0;
+    for (auto &r : ctx->prof)
+        if (r.kind == kind) {
+            float msf = 0.f;
+            RID_CUDA(cudaEventElapsedTime(&msf, r.a, r.b));
+            ++n; t += msf; w += r.work; tr += r.traffic;
+        }
+    if (launches) *launches = n;
+    if (ms) *ms = t;
+    if (work) *work = w;
+    if (traffic) *traffic = tr;
+    return RID_OK;
+}
+
+// user events on the library's stream (bench.py brackets its timed region with them)
+extern "C" int rid_ctx_event_record(rid_ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= 8) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->user_ev[slot]) RID_CUDA(cudaEventCreate(&ctx->user_ev[slot]));
+    RID_CUDA(cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+    return RID_OK;
+}
+
+extern "C" int rid_ctx_event_elapsed_ms(rid_ctx *ctx, int slot_a, int slot_b, double *ms)
+{
+    if (!ctx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !ctx->user_ev[slot_a] ||
+        !ctx->user_ev[slot_b])
+        return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaEventSynchronize(ctx->user_ev[slot_b]));
+    float f = 0.f;
+    RID_CUDA(cudaEventElapsedTime(&f, ctx->user_ev[slot_a], ctx->user_ev[slot_b]));
+    *ms = f;
+    return RID_OK;
+}
+
 static int allreduce(rid_ctx *ctx, void *buf, size_t count, ncclDataType_t dt)
 {
     if (ctx->world == 1) return RID_OK;

@@ -426,7 +426,11 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     size_t prep_smem = metric == RID_SPEARMAN ? (size_t)G * sizeof(double) : 0;
     if (prep_smem > 48 * 1024)
         DCHK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
+    {
+        cudaEvent_t pe = rid_prof_begin(ctx);
+        LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
+        rid_prof_end(ctx, pe, RID_PROF_PREP, (double)G * N * 16.0, (double)G * N * 32.0);
+    }
     DCHK(cudaGetLastError());
 
     if (metric == RID_EUCLIDEAN) {
@@ -452,7 +456,10 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         if (P.nloc > 0) {
             DCHK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
             dim3 grid((unsigned)(Np / GM_BN), (unsigned)((P.nloc + GM_BM - 1) / GM_BM));
+            cudaEvent_t pe = rid_prof_begin(ctx);
             LAUNCH(ctx, k_gram_dmma, grid, GM_THREADS, GM_SMEM, P);
+            // algorithmic flops: 2 * (owned rows) * N * G
+            rid_prof_end(ctx, pe, RID_PROF_GRAM, 2.0 * (double)P.nloc * (double)N * (double)G, (double)P.nloc * dm->ld * 4.0);
             DCHK(cudaGetLastError());
         }
     }

@@ -679,7 +679,7 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
 
 template <bool WITH_Q>
 static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP, const u32 *capQ, const int *grp,
-                       int check_done)
+                       int check_done, int prof_kind)
 {
     rid_ctx *ctx = dm->ctx;
     if (w->nls == 0) return RID_OK;
@@ -692,6 +692,8 @@ static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP,
     int chunks = (w->nls + rpc - 1) / rpc;
     dim3 grid(strips, chunks);
     u64 *SP = w->acc + 4, *AQ = SP + w->ld;
+    // algorithmic bytes: every distance of the (owned rows x subset) block once; traffic: whole owned rows are read
+    cudaEvent_t pe = rid_prof_begin(ctx);
     auto scan8 = k_scan<WITH_Q, 8>;
     auto scan2 = k_scan<WITH_Q, 2>;
     if (dm->bits <= 28)
@@ -700,6 +702,7 @@ static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP,
     else
         LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, w->nls, rpc, SP, AQ,
                w->state, check_done);
+    rid_prof_end(ctx, pe, prof_kind, (double)w->nls * (double)w->m * 4.0, (double)w->nls * (double)w->ld * 4.0);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -720,7 +723,7 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
     rid_ctx *ctx = dm->ctx;
     for (int s = k_from; s < k_to; ++s) {
         RID_TRY(zero_acc(dm, w, 0, 0));
-        RID_TRY((launch_scan<false>(dm, w, w->rows, w->capP, nullptr, nullptr, 0)));
+        RID_TRY((launch_scan<false>(dm, w, w->rows, w->capP, nullptr, nullptr, 0, RID_PROF_SCAN_BUILD)));
         RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
         auto sel_build = k_select<true>;
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med,
@@ -794,7 +797,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
             if (k < 2) break;
             {
                 RID_TRY(sort_rows_by_group(dm, w, k, chk));
-                RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, chk)));
+                RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, chk, RID_PROF_SCAN_SWAP)));
                 RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
                 auto sel_swap = k_select<false>;
                 LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
@@ -836,7 +839,7 @@ static int grouped_colsums(rid_dmat *dm, PamWs *w, int k)
         LAUNCH(ctx, k_groups_from_labels, nblk(w->nls, 256), 256, 0, w->rows_pos, w->nls, w->lab_pos, w->capP, w->capQ,
                w->grp, w->hist);
     RID_TRY(sort_rows_by_group(dm, w, k, 0));
-    RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, 0)));
+    RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, 0, RID_PROF_SCAN_GROUP)));
     RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
     return RID_OK;
 }

@@ -19,6 +19,7 @@ METRIC_CODES = {"pearson": 0, "spearman": 1, "logpearson": 2, "euclidean": 3}
 SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
+    "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp",
 ]
 
@@ -53,6 +54,11 @@ def load() -> C.CDLL:
     L.rid_ctx_last_ms.restype = C.c_double
     L.rid_ctx_launches.argtypes = [vp]
     L.rid_ctx_launches.restype = C.c_longlong
+    L.rid_ctx_profile.argtypes = [vp, C.c_int]
+    L.rid_ctx_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.rid_ctx_event_record.argtypes = [vp, C.c_int]
+    L.rid_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rid_dist.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
     L.rid_dmat_from_host.argtypes = [vp, dp, C.c_int, C.POINTER(vp)]
     L.rid_dmat_free.argtypes = [vp]
@@ -120,6 +126,25 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load().rid_ctx_launches(self._h))
+
+    PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4}
+
+    def profile(self, enable: bool = True):
+        _check(load().rid_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_get(self, kind: str) -> dict:
+        n, ms, work, tr = C.c_longlong(), C.c_double(), C.c_double(), C.c_double()
+        _check(load().rid_ctx_profile_get(self._h, self.PROF_KINDS[kind], C.byref(n), C.byref(ms), C.byref(work),
+                                          C.byref(tr)))
+        return {"launches": n.value, "ms": ms.value, "work": work.value, "traffic": tr.value}
+
+    def event_record(self, slot: int):
+        _check(load().rid_ctx_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        _check(load().rid_ctx_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
 
     # ---- distance matrices ----
     def dist(self, x_gn, metric: str = "pearson") -> "DistMatrix":
