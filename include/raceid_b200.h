@@ -55,6 +55,9 @@ double rid_ctx_last_ms(const rid_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 long long rid_ctx_launches(const rid_ctx *ctx);
 
+/* The row block [row0,row1) of an N x N matrix that rank `rank` of `world` owns (pure host function). */
+int rid_shard_rows(int N, int rank, int world, int *row0, int *row1);
+
 /* Measurement hooks (bench.py): per-kernel CUDA-event timing on the library's own stream.
  * kind: 0 Gram/DMMA distance kernel (work = flops), 1 SWAP scan, 2 BUILD scan, 3 grouped column sums (W.k, medoids,
  * silhouette), 4 prep (work = algorithmic bytes; traffic = bytes requested from memory). */

@@ -173,6 +173,8 @@ struct GramParams {
     const double *xraw; // euclid fallback: == Z
     int G;
     double inv_step;    // 1/step
+    int sym;            // 1: grid covers only tiles with col-tile >= row-tile; the mirror tile is written too
+    int tiles;          // tiles per dimension (sym)
 };
 
 __device__ __forceinline__ u32 quantise_corr(double r, double inv_step)
@@ -189,7 +191,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
     double *Bs = smem + GM_STAGES * GM_BM * GM_PITCH;    // [stage][128][20]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3; // 2 x 4 warps
-    const int bm = blockIdx.y, bn = blockIdx.x;
+    int bm = blockIdx.y, bn = blockIdx.x;
+    if (P.sym) {
+        // linear index over the upper triangle (row-major): t = bm*T - bm(bm-1)/2 + (bn - bm)
+        const long long T = P.tiles, t = blockIdx.x;
+        long long b = (long long)((2.0 * T + 1.0 - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)t)) * 0.5);
+        while (b > 0 && b * T - b * (b - 1) / 2 > t) --b;
+        while ((b + 1) * T - (b + 1) * b / 2 <= t) ++b;
+        bm = (int)b;
+        bn = (int)(t - (b * T - b * (b - 1) / 2) + b);
+    }
     const size_t a_row0 = (size_t)P.row0 + (size_t)bm * GM_BM; // global cell index of the tile's first row
     const size_t b_row0 = (size_t)bn * GM_BN;
     const int nslab = P.Gp / GM_BK;
@@ -245,21 +256,26 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
     cp_async_wait<0>();
 
     // epilogue: c0 -> (row = lane/4, col = 2*(lane%4)), c1 -> col+1
+    const bool mirror = P.sym && bn != bm;
+    u32 *stage = reinterpret_cast<u32 *>(smem); // [128][129] u32 = 66 KB, reuses the (drained) pipeline buffers
+    if (mirror) __syncthreads();                // every warp is done reading the last slab
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int lrow = bm * GM_BM + wm * 64 + i * 8 + (lane >> 2);
-        if (lrow >= P.nloc) continue;
+        const int trow = wm * 64 + i * 8 + (lane >> 2);
+        const int lrow = bm * GM_BM + trow;
+        const bool row_ok = lrow < P.nloc;
         const int grow = P.row0 + lrow;
-        const bool zr = P.zero_var[grow];
+        const bool zr = row_ok ? P.zero_var[grow] : false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int gcol = bn * GM_BN + wn * 32 + j * 8 + 2 * (lane & 3);
+            const int tcol = wn * 32 + j * 8 + 2 * (lane & 3);
+            const int gcol = bn * GM_BN + tcol;
             u32 q[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int cc = gcol + e;
                 u32 v;
-                if (cc >= P.N) {
+                if (cc >= P.N || !row_ok) {
                     v = 0u;
                 } else if (cc == grow) {
                     v = zr ? RID_Q_NA : 0u; // diagonal: exactly 0 (1 - 1), NA for a zero-variance cell
@@ -281,7 +297,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
                 }
                 q[e] = v;
             }
-            *reinterpret_cast<uint2 *>(P.D + (size_t)lrow * P.ld + gcol) = make_uint2(q[0], q[1]);
+            if (row_ok) *reinterpret_cast<uint2 *>(P.D + (size_t)lrow * P.ld + gcol) = make_uint2(q[0], q[1]);
+            if (mirror) {
+                stage[trow * 129 + tcol] = q[0];
+                stage[trow * 129 + tcol + 1] = q[1];
+            }
+        }
+    }
+    if (mirror) {
+        // D is symmetric: the same values, transposed, are the tile (bn, bm).  Column reads of the padded staging
+        // tile are bank-conflict free; every warp store is 128 contiguous bytes.
+        __syncthreads();
+        for (int c = warp; c < GM_BN; c += GM_THREADS / 32) {
+            const int mrow = bn * GM_BN + c; // row of the mirror tile (a column of this tile)
+            if (mrow >= P.nloc) break;
+            u32 *dst = P.D + (size_t)mrow * P.ld + (size_t)bm * GM_BM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = stage[(lane + 32 * i) * 129 + c];
         }
     }
 }
@@ -331,6 +363,17 @@ static void shard_rows(int N, int rank, int world, int *r0, int *r1)
     long long a = std::min<long long>((long long)rank * per, N), b = std::min<long long>(a + per, N);
     *r0 = (int)a;
     *r1 = (int)b;
+}
+
+// host-only: the row block rank `rank` of `world` owns (no GPU needed; the N>1 CPU tests check it)
+extern "C" int rid_shard_rows(int N, int rank, int world, int *row0, int *row1)
+{
+    if (N < 1 || world < 1 || rank < 0 || rank >= world || !row0 || !row1) {
+        rid_set_error("rid_shard_rows: bad arguments");
+        return RID_ERR_ARG;
+    }
+    shard_rows(N, rank, world, row0, row1);
+    return RID_OK;
 }
 
 static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
@@ -453,13 +496,20 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         P.Z = Z; P.Gp = Gp; P.N = N; P.row0 = dm->row0; P.nloc = dm->row1 - dm->row0; P.D = dm->D; P.ld = dm->ld;
         P.zero_var = zv; P.euclid = metric == RID_EUCLIDEAN; P.nrm2 = nrm2; P.xraw = Z; P.G = G;
         P.inv_step = 1.0 / dm->step;
+        // one GPU owns every row: compute only the tiles on or above the diagonal and mirror them (half the flops)
+        P.sym = ctx->world == 1 ? 1 : 0;
+        P.tiles = (int)(Np / GM_BN);
         if (P.nloc > 0) {
             DCHK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
             dim3 grid((unsigned)(Np / GM_BN), (unsigned)((P.nloc + GM_BM - 1) / GM_BM));
+            if (P.sym) grid = dim3((unsigned)((long long)P.tiles * (P.tiles + 1) / 2), 1u);
             cudaEvent_t pe = rid_prof_begin(ctx);
             LAUNCH(ctx, k_gram_dmma, grid, GM_THREADS, GM_SMEM, P);
-            // algorithmic flops: 2 * (owned rows) * N * G
-            rid_prof_end(ctx, pe, RID_PROF_GRAM, 2.0 * (double)P.nloc * (double)N * (double)G, (double)P.nloc * dm->ld * 4.0);
+            // work: flops actually issued (tiles computed x 2*128*128*G); the symmetric path issues about half of
+            // the algorithmic 2*N*N*G and must not be credited with the tiles it did not compute
+            double tiles_done = P.sym ? (double)P.tiles * (P.tiles + 1) / 2.0
+                                      : (double)(Np / GM_BN) * (double)((P.nloc + GM_BM - 1) / GM_BM);
+            rid_prof_end(ctx, pe, RID_PROF_GRAM, tiles_done * 2.0 * GM_BM * GM_BN * (double)G, (double)P.nloc * dm->ld * 4.0);
             DCHK(cudaGetLastError());
         }
     }

@@ -71,6 +71,8 @@ struct PamWs {
     double *sil = nullptr; // [N]
     double *dscratch = nullptr; // [8]
     PamState *state = nullptr;
+    int *chg_count = nullptr; // rows whose cap changed in the last BUILD step
+    int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
     std::vector<int> h_subset, h_rows, h_rows_pos, h_pos_of;
@@ -79,7 +81,8 @@ struct PamWs {
 static void ws_free_groups(PamWs *w)
 {
     cudaFree(w->med); cudaFree(w->medpos); cudaFree(w->hist); cudaFree(w->grp_sum); cudaFree(w->grp_cnt);
-    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc);
+    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc); cudaFree(w->chg_hist);
+    w->chg_hist = nullptr;
     w->med = w->medpos = w->hist = w->grp_cnt = w->grp_arg = nullptr;
     w->grp_sum = w->grp_min = w->acc = nullptr;
 }
@@ -90,7 +93,7 @@ void rid_pam_ws_free(PamWs *w)
     cudaFree(w->subset); cudaFree(w->pos_of); cudaFree(w->is_med); cudaFree(w->lab_pos);
     cudaFree(w->rows); cudaFree(w->rows_pos); cudaFree(w->capP); cudaFree(w->capQ); cudaFree(w->grp);
     cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
-    cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state);
+    cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state); cudaFree(w->chg_count);
     ws_free_groups(w);
     delete w;
 }
@@ -124,6 +127,7 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->sil, N * sizeof(double)));
         RID_CUDA(cudaMalloc(&w->dscratch, 8 * sizeof(double)));
         RID_CUDA(cudaMalloc(&w->state, sizeof(PamState)));
+        RID_CUDA(cudaMalloc(&w->chg_count, sizeof(int)));
     }
     if (k > w->kcap) {
         ws_free_groups(w);
@@ -135,6 +139,7 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->grp_cnt, kc * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->grp_min, kc * sizeof(u64)));
         RID_CUDA(cudaMalloc(&w->grp_arg, kc * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->chg_hist, kc * sizeof(int)));
         cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * w->ld) * sizeof(u64));
         if (e != cudaSuccess) {
             rid_set_error("out of device memory for %d group accumulators", kc);
@@ -210,87 +215,102 @@ __device__ __forceinline__ void red_add_u64(u64 *p, u64 v)
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <bool WITH_Q, int FLUSH>
+// MODE 0: SP[h] += sum_j min(d, capP_j)                                   (BUILD step 0)
+// MODE 1: MODE 0 plus AQ[g_j][h] += min(d, capQ_j) - min(d, capP_j)       (SWAP, grouped column sums)
+// MODE 2: only AQ[g_j][h] += min(d, capQ_j) - min(d, capP_j)              (incremental BUILD: capQ = old, capP = new cap)
+// A CTA owns 512 columns and walks row chunks blockIdx.y, blockIdx.y + gridDim.y, ...; the number of rows may live on
+// the device (nrows_dev), so the host never has to read it back.
+template <int MODE, int FLUSH>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ s_row,
        const u32 *__restrict__ s_capP, const u32 *__restrict__ s_capQ, const int *__restrict__ s_grp, int nrows,
-       int rows_per_cta, u64 *__restrict__ SP, u64 *__restrict__ AQ, const PamState *st, int check_done)
+       const int *__restrict__ nrows_dev, int rows_per_chunk, u64 *__restrict__ SP, u64 *__restrict__ AQ,
+       const PamState *st, int check_done)
 {
     if (check_done && st->done) return;
+    constexpr bool WITH_P = MODE != 2, WITH_Q = MODE != 0;
     __shared__ int sh_row[SCAN_MAXROWS];
     __shared__ u32 sh_cp[SCAN_MAXROWS];
     __shared__ u32 sh_cq[SCAN_MAXROWS];
     __shared__ int sh_g[SCAN_MAXROWS];
 
-    const int r_begin = blockIdx.y * rows_per_cta;
-    const int nr = min(nrows - r_begin, rows_per_cta);
-    if (nr <= 0) return;
-    const int nr8 = (nr + 7) & ~7;
-    for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
-        bool ok = i < nr;
-        int src = r_begin + (ok ? i : nr - 1);
-        sh_row[i] = ok ? s_row[src] - row0 : -1;
-        sh_cp[i] = ok ? s_capP[src] : 0u;
-        if (WITH_Q) {
-            sh_cq[i] = ok ? s_capQ[src] : 0u;
-            sh_g[i] = s_grp[src];
-        }
-    }
-    __syncthreads();
+    const int n = nrows_dev ? *nrows_dev : nrows;
     const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
-    if (col >= ld) return;
+    const bool active = col < ld;
     const u32 *base = D + col;
 
     u64 accP[4] = {0, 0, 0, 0}, accQ[4] = {0, 0, 0, 0};
     u32 p32[4] = {0, 0, 0, 0}, q32[4] = {0, 0, 0, 0};
-    int cur_g = WITH_Q ? sh_g[0] : 0;
+    int cur_g = -1;
+    bool any = false;
 
-    for (int r = 0; r < nr8; r += 8) {
-        uint4 d[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int lr = sh_row[r + u];
-            d[u] = lr >= 0 ? ld_stream(base + (size_t)lr * ld) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const u32 cp = sh_cp[r + u];
+    for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < n; chunk += gridDim.y) {
+        const int r_begin = chunk * rows_per_chunk;
+        const int nr = min(n - r_begin, rows_per_chunk);
+        const int nr8 = (nr + 7) & ~7;
+        __syncthreads(); // everyone is done with the previous chunk's shared arrays
+        for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
+            bool ok = i < nr;
+            int src = r_begin + (ok ? i : nr - 1);
+            sh_row[i] = ok ? s_row[src] - row0 : -1;
+            sh_cp[i] = ok ? s_capP[src] : 0u;
             if (WITH_Q) {
-                const int g = sh_g[r + u];
-                if (g != cur_g) { // uniform across the CTA
+                sh_cq[i] = ok ? s_capQ[src] : 0u;
+                sh_g[i] = s_grp[src];
+            }
+        }
+        __syncthreads();
+        if (!active) continue;
+        any = true;
+        if (WITH_Q && cur_g < 0) cur_g = sh_g[0];
+        for (int r = 0; r < nr8; r += 8) {
+            uint4 d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int lr = sh_row[r + u];
+                d[u] = lr >= 0 ? ld_stream(base + (size_t)lr * ld) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u32 cp = sh_cp[r + u];
+                if (WITH_Q) {
+                    const int g = sh_g[r + u];
+                    if (g != cur_g) { // uniform across the CTA
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (WITH_P) { accP[c] += p32[c]; p32[c] = 0; }
+                            accQ[c] += q32[c]; q32[c] = 0;
+                            red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
+                            accQ[c] = 0;
+                        }
+                        cur_g = g;
+                    }
+                    const u32 cq = sh_cq[r + u];
+                    u32 p, q;
+                    p = min(d[u].x, cp); q = min(d[u].x, cq); if (WITH_P) p32[0] += p; q32[0] += q - p;
+                    p = min(d[u].y, cp); q = min(d[u].y, cq); if (WITH_P) p32[1] += p; q32[1] += q - p;
+                    p = min(d[u].z, cp); q = min(d[u].z, cq); if (WITH_P) p32[2] += p; q32[2] += q - p;
+                    p = min(d[u].w, cp); q = min(d[u].w, cq); if (WITH_P) p32[3] += p; q32[3] += q - p;
+                } else {
+                    p32[0] += min(d[u].x, cp);
+                    p32[1] += min(d[u].y, cp);
+                    p32[2] += min(d[u].z, cp);
+                    p32[3] += min(d[u].w, cp);
+                }
+                if ((u % FLUSH) == FLUSH - 1) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        accP[c] += p32[c]; p32[c] = 0;
-                        accQ[c] += q32[c]; q32[c] = 0;
-                        red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
-                        accQ[c] = 0;
+                        if (WITH_P) { accP[c] += p32[c]; p32[c] = 0; }
+                        if (WITH_Q) { accQ[c] += q32[c]; q32[c] = 0; }
                     }
-                    cur_g = g;
-                }
-                const u32 cq = sh_cq[r + u];
-                u32 p, q;
-                p = min(d[u].x, cp); q = min(d[u].x, cq); p32[0] += p; q32[0] += q - p;
-                p = min(d[u].y, cp); q = min(d[u].y, cq); p32[1] += p; q32[1] += q - p;
-                p = min(d[u].z, cp); q = min(d[u].z, cq); p32[2] += p; q32[2] += q - p;
-                p = min(d[u].w, cp); q = min(d[u].w, cq); p32[3] += p; q32[3] += q - p;
-            } else {
-                p32[0] += min(d[u].x, cp);
-                p32[1] += min(d[u].y, cp);
-                p32[2] += min(d[u].z, cp);
-                p32[3] += min(d[u].w, cp);
-            }
-            if ((u % FLUSH) == FLUSH - 1) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    accP[c] += p32[c]; p32[c] = 0;
-                    if (WITH_Q) { accQ[c] += q32[c]; q32[c] = 0; }
                 }
             }
         }
     }
+    if (!any) return;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        red_add_u64(SP + col + c, accP[c]);
+        if (WITH_P) red_add_u64(SP + col + c, accP[c]);
         if (WITH_Q) red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
     }
 }
@@ -502,15 +522,33 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
     }
 }
 
-// after BUILD picked medoid `best_h`: dnearest_j = min(dnearest_j, D[j][best_h])
+// after BUILD picked medoid `best_h`: dnearest_j = min(dnearest_j, D[j][best_h]).  Rows whose cap changed are appended
+// (old cap, new cap) to the delta list: the next BUILD step only has to rescan those rows,
+//      SP_new[h] = SP_old[h] - sum_{changed j} ( min(D[j][h], old_j) - min(D[j][h], new_j) ).
 __global__ void k_build_update(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ rows,
-                               int nls, u32 *capP, const PamState *st)
+                               int nls, u32 *capP, const PamState *st, int *chg_count, int *c_row, u32 *c_new,
+                               u32 *c_old, int *c_grp)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nls) {
         u32 d = D[(size_t)(rows[t] - row0) * ld + st->best_h];
-        if (d < capP[t]) capP[t] = d;
+        u32 old = capP[t];
+        if (d < old) {
+            capP[t] = d;
+            int i = atomicAdd(chg_count, 1);
+            c_row[i] = rows[t];
+            c_new[i] = d;
+            c_old[i] = old;
+            c_grp[i] = 0;
+        }
     }
+}
+
+// SP[h] -= delta[h]   (delta = AQ group 0 of the incremental BUILD pass, already all-reduced)
+__global__ void k_sp_sub(u64 *SP, const u64 *__restrict__ delta, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) SP[i] -= delta[i];
 }
 
 __global__ void k_capture_td_build(PamState *st, const u64 *acc) { st->td_build = acc[0]; }
@@ -677,32 +715,33 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
     return RID_OK;
 }
 
-template <bool WITH_Q>
+// nrows_ub: upper bound of the row count known on the host (grid sizing); nrows_dev: optional exact count on the
+// device.  work_rows: rows to credit in the roofline accounting (<0: nrows_ub).
+template <int MODE>
 static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP, const u32 *capQ, const int *grp,
-                       int check_done, int prof_kind)
+                       int nrows_ub, const int *nrows_dev, int check_done, int prof_kind)
 {
     rid_ctx *ctx = dm->ctx;
-    if (w->nls == 0) return RID_OK;
+    if (nrows_ub <= 0) return RID_OK;
     int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
-    int want_ctas = ctx->sm_count * 16;
-    int chunks_needed = std::max(1, (want_ctas + strips - 1) / strips);
-    int rpc = (w->nls + chunks_needed - 1) / chunks_needed;
+    int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
+    int rpc = (nrows_ub + want_y - 1) / want_y;
     rpc = (rpc + 7) & ~7;
     rpc = std::min(std::max(rpc, 8), SCAN_MAXROWS);
-    int chunks = (w->nls + rpc - 1) / rpc;
-    dim3 grid(strips, chunks);
+    int chunks = (nrows_ub + rpc - 1) / rpc;
+    dim3 grid(strips, std::min(chunks, want_y * 2));
     u64 *SP = w->acc + 4, *AQ = SP + w->ld;
-    // algorithmic bytes: every distance of the (owned rows x subset) block once; traffic: whole owned rows are read
+    // algorithmic bytes: every distance of the (rows x subset) block once; traffic: whole rows are read
     cudaEvent_t pe = rid_prof_begin(ctx);
-    auto scan8 = k_scan<WITH_Q, 8>;
-    auto scan2 = k_scan<WITH_Q, 2>;
+    auto scan8 = k_scan<MODE, 8>;
+    auto scan2 = k_scan<MODE, 2>;
     if (dm->bits <= 28)
-        LAUNCH(ctx, scan8, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, w->nls, rpc, SP, AQ,
-               w->state, check_done);
+        LAUNCH(ctx, scan8, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, nrows_ub, nrows_dev,
+               rpc, SP, AQ, w->state, check_done);
     else
-        LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, w->nls, rpc, SP, AQ,
-               w->state, check_done);
-    rid_prof_end(ctx, pe, prof_kind, (double)w->nls * (double)w->m * 4.0, (double)w->nls * (double)w->ld * 4.0);
+        LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, nrows_ub, nrows_dev,
+               rpc, SP, AQ, w->state, check_done);
+    rid_prof_end(ctx, pe, prof_kind, (double)nrows_ub * (double)w->m * 4.0, (double)nrows_ub * (double)w->ld * 4.0);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -717,21 +756,51 @@ static int zero_acc(rid_dmat *dm, PamWs *w, int ngroups, int check_done)
     return RID_OK;
 }
 
-// BUILD: add medoids until `k` are chosen (continues from state.nmed; caps must be current)
+// BUILD: k greedy picks.  Step 0 is one full pass (SP[h] = sum_j D[j][h]); every later step rescans only the rows whose
+// nearest-medoid distance just dropped (about N/(s+1) of them) and corrects SP in place: ~N*H_k row reads instead of
+// N*k, with bit-identical picks because all sums are exact integers.
 static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
 {
     rid_ctx *ctx = dm->ctx;
+    u64 *SP = w->acc + 4, *AQ0 = SP + w->ld;
+    auto sel_build = k_select<true>;
+    const size_t prof_start = ctx->prof.size();
     for (int s = k_from; s < k_to; ++s) {
-        RID_TRY(zero_acc(dm, w, 0, 0));
-        RID_TRY((launch_scan<false>(dm, w, w->rows, w->capP, nullptr, nullptr, 0, RID_PROF_SCAN_BUILD)));
-        RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
-        auto sel_build = k_select<true>;
-        LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med,
-               w->medpos, w->is_med, w->blockbest, w->state, 0);
+        if (s == 0) {
+            RID_TRY(zero_acc(dm, w, 0, 0));
+            RID_TRY((launch_scan<0>(dm, w, w->rows, w->capP, nullptr, nullptr, w->nls, nullptr, 0, RID_PROF_SCAN_BUILD)));
+            RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
+        } else {
+            RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream));
+            RID_TRY((launch_scan<2>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, w->chg_count, 0,
+                                    RID_PROF_SCAN_BUILD)));
+            RID_TRY(rid_allreduce_u64(ctx, AQ0, w->ld));
+            LAUNCH(ctx, k_sp_sub, nblk((int)w->ld, 256), 256, 0, SP, AQ0, w->ld);
+        }
+        LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
+               w->is_med, w->blockbest, w->state, 0);
+        RID_CUDA(cudaMemsetAsync(w->chg_count, 0, sizeof(int), ctx->stream));
         if (w->nls)
             LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, dm->D, dm->ld, dm->row0, w->rows, w->nls, w->capP,
-                   w->state);
+                   w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
+        if (ctx->prof_on)
+            RID_CUDA(cudaMemcpyAsync(w->chg_hist + s, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         RID_CUDA(cudaGetLastError());
+    }
+    if (ctx->prof_on && k_to > k_from) {
+        // credit the incremental passes with the rows they really rescanned
+        std::vector<int> hist(k_to);
+        RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)k_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
+        int s = k_from;
+        for (size_t i = prof_start; i < ctx->prof.size(); ++i) {
+            if (ctx->prof[i].kind != RID_PROF_SCAN_BUILD) continue;
+            if (s > 0) {
+                ctx->prof[i].work = (double)hist[s - 1] * (double)w->m * 4.0;
+                ctx->prof[i].traffic = (double)hist[s - 1] * (double)w->ld * 4.0;
+            }
+            ++s;
+        }
     }
     return RID_OK;
 }
@@ -797,7 +866,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
             if (k < 2) break;
             {
                 RID_TRY(sort_rows_by_group(dm, w, k, chk));
-                RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, chk, RID_PROF_SCAN_SWAP)));
+                RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, chk, RID_PROF_SCAN_SWAP)));
                 RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
                 auto sel_swap = k_select<false>;
                 LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
@@ -839,7 +908,7 @@ static int grouped_colsums(rid_dmat *dm, PamWs *w, int k)
         LAUNCH(ctx, k_groups_from_labels, nblk(w->nls, 256), 256, 0, w->rows_pos, w->nls, w->lab_pos, w->capP, w->capQ,
                w->grp, w->hist);
     RID_TRY(sort_rows_by_group(dm, w, k, 0));
-    RID_TRY((launch_scan<true>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, 0, RID_PROF_SCAN_GROUP)));
+    RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, 0, RID_PROF_SCAN_GROUP)));
     RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
     return RID_OK;
 }

@@ -19,7 +19,7 @@ METRIC_CODES = {"pearson": 0, "spearman": 1, "logpearson": 2, "euclidean": 3}
 SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
-    "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms",
+    "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp",
 ]
 
@@ -54,6 +54,7 @@ def load() -> C.CDLL:
     L.rid_ctx_last_ms.restype = C.c_double
     L.rid_ctx_launches.argtypes = [vp]
     L.rid_ctx_launches.restype = C.c_longlong
+    L.rid_shard_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rid_ctx_profile.argtypes = [vp, C.c_int]
     L.rid_ctx_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -88,6 +89,13 @@ def _p(a):
 
 def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def shard_rows(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Row block [row0, row1) owned by `rank` (host-only helper of the library)."""
+    a, b = C.c_int(), C.c_int()
+    _check(load().rid_shard_rows(n, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def nccl_unique_id() -> bytes:

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Turns ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+  launches CSV (--metrics gpu__time_duration.sum)  -> per-kernel totals and shares of the step
+  .ncu-rep (--set full)                             -> the handful of metrics the roofline argument needs
+Usage: python scripts/ncu_summary.py launches <csv> <out.txt> | rep <file.ncu-rep> <out.txt>"""
+import csv
+import re
+import subprocess
+import sys
+from collections import defaultdict
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block", "launch__waves_per_multiprocessor",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "memory_l1_wavefronts_shared", "memory_l1_wavefronts_shared_ideal"]
+
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 5]
+    hdr = rows[0]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    iu = hdr.index("Metric Unit")
+    tot = defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[iv].replace(",", ""))
+        except ValueError:
+            continue
+        u = r[iu]
+        ms = v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6)
+        name = re.sub(r"\(.*", "", r[ik]).strip()
+        tot[name][0] += 1
+        tot[name][1] += ms
+    total = sum(v[1] for v in tot.values())
+    with open(out, "w") as f:
+        f.write(f"# per-kernel totals from {path} (ncu gpu__time_duration.sum; cold-cache, serialised launches: compare SHARES)\n")
+        f.write(f"# total {total:.3f} ms over {sum(v[0] for v in tot.values())} launches\n")
+        f.write(f"{'kernel':60s} {'launches':>9s} {'ms':>12s} {'share':>8s} {'avg_ms':>10s}\n")
+        for k, (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:60]:60s} {n:9d} {ms:12.3f} {ms / total:8.4f} {ms / n:10.4f}\n")
+
+
+def rep(path, out):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write(f"# selected metrics from {path} (ncu --set full --clock-control none)\n")
+        for r in rows[2:]:
+            f.write(f"\n## {r[hdr.index('Kernel Name')][:120]}  grid={r[hdr.index('Grid Size')]} block={r[hdr.index('Block Size')]}\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"{k:90s} {r[i]:>22s} {units[i]}\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
