@@ -149,7 +149,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "200", "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "500", "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:

@@ -50,7 +50,24 @@ struct rid_ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
     cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // freed large device buffers kept for reuse (a 40 GB cudaMalloc/cudaFree pair per compdist() costs ~0.3 s)
+    struct PoolBuf { void *p; size_t bytes; };
+    std::vector<PoolBuf> pool;
+    // peer distance-matrix shards mapped through CUDA IPC (multi-rank symmetric Gram kernel)
+    struct IpcMap { unsigned char handle[64]; void *ptr; };
+    std::vector<IpcMap> ipc;
+    void *scratch = nullptr; // small device scratch (barriers, handle exchange)
 };
+
+// Collect the device pointers of every rank's buffer (peers mapped with CUDA IPC).  peers[rank] = mine.
+// Returns RID_OK with *all_ok = 1 only if every rank could map every peer.
+int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok);
+int rid_barrier(rid_ctx *ctx);
+
+// cudaMalloc/cudaFree through the context's reuse pool (exact-size match)
+cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes);
+void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes);
+void rid_pool_trim(rid_ctx *ctx);
 
 // kinds for rid_ctx_profile_get
 enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,

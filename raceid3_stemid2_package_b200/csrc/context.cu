@@ -26,6 +26,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -44,6 +45,7 @@ static NcclApi *nccl_api()
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
         }
     }
@@ -136,6 +138,10 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     if (!ctx) return RID_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &m : ctx->ipc) cudaIpcCloseMemHandle(m.ptr);
+    ctx->ipc.clear();
+    rid_pool_trim(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -170,6 +176,37 @@ int rid_time_end(rid_ctx *ctx)
     RID_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
     return RID_OK;
+}
+
+// ---- device buffer reuse pool ---------------------------------------------------------------------------
+cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
+{
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (ctx->pool[i].bytes == bytes) {
+            *p = ctx->pool[i].p;
+            ctx->pool.erase(ctx->pool.begin() + i);
+            return cudaSuccess;
+        }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !ctx->pool.empty()) {
+        cudaGetLastError();
+        rid_pool_trim(ctx); // give cached buffers back and retry
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes < ((size_t)16 << 20) || ctx->pool.size() >= 6) { cudaFree(p); return; }
+    ctx->pool.push_back({p, bytes});
+}
+
+void rid_pool_trim(rid_ctx *ctx)
+{
+    for (auto &b : ctx->pool) cudaFree(b.p);
+    ctx->pool.clear();
 }
 
 // ---- per-kernel profiling -------------------------------------------------------------------------------
@@ -268,3 +305,69 @@ static int allreduce(rid_ctx *ctx, void *buf, size_t count, ncclDataType_t dt)
 int rid_allreduce_u64(rid_ctx *ctx, u64 *buf, size_t count) { return allreduce(ctx, buf, count, ncclUint64); }
 int rid_allreduce_i32(rid_ctx *ctx, int *buf, size_t count) { return allreduce(ctx, buf, count, ncclInt32); }
 int rid_allreduce_f64(rid_ctx *ctx, double *buf, size_t count) { return allreduce(ctx, buf, count, ncclFloat64); }
+
+// ---- peer memory (CUDA IPC) ---------------------------------------------------------------------------------
+static int ensure_scratch(rid_ctx *ctx)
+{
+    if (!ctx->scratch) {
+        RID_CUDA(cudaMalloc(&ctx->scratch, 4096));
+        RID_CUDA(cudaMemset(ctx->scratch, 0, 4096));
+    }
+    return RID_OK;
+}
+
+int rid_barrier(rid_ctx *ctx)
+{
+    if (ctx->world == 1) return RID_OK;
+    RID_TRY(ensure_scratch(ctx));
+    return rid_allreduce_i32(ctx, (int *)ctx->scratch + 512, 1);
+}
+
+int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok)
+{
+    *all_ok = 0;
+    for (int r = 0; r < ctx->world; ++r) peers[r] = nullptr;
+    peers[ctx->rank] = mine;
+    if (ctx->world == 1) { *all_ok = 1; return RID_OK; }
+    if (ctx->world > 16 || !ctx->nccl->AllGather) return RID_OK;
+    RID_TRY(ensure_scratch(ctx));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    cudaIpcMemHandle_t h;
+    int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+    if (!ok) { cudaGetLastError(); memset(&h, 0, sizeof(h)); }
+    unsigned char *dev = (unsigned char *)ctx->scratch; // world * 64 bytes <= 1024
+    RID_CUDA(cudaMemcpyAsync(dev + 64 * ctx->rank, &h, 64, cudaMemcpyHostToDevice, ctx->stream));
+    RID_NCCL(ctx->nccl, ctx->nccl->AllGather(dev + 64 * ctx->rank, dev, 64, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    unsigned char all[16 * 64];
+    RID_CUDA(cudaMemcpyAsync(all, dev, 64 * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < ctx->world && ok; ++r) {
+        if (r == ctx->rank) continue;
+        void *ptr = nullptr;
+        for (auto &m : ctx->ipc)
+            if (memcmp(m.handle, all + 64 * r, 64) == 0) { ptr = m.ptr; break; }
+        if (!ptr) {
+            cudaIpcMemHandle_t ph;
+            memcpy(&ph, all + 64 * r, 64);
+            if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            rid_ctx::IpcMap m;
+            memcpy(m.handle, all + 64 * r, 64);
+            m.ptr = ptr;
+            ctx->ipc.push_back(m);
+        }
+        peers[r] = ptr;
+    }
+    // every rank must take the same path
+    int *flag = (int *)ctx->scratch + 600;
+    RID_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_TRY(rid_allreduce_i32(ctx, flag, 1));
+    int sum = 0;
+    RID_CUDA(cudaMemcpyAsync(&sum, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    *all_ok = sum == ctx->world ? 1 : 0;
+    return RID_OK;
+}

@@ -175,6 +175,10 @@ struct GramParams {
     double inv_step;    // 1/step
     int sym;            // 1: grid covers only tiles with col-tile >= row-tile; the mirror tile is written too
     int tiles;          // tiles per dimension (sym)
+    // multi-rank symmetric mode: every off-diagonal tile pair is computed by exactly one of its two owners, which
+    // stores the tile into its own shard and the transposed tile straight into the peer's shard over NVLink
+    int psym, world, rank, tiles_per_rank;
+    u32 *peer[16];
 };
 
 __device__ __forceinline__ u32 quantise_corr(double r, double inv_step)
@@ -200,6 +204,20 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
         while ((b + 1) * T - (b + 1) * b / 2 <= t) ++b;
         bm = (int)b;
         bn = (int)(t - (b * T - b * (b - 1) / 2) + b);
+    }
+    int tile_i = bm;      // global tile row
+    int owner_j = P.rank; // rank owning tile row `bn` (the mirror's destination)
+    if (P.psym) {
+        tile_i = P.row0 / GM_BM + bm;
+        owner_j = min(bn / P.tiles_per_rank, P.world - 1);
+        bool mine;
+        if (owner_j == P.rank) {
+            mine = bn >= tile_i;
+        } else {
+            const int d = (owner_j - P.rank + P.world) % P.world;
+            mine = 2 * d < P.world || (2 * d == P.world && ((tile_i + bn) & 1) == (P.rank < owner_j ? 0 : 1));
+        }
+        if (!mine) return;
     }
     const size_t a_row0 = (size_t)P.row0 + (size_t)bm * GM_BM; // global cell index of the tile's first row
     const size_t b_row0 = (size_t)bn * GM_BN;
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
     cp_async_wait<0>();
 
     // epilogue: c0 -> (row = lane/4, col = 2*(lane%4)), c1 -> col+1
-    const bool mirror = P.sym && bn != bm;
+    const bool mirror = (P.sym || P.psym) && bn != tile_i;
     u32 *stage = reinterpret_cast<u32 *>(smem); // [128][129] u32 = 66 KB, reuses the (drained) pipeline buffers
     if (mirror) __syncthreads();                // every warp is done reading the last slab
 #pragma unroll
@@ -308,10 +326,12 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
         // D is symmetric: the same values, transposed, are the tile (bn, bm).  Column reads of the padded staging
         // tile are bank-conflict free; every warp store is 128 contiguous bytes.
         __syncthreads();
+        u32 *mbase = P.psym ? P.peer[owner_j] : P.D;
+        const int mrow0 = P.psym ? owner_j * P.tiles_per_rank * GM_BM : 0; // first row of the destination shard
         for (int c = warp; c < GM_BN; c += GM_THREADS / 32) {
-            const int mrow = bn * GM_BN + c; // row of the mirror tile (a column of this tile)
-            if (mrow >= P.nloc) break;
-            u32 *dst = P.D + (size_t)mrow * P.ld + (size_t)bm * GM_BM;
+            const int mrow = bn * GM_BN + c; // global row of the mirror tile (a column of this tile)
+            if (mrow >= P.N) break;
+            u32 *dst = mbase + (size_t)(mrow - mrow0) * P.ld + (size_t)tile_i * GM_BM;
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = stage[(lane + 32 * i) * 129 + c];
         }
@@ -384,7 +404,7 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
     shard_rows(N, ctx->rank, ctx->world, &dm->row0, &dm->row1);
     dm->ld = round_up((size_t)N, 128);
     size_t nloc = (size_t)(dm->row1 - dm->row0);
-    cudaError_t e = cudaMalloc(&dm->D, std::max<size_t>(nloc, 1) * dm->ld * sizeof(u32));
+    cudaError_t e = rid_pool_alloc(ctx, (void **)&dm->D, std::max<size_t>(nloc, 1) * dm->ld * sizeof(u32));
     if (e != cudaSuccess) {
         rid_set_error("cannot allocate %.2f GB for the distance-matrix shard (%zu x %zu): %s",
                       (double)nloc * dm->ld * 4 / 1e9, nloc, dm->ld, cudaGetErrorString(e));
@@ -401,7 +421,7 @@ extern "C" int rid_dmat_free(rid_dmat *dm)
     cudaSetDevice(dm->ctx->device);
     cudaStreamSynchronize(dm->ctx->stream);
     rid_pam_ws_free(dm->ws);
-    cudaFree(dm->D);
+    rid_pool_free(dm->ctx, dm->D, std::max<size_t>((size_t)(dm->row1 - dm->row0), 1) * dm->ld * sizeof(u32));
     delete dm;
     return RID_OK;
 }
@@ -438,9 +458,10 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     double *xd = nullptr, *Z = nullptr, *nrm2 = nullptr, *dmax = nullptr;
     unsigned char *zv = nullptr;
     int rc = RID_OK;
+    const size_t z_bytes = Np * (size_t)Gp * sizeof(double), x_bytes = (size_t)G * N * sizeof(double);
     auto fail = [&](int code) {
-        cudaFree(Z); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
-        if (!x_on_device) cudaFree(xd);
+        rid_pool_free(ctx, Z, z_bytes); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+        if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
         rid_dmat_free(dm);
         return code;
     };
@@ -452,7 +473,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
             return fail(RID_ERR_CUDA);                                                                     \
         }                                                                                                  \
     } while (0)
-    DCHK(cudaMalloc(&Z, Np * (size_t)Gp * sizeof(double)));
+    DCHK(rid_pool_alloc(ctx, (void **)&Z, z_bytes));
     DCHK(cudaMalloc(&nrm2, Np * sizeof(double)));
     DCHK(cudaMalloc(&zv, Np));
     DCHK(cudaMalloc(&dmax, sizeof(double)));
@@ -460,7 +481,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     if (x_on_device) {
         xd = const_cast<double *>(x);
     } else {
-        DCHK(cudaMalloc(&xd, (size_t)G * N * sizeof(double)));
+        DCHK(rid_pool_alloc(ctx, (void **)&xd, x_bytes));
         DCHK(cudaMemcpyAsync(xd, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     DCHK(cudaMemsetAsync(Z, 0, Np * (size_t)Gp * sizeof(double), ctx->stream));
@@ -499,6 +520,38 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         // one GPU owns every row: compute only the tiles on or above the diagonal and mirror them (half the flops)
         P.sym = ctx->world == 1 ? 1 : 0;
         P.tiles = (int)(Np / GM_BN);
+        P.psym = 0; P.world = ctx->world; P.rank = ctx->rank;
+        {
+            int r0, r1;
+            shard_rows(N, 0, ctx->world, &r0, &r1);
+            P.tiles_per_rank = std::max(1, (int)(round_up((size_t)std::max(r1 - r0, 1), GM_BM) / GM_BM));
+        }
+        for (int r = 0; r < 16; ++r) P.peer[r] = nullptr;
+        if (ctx->world > 1) {
+            void *peers[16];
+            int all_ok = 0;
+            if ((rc = rid_peer_pointers(ctx, dm->D, peers, &all_ok)) != RID_OK) return fail(rc);
+            if (all_ok) {
+                P.psym = 1;
+                for (int r = 0; r < ctx->world; ++r) P.peer[r] = (u32 *)peers[r];
+            }
+        }
+        double tiles_done = 0.0;
+        {
+            const int tloc = (P.nloc + GM_BM - 1) / GM_BM;
+            if (P.sym) tiles_done = (double)P.tiles * (P.tiles + 1) / 2.0;
+            else if (!P.psym) tiles_done = (double)P.tiles * tloc;
+            else
+                for (int bm = 0; bm < tloc; ++bm)
+                    for (int bn = 0; bn < P.tiles; ++bn) {
+                        int ti = P.row0 / GM_BM + bm, oj = std::min(bn / P.tiles_per_rank, P.world - 1);
+                        if (oj == P.rank) tiles_done += bn >= ti;
+                        else {
+                            int d = (oj - P.rank + P.world) % P.world;
+                            tiles_done += (2 * d < P.world || (2 * d == P.world && ((ti + bn) & 1) == (P.rank < oj ? 0 : 1)));
+                        }
+                    }
+        }
         if (P.nloc > 0) {
             DCHK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
             dim3 grid((unsigned)(Np / GM_BN), (unsigned)((P.nloc + GM_BM - 1) / GM_BM));
@@ -507,11 +560,11 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
             LAUNCH(ctx, k_gram_dmma, grid, GM_THREADS, GM_SMEM, P);
             // work: flops actually issued (tiles computed x 2*128*128*G); the symmetric path issues about half of
             // the algorithmic 2*N*N*G and must not be credited with the tiles it did not compute
-            double tiles_done = P.sym ? (double)P.tiles * (P.tiles + 1) / 2.0
-                                      : (double)(Np / GM_BN) * (double)((P.nloc + GM_BM - 1) / GM_BM);
             rid_prof_end(ctx, pe, RID_PROF_GRAM, tiles_done * 2.0 * GM_BM * GM_BN * (double)G, (double)P.nloc * dm->ld * 4.0);
             DCHK(cudaGetLastError());
         }
+        // peers have written mirror tiles into this rank's shard: nobody may go on before every kernel is done
+        if (P.psym && (rc = rid_barrier(ctx)) != RID_OK) return fail(rc);
     }
     // zero-variance cells (cor(): NA + warning "the standard deviation is zero")
     dm->na_cell.assign(N, 0);
@@ -521,8 +574,8 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     for (int i = 0; i < N; ++i) nz += dm->na_cell[i];
     dm->has_na = nz > 0;
     if (n_zero_var) *n_zero_var = nz;
-    cudaFree(Z); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
-    if (!x_on_device) cudaFree(xd);
+    rid_pool_free(ctx, Z, z_bytes); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+    if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
     *out = dm;
     return RID_OK;
 #undef DCHK
