@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
 __global__ void k_import(const double *__restrict__ src, int N, int row0, int nloc, u32 *__restrict__ D, size_t ld,
                          double inv_step, int *has_na)
 {
-    size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int lrow = blockIdx.y;
+    size_t col = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
+    int lrow = blockIdx.x;
     if (col >= ld || lrow >= nloc) return;
     int r = row0 + lrow;
     u32 v = 0u;
@@ -618,7 +618,7 @@ extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat
     cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
     int nloc = dm->row1 - dm->row0;
     if (nloc > 0) {
-        dim3 grid((unsigned)((dm->ld + 255) / 256), (unsigned)nloc);
+        dim3 grid((unsigned)nloc, (unsigned)((dm->ld + 255) / 256));
         LAUNCH(ctx, k_import, grid, 256, 0, src, N, dm->row0, nloc, dm->D, dm->ld, 1.0 / dm->step, flag);
     }
     int h = 0;
@@ -651,7 +651,7 @@ extern "C" int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cid
     double *d_out = nullptr;
     int *d_r = nullptr, *d_c = nullptr;
     // export in column panels to bound the staging buffer
-    const int panel = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / ((size_t)m * 8)));
+    const int panel = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)n, 65535), ((size_t)256 << 20) / ((size_t)m * 8)));
     RID_CUDA(cudaMalloc(&d_out, (size_t)m * panel * sizeof(double)));
     if (ridx) { RID_CUDA(cudaMalloc(&d_r, (size_t)m * sizeof(int))); RID_CUDA(cudaMemcpy(d_r, ridx, (size_t)m * sizeof(int), cudaMemcpyHostToDevice)); }
     if (cidx) { RID_CUDA(cudaMalloc(&d_c, (size_t)n * sizeof(int))); RID_CUDA(cudaMemcpy(d_c, cidx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice)); }

@@ -71,11 +71,19 @@ struct PamWs {
     double *sil = nullptr; // [N]
     double *dscratch = nullptr; // [8]
     PamState *state = nullptr;
+    // active matrix view: the rank's shard of D, or a compacted copy D[subset, subset] (columns in sorted-cell order)
+    const u32 *mat = nullptr;
+    bool compact = false;
+    u32 *cbuf = nullptr;        // compact copy (owned subset rows x ldc)
+    size_t cbuf_bytes = 0;
+    int *subset_cells = nullptr; // [N] cell by position (== subset unless compact)
+    int *colmap = nullptr;       // [N] compact column of a cell, or -1
+    int *src_rows = nullptr;     // [nloc] shard row of each owned subset row (compaction source)
     int *chg_count = nullptr; // rows whose cap changed in the last BUILD step
     int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
-    std::vector<int> h_subset, h_rows, h_rows_pos, h_pos_of;
+    std::vector<int> h_subset, h_rows, h_rows_pos, h_pos_of, h_cells, h_colmap, h_src;
 };
 
 static void ws_free_groups(PamWs *w)
@@ -90,10 +98,12 @@ static void ws_free_groups(PamWs *w)
 void rid_pam_ws_free(PamWs *w)
 {
     if (!w) return;
+    if (w->cbuf) cudaFree(w->cbuf);
     cudaFree(w->subset); cudaFree(w->pos_of); cudaFree(w->is_med); cudaFree(w->lab_pos);
     cudaFree(w->rows); cudaFree(w->rows_pos); cudaFree(w->capP); cudaFree(w->capQ); cudaFree(w->grp);
     cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
     cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state); cudaFree(w->chg_count);
+    cudaFree(w->subset_cells); cudaFree(w->colmap); cudaFree(w->src_rows);
     ws_free_groups(w);
     delete w;
 }
@@ -128,6 +138,9 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->dscratch, 8 * sizeof(double)));
         RID_CUDA(cudaMalloc(&w->state, sizeof(PamState)));
         RID_CUDA(cudaMalloc(&w->chg_count, sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->subset_cells, N * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->colmap, N * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->src_rows, nl * sizeof(int)));
     }
     if (k > w->kcap) {
         ws_free_groups(w);
@@ -140,7 +153,7 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->grp_min, kc * sizeof(u64)));
         RID_CUDA(cudaMalloc(&w->grp_arg, kc * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->chg_hist, kc * sizeof(int)));
-        cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * w->ld) * sizeof(u64));
+        cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * dm->ld) * sizeof(u64));
         if (e != cudaSuccess) {
             rid_set_error("out of device memory for %d group accumulators", kc);
             return RID_ERR_NOMEM;
@@ -222,7 +235,7 @@ __device__ __forceinline__ void red_add_u64(u64 *p, u64 v)
 // the device (nrows_dev), so the host never has to read it back.
 template <int MODE, int FLUSH>
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ s_row,
+k_scan(const u32 *__restrict__ D, size_t ld, const int *__restrict__ s_row,
        const u32 *__restrict__ s_capP, const u32 *__restrict__ s_capQ, const int *__restrict__ s_grp, int nrows,
        const int *__restrict__ nrows_dev, int rows_per_chunk, u64 *__restrict__ SP, u64 *__restrict__ AQ,
        const PamState *st, int check_done)
@@ -252,7 +265,7 @@ k_scan(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ s
         for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
             bool ok = i < nr;
             int src = r_begin + (ok ? i : nr - 1);
-            sh_row[i] = ok ? s_row[src] - row0 : -1;
+            sh_row[i] = ok ? s_row[src] : -1;
             sh_cp[i] = ok ? s_capP[src] : 0u;
             if (WITH_Q) {
                 sh_cq[i] = ok ? s_capQ[src] : 0u;
@@ -317,7 +330,7 @@ k_scan(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ s
 
 // nearest / second-nearest medoid of every owned subset row (cstat + the dysma/dysmb refresh of bswap):
 // strict '<' with medoids visited in index (position) order => the lowest-position medoid wins ties.
-__global__ void k_assign(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ rows, int nls,
+__global__ void k_assign(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows, int nls,
                          const int *__restrict__ med, const int *__restrict__ medpos, int k, u32 *capP, u32 *capQ,
                          int *grp, int *hist, u64 *td, const PamState *st, int check_done)
 {
@@ -329,7 +342,7 @@ __global__ void k_assign(const u32 *__restrict__ D, size_t ld, int row0, const i
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     u64 mine = 0;
     if (t < nls) {
-        const u32 *row = D + (size_t)(rows[t] - row0) * ld;
+        const u32 *row = D + (size_t)rows[t] * ld;
         u32 d1 = 0xFFFFFFFFu, d2 = 0xFFFFFFFFu;
         int g = -1, gp = INT_MAX;
         for (int c = 0; c < k; ++c) {
@@ -525,13 +538,13 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
 // after BUILD picked medoid `best_h`: dnearest_j = min(dnearest_j, D[j][best_h]).  Rows whose cap changed are appended
 // (old cap, new cap) to the delta list: the next BUILD step only has to rescan those rows,
 //      SP_new[h] = SP_old[h] - sum_{changed j} ( min(D[j][h], old_j) - min(D[j][h], new_j) ).
-__global__ void k_build_update(const u32 *__restrict__ D, size_t ld, int row0, const int *__restrict__ rows,
+__global__ void k_build_update(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows,
                                int nls, u32 *capP, const PamState *st, int *chg_count, int *c_row, u32 *c_new,
                                u32 *c_old, int *c_grp)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nls) {
-        u32 d = D[(size_t)(rows[t] - row0) * ld + st->best_h];
+        u32 d = D[(size_t)rows[t] * ld + st->best_h];
         u32 old = capP[t];
         if (d < old) {
             capP[t] = d;
@@ -640,6 +653,29 @@ __global__ void k_refresh(const u32 *__restrict__ D, size_t ld, int row0, int nl
     }
 }
 
+// D[subset, subset] -> compact copy.  One source row per blockIdx.y; a thread reads 4 consecutive source columns and
+// writes the ones that belong to the subset at their compact column (colmap is monotone, so writes stay nearly
+// coalesced).  Pad columns [m, ldc) are zeroed.
+__global__ void k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows,
+                          const int *__restrict__ colmap, int ncols, u32 *__restrict__ out, size_t ldc, int m)
+{
+    const int t = blockIdx.x;
+    const size_t col = ((size_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    u32 *orow = out + (size_t)t * ldc;
+    if (col < ld) {
+        const uint4 d = ld_stream(D + (size_t)src_rows[t] * ld + col);
+        const u32 v[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (col + c < (size_t)ncols) {
+                int sidx = colmap[col + c];
+                if (sidx >= 0) orow[sidx] = v[c];
+            }
+    }
+    if (blockIdx.y == 0)
+        for (size_t c = (size_t)m + threadIdx.x; c < ldc; c += blockDim.x) orow[c] = 0u;
+}
+
 // clusterboot: k x k contingency table of (c1 label of the resampled cell, bootstrap label)
 __global__ void k_contingency(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
                               const int *__restrict__ part_slot /* [N] c1 group by cell */, int k, int *tab)
@@ -670,8 +706,12 @@ static int pam_check_na(rid_dmat *dm, const int *subset, int m)
     return RID_OK;
 }
 
-// install the subset (positions -> cells) and the list of owned subset rows
-static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
+// Install the subset (positions -> cells) and the list of owned subset rows.
+// want_compact: the caller will make many passes (PAM): if the subset is a proper subset, copy D[subset, subset] into
+// a compact matrix once (columns in sorted-cell order; tie-breaking still follows the POSITIONS) so that every later
+// pass reads only the distances it needs instead of whole rows of the resident matrix.
+#define RID_COMPACT_MIN_BYTES ((size_t)1 << 20)
+static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool want_compact)
 {
     rid_ctx *ctx = dm->ctx;
     int N = dm->N;
@@ -679,7 +719,7 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
         rid_set_error("subset size %d out of range", m);
         return RID_ERR_ARG;
     }
-    w->h_subset.resize(m);
+    w->h_cells.resize(m);
     w->h_pos_of.assign(N, -1);
     for (int p = 0; p < m; ++p) {
         int h = subset ? subset[p] : p;
@@ -691,20 +731,86 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m)
             rid_set_error("subset holds cell %d twice", h);
             return RID_ERR_ARG;
         }
-        w->h_subset[p] = h;
+        w->h_cells[p] = h;
         w->h_pos_of[h] = p;
     }
-    w->h_rows.clear();
-    w->h_rows_pos.clear();
-    // owned rows in cell order (any order works: all sums are exact integers)
+    w->m = m;
+    bool compact = want_compact && m < N && (size_t)m * (size_t)m * sizeof(u32) >= RID_COMPACT_MIN_BYTES;
+    // owned subset rows in cell order (any order works: all sums are exact integers)
+    w->h_rows.clear(); w->h_rows_pos.clear(); w->h_src.clear();
+    if (compact) {
+        // compact column of a cell = its rank among the subset's cells
+        w->h_colmap.assign(N, -1);
+        int sidx = 0;
+        for (int h = 0; h < N; ++h)
+            if (w->h_pos_of[h] >= 0) w->h_colmap[h] = sidx++;
+        for (int h = dm->row0; h < dm->row1; ++h)
+            if (w->h_pos_of[h] >= 0) {
+                w->h_rows.push_back((int)w->h_src.size()); // compact local row = running index
+                w->h_src.push_back(h - dm->row0);
+                w->h_rows_pos.push_back(w->h_pos_of[h]);
+            }
+        w->nls = (int)w->h_rows.size();
+        const size_t ldc = round_up((size_t)m, 128);
+        const size_t need = std::max<size_t>((size_t)w->nls, 1) * ldc * sizeof(u32);
+        int ok = 1;
+        if (need > w->cbuf_bytes) {
+            if (w->cbuf) { cudaFree(w->cbuf); w->cbuf = nullptr; w->cbuf_bytes = 0; }
+            size_t want = need + need / 32; // head-room: bootstrap resamples differ by a fraction of a percent
+            if (cudaMalloc(&w->cbuf, want) == cudaSuccess) w->cbuf_bytes = want;
+            else { cudaGetLastError(); ok = 0; }
+        }
+        if (ctx->world > 1) { // every rank must take the same path
+            int *flag = (int *)w->dscratch;
+            int miss = ok ? 0 : 1;
+            RID_CUDA(cudaMemcpyAsync(flag, &miss, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_TRY(rid_allreduce_i32(ctx, flag, 1));
+            RID_CUDA(cudaMemcpyAsync(&miss, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            RID_CUDA(cudaStreamSynchronize(ctx->stream));
+            ok = miss == 0;
+        }
+        if (!ok) compact = false; // not enough memory somewhere: scan the resident matrix through the row list
+        else {
+            // positions index compact columns: subset[p] = compact column, pos_of[compact column] = p
+            w->h_subset.resize(m);
+            std::vector<int> pos_c(m);
+            for (int p = 0; p < m; ++p) {
+                int c = w->h_colmap[w->h_cells[p]];
+                w->h_subset[p] = c;
+                pos_c[c] = p;
+            }
+            RID_CUDA(cudaMemcpyAsync(w->subset, w->h_subset.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->pos_of, pos_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->colmap, w->h_colmap.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->subset_cells, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            if (w->nls) {
+                RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->src_rows, w->h_src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                dim3 grid((unsigned)w->nls, (unsigned)((dm->ld + 511) / 512));
+                LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->colmap, N, w->cbuf, ldc, m);
+                RID_CUDA(cudaGetLastError());
+            }
+            RID_CUDA(cudaStreamSynchronize(ctx->stream)); // pos_c is a local
+            w->mat = w->cbuf;
+            w->ld = ldc;
+            w->compact = true;
+            return RID_OK;
+        }
+    }
+    // view mode: rows of the resident shard through a row list, columns masked by the candidate list
+    w->compact = false;
+    w->mat = dm->D;
+    w->ld = dm->ld;
+    w->h_rows.clear(); w->h_rows_pos.clear();
     for (int h = dm->row0; h < dm->row1; ++h)
         if (w->h_pos_of[h] >= 0) {
-            w->h_rows.push_back(h);
+            w->h_rows.push_back(h - dm->row0);
             w->h_rows_pos.push_back(w->h_pos_of[h]);
         }
-    w->m = m;
     w->nls = (int)w->h_rows.size();
-    RID_CUDA(cudaMemcpyAsync(w->subset, w->h_subset.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->subset, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->subset_cells, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(w->pos_of, w->h_pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (w->nls) {
         RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -736,10 +842,10 @@ static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP,
     auto scan8 = k_scan<MODE, 8>;
     auto scan2 = k_scan<MODE, 2>;
     if (dm->bits <= 28)
-        LAUNCH(ctx, scan8, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, nrows_ub, nrows_dev,
+        LAUNCH(ctx, scan8, grid, SCAN_THREADS, 0, w->mat, w->ld, rows, capP, capQ, grp, nrows_ub, nrows_dev,
                rpc, SP, AQ, w->state, check_done);
     else
-        LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, dm->D, dm->ld, dm->row0, rows, capP, capQ, grp, nrows_ub, nrows_dev,
+        LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, w->mat, w->ld, rows, capP, capQ, grp, nrows_ub, nrows_dev,
                rpc, SP, AQ, w->state, check_done);
     rid_prof_end(ctx, pe, prof_kind, (double)nrows_ub * (double)w->m * 4.0, (double)nrows_ub * (double)w->ld * 4.0);
     RID_CUDA(cudaGetLastError());
@@ -781,7 +887,7 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
                w->is_med, w->blockbest, w->state, 0);
         RID_CUDA(cudaMemsetAsync(w->chg_count, 0, sizeof(int), ctx->stream));
         if (w->nls)
-            LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, dm->D, dm->ld, dm->row0, w->rows, w->nls, w->capP,
+            LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, w->mat, w->ld, w->rows, w->nls, w->capP,
                    w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
         if (ctx->prof_on)
             RID_CUDA(cudaMemcpyAsync(w->chg_hist + s, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -821,7 +927,7 @@ static int pam_assign(rid_dmat *dm, PamWs *w, int k, int check_done)
     rid_ctx *ctx = dm->ctx;
     RID_TRY(zero_acc(dm, w, k, check_done));
     if (w->nls)
-        LAUNCH(ctx, k_assign, nblk(w->nls, 128), 128, 2 * k * sizeof(int), dm->D, dm->ld, dm->row0, w->rows, w->nls,
+        LAUNCH(ctx, k_assign, nblk(w->nls, 128), 128, 2 * k * sizeof(int), w->mat, w->ld, w->rows, w->nls,
                w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, w->acc, w->state, check_done);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
@@ -964,7 +1070,7 @@ static int pam_run(rid_dmat *dm, const int *subset, int m, int k, int *medoids, 
     RID_TRY(pam_check_na(dm, subset, m));
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
-    RID_TRY(pam_set_subset(dm, w, subset, m));
+    RID_TRY(pam_set_subset(dm, w, subset, m, true));
     RID_TRY(pam_begin(dm, w));
     RID_TRY(pam_build(dm, w, 0, k));
     PamState hs;
@@ -1019,7 +1125,7 @@ extern "C" int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int
     RID_TRY(pam_check_na(dm, subset, m));
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
-    RID_TRY(pam_set_subset(dm, w, subset, m));
+    RID_TRY(pam_set_subset(dm, w, subset, m, false));
     std::vector<int> g(m);
     for (int p = 0; p < m; ++p) {
         if (labels[p] < 1 || labels[p] > k) { rid_set_error("label %d out of 1..%d", labels[p], k); return RID_ERR_ARG; }
@@ -1043,7 +1149,7 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
     rid_ctx *ctx = dm->ctx;
     PamWs *w;
     RID_TRY(ws_get(dm, Kmax, &w));
-    RID_TRY(pam_set_subset(dm, w, subset, m));
+    RID_TRY(pam_set_subset(dm, w, subset, m, true));
     RID_TRY(rid_time_begin(ctx));
     RID_TRY(pam_begin(dm, w));
     RID_TRY(pam_build(dm, w, 0, Kmax));
@@ -1106,7 +1212,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         if (rc != RID_OK) break;
         // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
         cudaMemsetAsync(d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
-        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, d_part, k, d_tab);
+        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset_cells, w->lab_pos, m, d_part, k, d_tab);
         if (cudaMemcpyAsync(tab.data(), d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             rid_set_error("rid_clusterboot: contingency table copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1155,7 +1261,7 @@ extern "C" int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_i
     RID_TRY(pam_check_na(dm, sub.data(), m));
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
-    RID_TRY(pam_set_subset(dm, w, sub.data(), m));
+    RID_TRY(pam_set_subset(dm, w, sub.data(), m, false));
     RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
     RID_TRY(rid_time_begin(ctx));
     RID_TRY(grouped_colsums(dm, w, k));

@@ -96,6 +96,30 @@ def test_pam_identical_to_oracle_on_device_matrix(ctx, oracle, metric):
     dm.free()
 
 
+def test_subset_runs_use_compact_copy_and_stay_identical(ctx, oracle):
+    """Subsets large enough (m*m*4 >= 1 MB) are clustered on a compacted copy D[subset, subset] whose columns are in
+    sorted-cell order; positions (the order of `subset`) must still drive every tie-break and the label numbering."""
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+
+    x, _ = _features(seed=21, G=120, N=1500, C=5)
+    x[:, 700] = x[:, 3]
+    x[:, 1400] = x[:, 3]  # duplicate cells => exact ties inside the subset
+    dm = ctx.dist(x, "pearson")
+    Dg = dm.as_matrix()
+    samples = bootstrap_samples(1500, 3, 4242)
+    for sub in samples:
+        assert len(sub) * len(sub) * 4 >= (1 << 20)
+        for k in (1, 3, 6):
+            _check_pam(dm, oracle, Dg, k, subset=sub)
+    rev = np.arange(1499, -1, -1)[::1][:1100].astype(np.int32)  # descending cell order: position != sorted order
+    _check_pam(dm, oracle, Dg, 4, subset=rev)
+    assert np.max(np.abs(dm.gap_sweep(7, subset=rev) - oracle.gap_sweep(Dg, 7, subset=rev))) < 1e-12
+    r = dm.clusterboot(5, samples)
+    ro = oracle.clusterboot(Dg, 5, samples)
+    assert np.array_equal(r["partition"], ro["partition"]) and np.array_equal(r["bootresult"], ro["bootresult"])
+    dm.free()
+
+
 def test_pam_matches_fp64_reference_path(ctx, oracle):
     """Against the oracle's OWN double-precision distances (the reference's path end to end): ARI = 1 and the
     same medoids on well-separated data."""
