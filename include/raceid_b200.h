@@ -60,9 +60,13 @@ int rid_shard_rows(int N, int rank, int world, int *row0, int *row1);
 
 /* Measurement hooks (bench.py): per-kernel CUDA-event timing on the library's own stream.
  * kind: 0 Gram/DMMA distance kernel (work = flops), 1 SWAP scan, 2 BUILD scan, 3 grouped column sums (W.k, medoids,
- * silhouette), 4 prep (work = algorithmic bytes; traffic = bytes requested from memory). */
+ * silhouette), 4 prep, 5 subset compaction (work = algorithmic bytes; traffic = bytes requested from memory). */
 int rid_ctx_profile(rid_ctx *ctx, int enable);
 int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, double *ms, double *work, double *traffic);
+/* Ceilings measured on the spot: issue rate of the FP64 tensor pipe (DMMA m8n8k4), TFLOP/s, and a read-only
+ * 128-bit streaming loop over `gib` GiB of HBM, GB/s (MEASURED_PEAKS.json holds a copy figure and a bf16 figure only). */
+int rid_measure_dmma_peak(rid_ctx *ctx, double *tflops);
+int rid_measure_read_peak(rid_ctx *ctx, double gib, double *gbs);
 /* user events on the library's stream, slots 0..7 */
 int rid_ctx_event_record(rid_ctx *ctx, int slot);
 int rid_ctx_event_elapsed_ms(rid_ctx *ctx, int slot_a, int slot_b, double *ms);

@@ -71,7 +71,7 @@ void rid_pool_trim(rid_ctx *ctx);
 
 // kinds for rid_ctx_profile_get
 enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,
-       RID_PROF_NKINDS = 5 };
+       RID_PROF_COMPACT = 5, RID_PROF_NKINDS = 6 };
 
 // RAII-less helpers: call prof_begin right before the launch and prof_end right after it.
 cudaEvent_t rid_prof_begin(rid_ctx *ctx);
@@ -102,4 +102,4 @@ static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 int rid_time_begin(rid_ctx *ctx);
 int rid_time_end(rid_ctx *ctx);
 
-void rid_pam_ws_free(PamWs *ws);
+void rid_pam_ws_free(PamWs *ws, rid_ctx *ctx);

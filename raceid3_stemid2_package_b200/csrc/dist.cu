@@ -420,7 +420,7 @@ extern "C" int rid_dmat_free(rid_dmat *dm)
     if (!dm) return RID_OK;
     cudaSetDevice(dm->ctx->device);
     cudaStreamSynchronize(dm->ctx->stream);
-    rid_pam_ws_free(dm->ws);
+    rid_pam_ws_free(dm->ws, dm->ctx);
     rid_pool_free(dm->ctx, dm->D, std::max<size_t>((size_t)(dm->row1 - dm->row0), 1) * dm->ld * sizeof(u32));
     delete dm;
     return RID_OK;
@@ -673,4 +673,88 @@ extern "C" int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cid
     else if (rc == RID_ERR_CUDA) rid_set_error("rid_dmat_sub: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(d_out); cudaFree(d_r); cudaFree(d_c);
     return rc;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// measurement hooks: the ceilings the two hot kernels are held against, measured on the spot
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters, double seed)
+{
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = seed * i; c[i][1] = seed; }
+    double a = seed + threadIdx.x, b = seed * 0.5 + blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s; // never true: keeps the loop alive
+}
+
+// issue-rate ceiling of the FP64 tensor pipe (mma.sync.m8n8k4.f64), TFLOP/s
+extern "C" int rid_measure_dmma_peak(rid_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    double *out = nullptr;
+    RID_CUDA(cudaMalloc(&out, sizeof(double)));
+    const int iters = 20000, blocks = ctx->sm_count * 2;
+    k_dmma_peak<<<blocks, 256, 0, ctx->stream>>>(out, 2000, 1e-3); // warm-up
+    cudaEvent_t a, b;
+    RID_CUDA(cudaEventCreate(&a));
+    RID_CUDA(cudaEventCreate(&b));
+    RID_CUDA(cudaEventRecord(a, ctx->stream));
+    k_dmma_peak<<<blocks, 256, 0, ctx->stream>>>(out, iters, 1e-3);
+    RID_CUDA(cudaEventRecord(b, ctx->stream));
+    RID_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    RID_CUDA(cudaEventElapsedTime(&ms, a, b));
+    *tflops = (double)blocks * 8.0 /*warps*/ * iters * 8.0 * 512.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    return RID_OK;
+}
+
+__global__ void __launch_bounds__(256) k_read_peak(const uint4 *__restrict__ p, size_t n16, unsigned *out)
+{
+    unsigned acc = 0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        uint4 v0 = p[i], v1 = p[i + stride], v2 = p[i + 2 * stride], v3 = p[i + 3 * stride];
+        acc += v0.x ^ v0.y ^ v0.z ^ v0.w ^ v1.x ^ v1.y ^ v1.z ^ v1.w ^ v2.x ^ v2.y ^ v2.z ^ v2.w ^ v3.x ^ v3.y ^ v3.z ^ v3.w;
+    }
+    for (; i < n16; i += stride) { uint4 v = p[i]; acc += v.x ^ v.y ^ v.z ^ v.w; }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+// read-only streaming ceiling over `gib` GiB of device memory (a plain grid-stride 128-bit load loop), GB/s
+extern "C" int rid_measure_read_peak(rid_ctx *ctx, double gib, double *gbs)
+{
+    if (!ctx || !gbs || gib <= 0) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)(gib * 1024.0 * 1024.0 * 1024.0) / 16 * 16;
+    void *buf = nullptr;
+    unsigned *out = nullptr;
+    if (rid_pool_alloc(ctx, &buf, bytes) != cudaSuccess) { rid_set_error("rid_measure_read_peak: out of memory"); return RID_ERR_NOMEM; }
+    RID_CUDA(cudaMalloc(&out, sizeof(unsigned)));
+    RID_CUDA(cudaMemsetAsync(buf, 1, bytes, ctx->stream));
+    cudaEvent_t a, b;
+    RID_CUDA(cudaEventCreate(&a));
+    RID_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        RID_CUDA(cudaEventRecord(a, ctx->stream));
+        k_read_peak<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>((const uint4 *)buf, bytes / 16, out);
+        RID_CUDA(cudaEventRecord(b, ctx->stream));
+        RID_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        RID_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *gbs = (double)bytes / (best * 1e-3) / 1e9;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    rid_pool_free(ctx, buf, bytes);
+    return RID_OK;
 }

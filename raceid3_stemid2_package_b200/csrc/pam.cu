@@ -95,10 +95,10 @@ static void ws_free_groups(PamWs *w)
     w->grp_sum = w->grp_min = w->acc = nullptr;
 }
 
-void rid_pam_ws_free(PamWs *w)
+void rid_pam_ws_free(PamWs *w, rid_ctx *ctx)
 {
+    if (w && w->cbuf) rid_pool_free(ctx, w->cbuf, w->cbuf_bytes);
     if (!w) return;
-    if (w->cbuf) cudaFree(w->cbuf);
     cudaFree(w->subset); cudaFree(w->pos_of); cudaFree(w->is_med); cudaFree(w->lab_pos);
     cudaFree(w->rows); cudaFree(w->rows_pos); cudaFree(w->capP); cudaFree(w->capQ); cudaFree(w->grp);
     cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
@@ -755,9 +755,11 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
         const size_t need = std::max<size_t>((size_t)w->nls, 1) * ldc * sizeof(u32);
         int ok = 1;
         if (need > w->cbuf_bytes) {
-            if (w->cbuf) { cudaFree(w->cbuf); w->cbuf = nullptr; w->cbuf_bytes = 0; }
-            size_t want = need + need / 32; // head-room: bootstrap resamples differ by a fraction of a percent
-            if (cudaMalloc(&w->cbuf, want) == cudaSuccess) w->cbuf_bytes = want;
+            if (w->cbuf) { rid_pool_free(ctx, w->cbuf, w->cbuf_bytes); w->cbuf = nullptr; w->cbuf_bytes = 0; }
+            // head-room (bootstrap resamples differ by a fraction of a percent), rounded so that the context's
+            // exact-size reuse pool hits again on the next clustexp() call
+            size_t want = round_up(need + need / 32, (size_t)256 << 20);
+            if (rid_pool_alloc(ctx, (void **)&w->cbuf, want) == cudaSuccess) w->cbuf_bytes = want;
             else { cudaGetLastError(); ok = 0; }
         }
         if (ctx->world > 1) { // every rank must take the same path
@@ -788,7 +790,10 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
                 RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 RID_CUDA(cudaMemcpyAsync(w->src_rows, w->h_src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 dim3 grid((unsigned)w->nls, (unsigned)((dm->ld + 511) / 512));
+                cudaEvent_t pe = rid_prof_begin(ctx);
                 LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->colmap, N, w->cbuf, ldc, m);
+                rid_prof_end(ctx, pe, RID_PROF_COMPACT, (double)w->nls * ((double)N + (double)m) * 4.0,
+                             (double)w->nls * ((double)dm->ld + (double)ldc) * 4.0);
                 RID_CUDA(cudaGetLastError());
             }
             RID_CUDA(cudaStreamSynchronize(ctx->stream)); // pos_c is a local

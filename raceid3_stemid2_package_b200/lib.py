@@ -19,7 +19,7 @@ METRIC_CODES = {"pearson": 0, "spearman": 1, "logpearson": 2, "euclidean": 3}
 SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
-    "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms",
+    "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp",
 ]
 
@@ -58,6 +58,8 @@ def load() -> C.CDLL:
     L.rid_ctx_profile.argtypes = [vp, C.c_int]
     L.rid_ctx_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.rid_measure_dmma_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.rid_measure_read_peak.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.rid_ctx_event_record.argtypes = [vp, C.c_int]
     L.rid_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rid_dist.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
@@ -135,7 +137,7 @@ class Context:
     def launches(self) -> int:
         return int(load().rid_ctx_launches(self._h))
 
-    PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4}
+    PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4, "compact": 5}
 
     def profile(self, enable: bool = True):
         _check(load().rid_ctx_profile(self._h, 1 if enable else 0))
@@ -145,6 +147,16 @@ class Context:
         _check(load().rid_ctx_profile_get(self._h, self.PROF_KINDS[kind], C.byref(n), C.byref(ms), C.byref(work),
                                           C.byref(tr)))
         return {"launches": n.value, "ms": ms.value, "work": work.value, "traffic": tr.value}
+
+    def measure_dmma_peak(self) -> float:
+        v = C.c_double()
+        _check(load().rid_measure_dmma_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_read_peak(self, gib: float = 8.0) -> float:
+        v = C.c_double()
+        _check(load().rid_measure_read_peak(self._h, gib, C.byref(v)))
+        return v.value
 
     def event_record(self, slot: int):
         _check(load().rid_ctx_event_record(self._h, slot))
