@@ -271,7 +271,7 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ctx.event_elapsed_ms(0, 1)
     launches = ctx.launches - l0
-    prof = {k: ctx.profile_get(k) for k in ("gram", "scan_swap", "scan_build", "scan_group", "prep", "compact")}
+    prof = {k: ctx.profile_get(k) for k in ("gram", "gram_i8", "scan_swap", "scan_build", "scan_group", "prep", "compact")}
     ctx.profile(False)
     clk = clocks.stop()
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
@@ -328,6 +328,21 @@ def main():
                       "algorithmic_flops_per_launch": 2.0 * N * N * G / world,
                       "note": "work = flops actually issued (upper-triangle tiles only; the mirror tile is a store)",
                       "share_of_step": gm["ms"] / step_ms_total})
+    g8 = prof["gram_i8"]
+    if g8["launches"]:
+        ach = g8["work"] / (g8["ms"] * 1e-3) / 1e12
+        bf16 = float(peaks.get("bf16_tflops", 1590.0))
+        i8_peak = 2.0 * bf16  # int8 tcgen05 issues at twice the bf16 rate; the bf16 figure is the measured cuBLAS burst
+        roofs.append({"bound": "tensor", "kernel": "k_gram_i8 (tcgen05.mma kind::i8, exact Ozaki-split distance contraction)",
+                      "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": None,
+                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (measured cuBLAS bf16 burst; int8 dense is 2x bf16 "
+                                     "on sm_100: nominal 4500 TOP/s)" if "bf16_tflops" in peaks else
+                                     "2 x fallback 1590 TFLOP/s bf16 (B200_PROFILING.md)",
+                      "launches": g8["launches"], "avg_launch_ms": g8["ms"] / g8["launches"],
+                      "issued_int8_ops_per_launch": g8["work"] / g8["launches"],
+                      "fp64_equivalent_tflops_2N2G": 2.0 * N * N * G * g8["launches"] / (g8["ms"] * 1e-3) / 1e12,
+                      "note": "work = 13 digit products x 2*128*96*Kp per computed tile (tiles touching the upper triangle)",
+                      "share_of_step": g8["ms"] / step_ms_total})
     roofs.sort(key=lambda r: -r["share_of_step"])
     roof = roofs[0] if roofs else None
     detail = {}
@@ -335,7 +350,10 @@ def main():
         if not v["launches"]:
             continue
         d = {"launches": v["launches"], "ms_total": v["ms"], "share_of_step": v["ms"] / step_ms_total}
-        if k == "gram":
+        if k == "gram_i8":
+            d["int8_tops_issued"] = v["work"] / (v["ms"] * 1e-3) / 1e12
+            d["tflops_algorithmic_2N2G"] = 2.0 * N * N * G / world * v["launches"] / (v["ms"] * 1e-3) / 1e12
+        elif k == "gram":
             d["tflops_issued"] = v["work"] / (v["ms"] * 1e-3) / 1e12
             d["tflops_algorithmic_2N2G"] = 2.0 * N * N * G / world * v["launches"] / (v["ms"] * 1e-3) / 1e12
         else:
@@ -360,7 +378,7 @@ def main():
                 "config": {"workload": workload_name(a), "seed": a.seed, "parallelism": f"row-block shard x{world}",
                            "l2": "inputs (distance matrix %.1f GB) larger than L2" % (N * N * 4 / 1e9)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "dist_tflops": detail.get("gram", {}).get("tflops_issued"),
+                "dist_tflops": (detail.get("gram_i8") or detail.get("gram") or {}).get("tflops_algorithmic_2N2G"),
                 "pam_swap_gbs": detail.get("scan_swap", {}).get("algorithmic_gbs"), "detail": detail}
         print(json.dumps(line))
     if dist is not None:

@@ -71,7 +71,7 @@ void rid_pool_trim(rid_ctx *ctx);
 
 // kinds for rid_ctx_profile_get
 enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,
-       RID_PROF_COMPACT = 5, RID_PROF_NKINDS = 6 };
+       RID_PROF_COMPACT = 5, RID_PROF_GRAM_I8 = 6, RID_PROF_NKINDS = 7 };
 
 // RAII-less helpers: call prof_begin right before the launch and prof_end right after it.
 cudaEvent_t rid_prof_begin(rid_ctx *ctx);
@@ -103,3 +103,7 @@ int rid_time_begin(rid_ctx *ctx);
 int rid_time_end(rid_ctx *ctx);
 
 void rid_pam_ws_free(PamWs *ws, rid_ctx *ctx);
+
+// gram_i8.cu: exact int8 tensor-core contraction (single GPU, correlation metrics)
+int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const unsigned char *zero_var, rid_dmat *dm,
+                int *used, double *bound_out);

@@ -512,7 +512,24 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         dm->bits = 28;
         dm->step = ldexp(1.0, -27); // D in [0,2] -> q in [0, 2^28]
     }
+    // exact int8 tensor-core path (tcgen05) for correlation metrics on one GPU; RID_GRAM=f64 forces the FP64 DMMA kernel,
+    // RID_GRAM=i8 makes a fallback an error (tests)
+    bool gram_done = false;
     {
+        const char *mode = getenv("RID_GRAM");
+        const bool want_i8 = metric != RID_EUCLIDEAN && ctx->world == 1 && !(mode && strcmp(mode, "f64") == 0);
+        if (want_i8) {
+            int used = 0;
+            double bound = 0.0;
+            if ((rc = rid_gram_i8(ctx, Z, Gp, G, N, zv, dm, &used, &bound)) != RID_OK) return fail(rc);
+            gram_done = used != 0;
+            if (!gram_done && mode && strcmp(mode, "i8") == 0) {
+                rid_set_error("RID_GRAM=i8 but the int8 path was not taken (a-posteriori bound %.3g)", bound);
+                return fail(RID_ERR_UNSUPPORTED);
+            }
+        }
+    }
+    if (!gram_done) {
         GramParams P;
         P.Z = Z; P.Gp = Gp; P.N = N; P.row0 = dm->row0; P.nloc = dm->row1 - dm->row0; P.D = dm->D; P.ld = dm->ld;
         P.zero_var = zv; P.euclid = metric == RID_EUCLIDEAN; P.nrm2 = nrm2; P.xraw = Z; P.G = G;

@@ -1,0 +1,418 @@
+// gram_i8.cu — the correlation contraction r = Z Z^T on the 5th-generation tensor cores, EXACTLY.
+//
+// tcgen05 has no FP64 kind, and TF32/BF16 kinds accumulate in FP32, which cannot hold |r| <= 1 to 1e-7 over G ~ 3000
+// terms.  Integers can: every row of Z has unit norm, so it is a natural fixed-point operand.  Each row i is scaled by
+// a power of two (max|z| * 2^e_i in [0.496, 0.992]), rounded to a 27-bit integer m_ik = rint(z_ik * 2^(e_i+27)), and split into
+// four balanced radix-128 digits d_s in [-64, 63]  (an "Ozaki split"):  m = sum_s d_s 128^s.  Then
+//      sum_k m_ik m_jk = sum_{s,t} 128^(s+t) * P_st,     P_st = sum_k d_s(i,k) d_t(j,k)
+// and every P_st is an int8 x int8 -> int32 GEMM that `tcgen05.mma.kind::i8` computes without any rounding
+// (G * 64^2 < 2^31).  The five diagonals s+t = 2..6 (13 digit products) are accumulated in five TMEM accumulators; the
+// two lowest diagonals (s+t <= 1) are below 2^-54 * 257 * G * 64^2 and are covered by an a-posteriori bound computed
+// from the actual digit norms (the host falls back to the FP64 DMMA kernel if the bound exceeds 8e-7).
+//
+// Kernel shape: one 128 x 96 output tile per CTA (5 accumulators x 96 columns = 480 of the 512 TMEM columns),
+// K blocks of 128 bytes, two 112 KB shared-memory stages filled by TMA (SWIZZLE_128B, K-major), one elected thread
+// issuing 13 x 4 tcgen05.mma per stage, tcgen05.commit -> mbarrier to recycle stages and to hand the accumulators to
+// the four epilogue warps, which read TMEM with tcgen05.ld, rebuild the 64-bit integer dot product, turn it into the
+// fixed-point distance and store the tile and its mirror image (D is symmetric; only tiles touching the upper
+// triangle are computed).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+#define I8_BM 128
+#define I8_BN 96
+#define I8_BK 128
+#define I8_STAGES 2
+#define I8_A_PLANE (I8_BM * I8_BK)                 // 16384
+#define I8_B_PLANE (I8_BN * I8_BK)                 // 12288
+#define I8_STAGE_BYTES (4 * I8_A_PLANE + 4 * I8_B_PLANE) // 114688
+#define I8_SMEM (I8_STAGES * I8_STAGE_BYTES + 1024)
+#define I8_TMEM_COLS 512
+#define I8_THREADS 256
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (unsigned long long spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1ull << 26)) __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
+// version=1 | layout=SWIZZLE_128B(2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=S32 (2) @4, a=INT8 (1) @7, b=INT8 (1) @10, K-major both,
+// N>>3 @17, M>>4 @24
+#define I8_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_BN >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24))
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+struct I8Params {
+    int N, nkb;
+    u32 *D;
+    size_t ld;
+    int plane_rows; // rows per digit plane in the operand matrix
+    const unsigned char *zero_var;
+    const double *rowscale; // 2^-(e_i+27)
+    double inv_step;
+};
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, I8Params P)
+{
+    const int i0 = blockIdx.y * I8_BM, j0 = blockIdx.x * I8_BN;
+    if (j0 + I8_BN <= i0) return; // tile entirely below the diagonal: its mirror image is written by tile (j,i)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < P.nkb; ++kb) {
+                const int st = kb % I8_STAGES;
+                const uint32_t ph = (kb / I8_STAGES) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1); // passes immediately the first time round
+                uint8_t *sa = smem + (size_t)st * I8_STAGE_BYTES, *sb = sa + 4 * I8_A_PLANE;
+                mbar_expect_tx(&full_bar[st], I8_STAGE_BYTES);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    tma_load_2d(sa + s * I8_A_PLANE, &tmA, kb * I8_BK, s * P.plane_rows + i0, &full_bar[st]);
+                    tma_load_2d(sb + s * I8_B_PLANE, &tmB, kb * I8_BK, s * P.plane_rows + j0, &full_bar[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < P.nkb; ++kb) {
+                const int st = kb % I8_STAGES;
+                const uint32_t ph = (kb / I8_STAGES) & 1;
+                mbar_wait(&full_bar[st], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)st * I8_STAGE_BYTES), sb = sa + 4 * I8_A_PLANE;
+                uint32_t started = 0; // per-diagonal "has been written in this k-block" bits
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (s + t < 2) continue;
+                        const int d = s + t - 2;
+                        const uint64_t ad = umma_desc_sw128(sa + s * I8_A_PLANE), bd = umma_desc_sw128(sb + t * I8_B_PLANE);
+#pragma unroll
+                        for (int kk = 0; kk < I8_BK / 32; ++kk) {
+                            // advancing K inside the 128-byte swizzle atom: +32 bytes = +2 in the (addr >> 4) field
+                            const uint32_t acc = (kb > 0 || ((started >> d) & 1u) || kk > 0) ? 1u : 0u;
+                            umma_i8(tmem_base + (uint32_t)(d * I8_BN), ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), acc);
+                        }
+                        started |= 1u << d;
+                    }
+                umma_commit(&empty_bar[st]); // frees this stage once the MMAs above have read it
+            }
+            umma_commit(&tmem_full_bar);     // all accumulators final
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp - 4;          // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;     // tile row = TMEM lane
+        const int gi = i0 + r;
+        const bool row_ok = gi < P.N;
+        const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
+        const bool zr = row_ok ? P.zero_var[gi] : false;
+        for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+            int a2[16], a3[16], a4[16], a5[16], a6[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld16(ta + 0 * I8_BN, a2);
+            tmem_ld16(ta + 1 * I8_BN, a3);
+            tmem_ld16(ta + 2 * I8_BN, a4);
+            tmem_ld16(ta + 3 * I8_BN, a5);
+            tmem_ld16(ta + 4 * I8_BN, a6);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            u32 qv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int gj = j0 + c0 + c;
+                u32 v = 0u;
+                if (row_ok && gj < P.N) {
+                    if (gj == gi) {
+                        v = zr ? RID_Q_NA : 0u;
+                    } else if (zr || P.zero_var[gj]) {
+                        v = RID_Q_NA;
+                    } else {
+                        long long acc = (long long)a6[c];
+                        acc = acc * 128 + a5[c];
+                        acc = acc * 128 + a4[c];
+                        acc = acc * 128 + a3[c];
+                        acc = acc * 128 + a2[c];
+                        double rr = (double)acc * rs_i * P.rowscale[gj];
+                        rr = fmin(1.0, fmax(-1.0, rr));
+                        v = (u32)__double2ull_rn((1.0 - rr) * P.inv_step);
+                    }
+                }
+                qv[c] = v;
+            }
+            // direct store: 16 consecutive columns of row gi
+            if (row_ok) {
+                u32 *dst = P.D + (size_t)gi * P.ld + j0 + c0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
+            }
+            // mirror store: column gi of rows j0+c0..+15; a warp's 32 lanes write 128 contiguous bytes
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const int gj = j0 + c0 + c;
+                if (gj < P.N && (size_t)gi < P.ld) P.D[(size_t)gj * P.ld + gi] = row_ok ? qv[c] : 0u;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Z (FP64, unit rows) -> four int8 digit planes + per-row scale; statistics for the a-posteriori error bound
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_quant_i8(const double *__restrict__ Z, int Gp_src, int G, int N, int8_t *__restrict__ planes, size_t plane_rows,
+           int Kp, double *__restrict__ rowscale, double *__restrict__ stats /* [4]: max 2^-e*|d0|, 2^-e*|d1|, 2^-e, |z|_1 */)
+{
+    __shared__ double sh[256];
+    const int i = blockIdx.x;
+    const double *z = Z + (size_t)i * Gp_src;
+    double amax = 0.0, l1 = 0.0;
+    for (int k = threadIdx.x; k < G; k += blockDim.x) { double a = fabs(z[k]); amax = fmax(amax, a); l1 += a; }
+    sh[threadIdx.x] = amax;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]); __syncthreads(); }
+    amax = sh[0];
+    __syncthreads();
+    sh[threadIdx.x] = l1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    l1 = sh[0];
+    __syncthreads();
+    int x = 0;
+    double f = 0.0;
+    if (amax > 0.0) f = frexp(amax, &x); // amax = f * 2^x, f in [0.5, 1)
+    // amax * 2^e in [0.496, 0.992]: |m| <= 0.992 * 2^27 fits four balanced radix-128 digits (max 63*(128^4-1)/127)
+    const int e = f > 0.992 ? -x - 1 : -x;
+    const double up = ldexp(1.0, e + 27);
+    double n0 = 0.0, n1 = 0.0;
+    int8_t *p0 = planes + (size_t)i * Kp;
+    const size_t ps = plane_rows * (size_t)Kp;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        long long m = k < G ? llrint(z[k] * up) : 0;
+        int d[4];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            int dd = (int)(((m + 64) % 128 + 128) % 128) - 64; // balanced digit in [-64, 63]
+            d[s] = dd;
+            m = (m - dd) / 128;
+        }
+        d[3] = (int)m;
+        p0[k] = (int8_t)d[0];
+        p0[ps + k] = (int8_t)d[1];
+        p0[2 * ps + k] = (int8_t)d[2];
+        p0[3 * ps + k] = (int8_t)d[3];
+        n0 += (double)d[0] * d[0];
+        n1 += (double)d[1] * d[1];
+    }
+    sh[threadIdx.x] = n0;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    n0 = sh[0];
+    __syncthreads();
+    sh[threadIdx.x] = n1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    n1 = sh[0];
+    if (threadIdx.x == 0) {
+        const double inv2e = ldexp(1.0, -e);
+        rowscale[i] = ldexp(1.0, -(e + 27));
+        // positive doubles order like their bit patterns
+        atomicMax((unsigned long long *)&stats[0], (unsigned long long)__double_as_longlong(sqrt(n0) * inv2e));
+        atomicMax((unsigned long long *)&stats[1], (unsigned long long)__double_as_longlong(sqrt(n1) * inv2e));
+        atomicMax((unsigned long long *)&stats[2], (unsigned long long)__double_as_longlong(inv2e));
+        atomicMax((unsigned long long *)&stats[3], (unsigned long long)__double_as_longlong(l1));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// Runs the exact tensor-core contraction for a single-GPU correlation matrix.  Returns RID_OK and *used = 1 when the
+// matrix was produced, *used = 0 when the caller must use the FP64 DMMA kernel instead (bound not met / unsupported).
+int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const unsigned char *zero_var, rid_dmat *dm,
+                int *used, double *bound_out)
+{
+    *used = 0;
+    PFN_encodeTiled encode = get_encode();
+    if (!encode) return RID_OK;
+    const int Kp = (int)round_up((size_t)G, I8_BK);
+    const int tiles_m = (N + I8_BM - 1) / I8_BM, tiles_n = (N + I8_BN - 1) / I8_BN;
+    const size_t plane_rows = std::max((size_t)tiles_m * I8_BM, (size_t)tiles_n * I8_BN);
+    const size_t planes_bytes = 4 * plane_rows * (size_t)Kp;
+    int8_t *planes = nullptr;
+    double *rowscale = nullptr, *stats = nullptr;
+    if (rid_pool_alloc(ctx, (void **)&planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); return RID_OK; }
+    auto cleanup = [&]() { rid_pool_free(ctx, planes, planes_bytes); cudaFree(rowscale); cudaFree(stats); };
+    if (cudaMalloc(&rowscale, plane_rows * sizeof(double)) != cudaSuccess || cudaMalloc(&stats, 4 * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError(); cleanup(); return RID_OK;
+    }
+    cudaMemsetAsync(planes, 0, planes_bytes, ctx->stream);
+    cudaMemsetAsync(rowscale, 0, plane_rows * sizeof(double), ctx->stream);
+    cudaMemsetAsync(stats, 0, 4 * sizeof(double), ctx->stream);
+    k_quant_i8<<<N, 256, 0, ctx->stream>>>(Z, Gp_src, G, N, planes, plane_rows, Kp, rowscale, stats);
+    ctx->launches++;
+    double h[4];
+    if (cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        rid_set_error("rid_gram_i8: quantisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cleanup();
+        return RID_ERR_CUDA;
+    }
+    // a-posteriori bound on |r - r_exact|:  dropped diagonals (s+t <= 1) by Cauchy-Schwarz on the digit norms, plus the
+    // rounding of z to 27 bits:  2^-54 (256 U0 U1 + U0^2)  +  2^-27 V W1     (U_s = max 2^-e |d_s|, V = max 2^-e, W1 = max |z|_1)
+    const double bound = ldexp(256.0 * h[0] * h[1] + h[0] * h[0], -54) + ldexp(h[2] * h[3], -27);
+    if (bound_out) *bound_out = bound;
+    if (!(bound <= 8e-7)) { cleanup(); return RID_OK; } // + 2^-28 quantisation of D stays under the 1e-6 bar
+
+    CUtensorMap tmA, tmB;
+    cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)(4 * plane_rows)};
+    cuuint64_t gstr[1] = {(cuuint64_t)Kp};
+    cuuint32_t boxA[2] = {I8_BK, I8_BM}, boxB[2] = {I8_BK, I8_BN}, estr[2] = {1, 1};
+    if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        cleanup();
+        return RID_OK;
+    }
+    I8Params P;
+    P.N = N; P.nkb = Kp / I8_BK; P.D = dm->D; P.ld = dm->ld; P.plane_rows = (int)plane_rows; P.zero_var = zero_var;
+    P.rowscale = rowscale; P.inv_step = 1.0 / dm->step;
+    if (cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) {
+        cudaGetLastError(); cleanup(); return RID_OK;
+    }
+    // pad columns [N, ld) of every row are never touched by the tiles: clear them
+    cudaMemset2DAsync(dm->D + N, dm->ld * sizeof(u32), 0, (dm->ld - (size_t)N) * sizeof(u32), (size_t)N, ctx->stream);
+    dim3 grid((unsigned)tiles_n, (unsigned)tiles_m);
+    cudaEvent_t pe = rid_prof_begin(ctx);
+    k_gram_i8<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
+    ctx->launches++;
+    // work: int8 multiply-adds actually issued x 2 (13 digit products per computed tile)
+    double tiles_done = 0;
+    for (int bm = 0; bm < tiles_m; ++bm)
+        for (int bn = 0; bn < tiles_n; ++bn) tiles_done += (bn * I8_BN + I8_BN > bm * I8_BM);
+    rid_prof_end(ctx, pe, RID_PROF_GRAM_I8, tiles_done * 13.0 * 2.0 * I8_BM * I8_BN * (double)Kp, (double)N * dm->ld * 4.0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) {
+        rid_set_error("k_gram_i8 failed: %s", cudaGetErrorString(e));
+        return RID_ERR_CUDA;
+    }
+    *used = 1;
+    return RID_OK;
+}

@@ -74,6 +74,7 @@ struct PamWs {
     // active matrix view: the rank's shard of D, or a compacted copy D[subset, subset] (columns in sorted-cell order)
     const u32 *mat = nullptr;
     bool compact = false;
+    bool sp0_ready = false;     // the compaction pass already left BUILD's step-0 sums in acc
     u32 *cbuf = nullptr;        // compact copy (owned subset rows x ldc)
     size_t cbuf_bytes = 0;
     int *subset_cells = nullptr; // [N] cell by position (== subset unless compact)
@@ -653,27 +654,58 @@ __global__ void k_refresh(const u32 *__restrict__ D, size_t ld, int row0, int nl
     }
 }
 
-// D[subset, subset] -> compact copy.  One source row per blockIdx.y; a thread reads 4 consecutive source columns and
-// writes the ones that belong to the subset at their compact column (colmap is monotone, so writes stay nearly
-// coalesced).  Pad columns [m, ldc) are zeroed.
-__global__ void k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows,
-                          const int *__restrict__ colmap, int ncols, u32 *__restrict__ out, size_t ldc, int m)
+// D[subset, subset] -> compact copy, fused with BUILD's step 0.  A thread owns 4 consecutive COMPACT columns (their
+// source columns are looked up once), walks a chunk of owned subset rows gathering 4 x 8 independent 32-bit loads (the
+// gathers of neighbouring lanes fall into the same sectors, so DRAM sees whole rows streamed once) and writes one
+// aligned 128-bit store per row.  The column sums it keeps are exactly BUILD's first pass:
+// SP0[c] += sum_rows D[row][c].
+#define COMPACT_ROWS 64
+__global__ void __launch_bounds__(128)
+k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows, int nrows,
+          const int *__restrict__ ccells, u32 *__restrict__ out, size_t ldc, int m, u64 *__restrict__ SP0)
 {
-    const int t = blockIdx.x;
-    const size_t col = ((size_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    u32 *orow = out + (size_t)t * ldc;
-    if (col < ld) {
-        const uint4 d = ld_stream(D + (size_t)src_rows[t] * ld + col);
-        const u32 v[4] = {d.x, d.y, d.z, d.w};
+    __shared__ int sh_src[COMPACT_ROWS];
+    const int r0 = blockIdx.x * COMPACT_ROWS;
+    const int nr = min(COMPACT_ROWS, nrows - r0);
+    for (int i = threadIdx.x; i < COMPACT_ROWS; i += blockDim.x) sh_src[i] = i < nr ? src_rows[r0 + i] : 0;
+    __syncthreads();
+    const size_t c0 = ((size_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= ldc) return;
+    int src[4];
+    bool keep[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (col + c < (size_t)ncols) {
-                int sidx = colmap[col + c];
-                if (sidx >= 0) orow[sidx] = v[c];
-            }
+    for (int c = 0; c < 4; ++c) {
+        keep[c] = c0 + c < (size_t)m;
+        src[c] = keep[c] ? ccells[c0 + c] : 0;
     }
-    if (blockIdx.y == 0)
-        for (size_t c = (size_t)m + threadIdx.x; c < ldc; c += blockDim.x) orow[c] = 0u;
+    u64 sum[4] = {0, 0, 0, 0};
+    for (int r = 0; r < nr; r += 8) {
+        u32 v[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const u32 *row = D + (size_t)sh_src[min(r + u, nr - 1)] * ld;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[u][c] = __ldg(row + src[c]);
+        }
+        u32 p32[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r + u < nr) {
+                uint4 o = make_uint4(keep[0] ? v[u][0] : 0u, keep[1] ? v[u][1] : 0u, keep[2] ? v[u][2] : 0u,
+                                     keep[3] ? v[u][3] : 0u);
+                *reinterpret_cast<uint4 *>(out + (size_t)(r0 + r + u) * ldc + c0) = o;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) p32[c] += v[u][c];
+            }
+            if (u & 1) { // two rows of q < 2^31 fit 32 bits
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { sum[c] += p32[c]; p32[c] = 0; }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (keep[c]) red_add_u64(SP0 + c0 + c, sum[c]);
 }
 
 // clusterboot: k x k contingency table of (c1 label of the resampled cell, bootstrap label)
@@ -783,28 +815,39 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
             }
             RID_CUDA(cudaMemcpyAsync(w->subset, w->h_subset.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             RID_CUDA(cudaMemcpyAsync(w->pos_of, pos_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->colmap, w->h_colmap.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            // compact column -> cell (the sorted subset); reuses the colmap device buffer
+            std::vector<int> ccells(m);
+            for (int h = 0; h < N; ++h)
+                if (w->h_colmap[h] >= 0) ccells[w->h_colmap[h]] = h;
+            RID_CUDA(cudaMemcpyAsync(w->colmap, ccells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaStreamSynchronize(ctx->stream));
             RID_CUDA(cudaMemcpyAsync(w->subset_cells, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             if (w->nls) {
                 RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 RID_CUDA(cudaMemcpyAsync(w->src_rows, w->h_src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                dim3 grid((unsigned)w->nls, (unsigned)((dm->ld + 511) / 512));
+                // SP (BUILD step 0) is accumulated by the same pass
+                RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
+                dim3 grid((unsigned)((w->nls + COMPACT_ROWS - 1) / COMPACT_ROWS), (unsigned)((ldc + 511) / 512));
                 cudaEvent_t pe = rid_prof_begin(ctx);
-                LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->colmap, N, w->cbuf, ldc, m);
+                LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->nls, w->colmap, w->cbuf, ldc, m,
+                       w->acc + 4);
                 rid_prof_end(ctx, pe, RID_PROF_COMPACT, (double)w->nls * ((double)N + (double)m) * 4.0,
                              (double)w->nls * ((double)dm->ld + (double)ldc) * 4.0);
                 RID_CUDA(cudaGetLastError());
             }
+            if (!w->nls) RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
             RID_CUDA(cudaStreamSynchronize(ctx->stream)); // pos_c is a local
             w->mat = w->cbuf;
             w->ld = ldc;
             w->compact = true;
+            w->sp0_ready = true;
             return RID_OK;
         }
     }
     // view mode: rows of the resident shard through a row list, columns masked by the candidate list
     w->compact = false;
+    w->sp0_ready = false;
     w->mat = dm->D;
     w->ld = dm->ld;
     w->h_rows.clear(); w->h_rows_pos.clear();
@@ -876,10 +919,16 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
     u64 *SP = w->acc + 4, *AQ0 = SP + w->ld;
     auto sel_build = k_select<true>;
     const size_t prof_start = ctx->prof.size();
+    bool step0_fused = false;
     for (int s = k_from; s < k_to; ++s) {
         if (s == 0) {
-            RID_TRY(zero_acc(dm, w, 0, 0));
-            RID_TRY((launch_scan<0>(dm, w, w->rows, w->capP, nullptr, nullptr, w->nls, nullptr, 0, RID_PROF_SCAN_BUILD)));
+            if (!w->sp0_ready) {
+                RID_TRY(zero_acc(dm, w, 0, 0));
+                RID_TRY((launch_scan<0>(dm, w, w->rows, w->capP, nullptr, nullptr, w->nls, nullptr, 0, RID_PROF_SCAN_BUILD)));
+            } else {
+                step0_fused = true;
+            }
+            w->sp0_ready = false;
             RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
         } else {
             RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream));
@@ -903,7 +952,7 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         std::vector<int> hist(k_to);
         RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)k_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         RID_CUDA(cudaStreamSynchronize(ctx->stream));
-        int s = k_from;
+        int s = k_from + (step0_fused ? 1 : 0);
         for (size_t i = prof_start; i < ctx->prof.size(); ++i) {
             if (ctx->prof[i].kind != RID_PROF_SCAN_BUILD) continue;
             if (s > 0) {

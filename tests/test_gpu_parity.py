@@ -37,6 +37,33 @@ def test_dist_matches_oracle(ctx, oracle, metric):
     dm.free()
 
 
+@pytest.mark.parametrize("shape", [(300, 500, 6), (17, 129, 3), (1000, 2000, 8), (130, 97, 2)])
+@pytest.mark.parametrize("metric", ["pearson", "spearman", "logpearson"])
+def test_dist_int8_tcgen05_path_matches_fp64_dmma_path(ctx, oracle, metric, shape, monkeypatch):
+    """The exact int8 tensor-core contraction (tcgen05.mma kind::i8, Ozaki split of the unit-norm rows) against the
+    FP64 DMMA kernel and the oracle.  RID_GRAM=i8 turns a silent fallback into an error."""
+    G, N, C = shape
+    x, _ = _features(seed=31, G=G, N=N, C=C)
+    x[:, N // 2] = x[:, 1]  # duplicate cell
+    if metric == "pearson":
+        x[:, 5] = 2.5       # zero-variance cell -> NA row/column
+    monkeypatch.setenv("RID_GRAM", "i8")
+    dm = ctx.dist(x, metric)
+    Di = dm.as_matrix()
+    dm.free()
+    monkeypatch.setenv("RID_GRAM", "f64")
+    dm = ctx.dist(x, metric)
+    Df = dm.as_matrix()
+    dm.free()
+    assert np.array_equal(np.isnan(Di), np.isnan(Df))
+    ok = ~np.isnan(Df)
+    assert np.max(np.abs(Di[ok] - Df[ok])) <= 4e-7  # the int8 path's a-posteriori bound is <= 8e-7; measured ~7e-8
+    Do, _ = oracle.dist(x, metric)
+    assert np.max(np.abs(Di[ok] - Do[ok])) <= DIST_TOL
+    assert np.array_equal(Di[ok], Di.T[ok]) and np.all(np.diag(Di)[~np.isnan(np.diag(Di))] == 0.0)
+    assert Di[N // 2, 1] <= 4e-7
+
+
 def test_dist_zero_variance_cell(ctx, oracle):
     x, _ = _features(seed=2, G=120, N=200)
     x[:, 9] = 3.25
