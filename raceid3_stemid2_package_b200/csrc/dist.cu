@@ -517,7 +517,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     bool gram_done = false;
     {
         const char *mode = getenv("RID_GRAM");
-        const bool want_i8 = metric != RID_EUCLIDEAN && ctx->world == 1 && !(mode && strcmp(mode, "f64") == 0);
+        const bool want_i8 = metric != RID_EUCLIDEAN && ctx->world <= 16 && !(mode && strcmp(mode, "f64") == 0);
         if (want_i8) {
             int used = 0;
             double bound = 0.0;

@@ -108,13 +108,31 @@ struct I8Params {
     const unsigned char *zero_var;
     const double *rowscale; // 2^-(e_i+27)
     double inv_step;
+    // row-block sharding: this rank owns rows [row0, row0+nloc); rank b owns [b*per, ...).  Every off-diagonal pair of
+    // shards is computed by exactly one of its two owners, which stores the mirror image into the peer's shard (NVLink).
+    int row0, nloc, world, rank, per;
+    u32 *peer[16];
 };
+
+// Does rank `me` compute the elements (rows of me) x (columns of rank b)?  Antipodal pairs (world even) are split by the
+// parity of the 384 x 384 super-block (384 = lcm of the 128-row and 96-column tiles), which both owners evaluate alike.
+__device__ __host__ __forceinline__ bool i8_pair_mine(int me, int b, int world, int i0, int j0)
+{
+    if (b == me) return j0 + I8_BN > i0;
+    const int d = (b - me + world) % world;
+    if (2 * d != world) return 2 * d < world;
+    return (((i0 / 384) + (j0 / 384)) & 1) == (me < b ? 0 : 1);
+}
 
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, I8Params P)
 {
-    const int i0 = blockIdx.y * I8_BM, j0 = blockIdx.x * I8_BN;
-    if (j0 + I8_BN <= i0) return; // tile entirely below the diagonal: its mirror image is written by tile (j,i)
+    const int i0 = P.row0 + blockIdx.y * I8_BM, j0 = blockIdx.x * I8_BN; // global row / column of the tile origin
+    {
+        // a column tile may straddle two shards: compute it if either owner's pair is ours
+        const int b1 = min(j0 / P.per, P.world - 1), b2 = min(min(j0 + I8_BN - 1, P.N - 1) / P.per, P.world - 1);
+        if (!i8_pair_mine(P.rank, b1, P.world, i0, j0) && !i8_pair_mine(P.rank, b2, P.world, i0, j0)) return;
+    }
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -195,7 +213,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int q = warp - 4;          // TMEM lane quarter this warp may touch
         const int r = q * 32 + lane;     // tile row = TMEM lane
         const int gi = i0 + r;
-        const bool row_ok = gi < P.N;
+        const bool row_ok = gi < P.row0 + P.nloc;
         const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
         const bool zr = row_ok ? P.zero_var[gi] : false;
         for (int c0 = 0; c0 < I8_BN; c0 += 16) {
@@ -232,7 +250,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             // direct store: 16 consecutive columns of row gi
             if (row_ok) {
-                u32 *dst = P.D + (size_t)gi * P.ld + j0 + c0;
+                u32 *dst = P.D + (size_t)(gi - P.row0) * P.ld + j0 + c0;
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
@@ -241,7 +259,10 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const int gj = j0 + c0 + c;
-                if (gj < P.N && (size_t)gi < P.ld) P.D[(size_t)gj * P.ld + gi] = row_ok ? qv[c] : 0u;
+                if (gj < P.N && (size_t)gi < P.ld) {
+                    const int ow = min(gj / P.per, P.world - 1);
+                    P.peer[ow][(size_t)(gj - ow * P.per) * P.ld + gi] = row_ok ? qv[c] : 0u;
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -347,10 +368,20 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
                 int *used, double *bound_out)
 {
     *used = 0;
+    // multi-rank: the mirror tiles go straight into the peers' shards, so every rank needs every shard mapped
+    void *peers[16];
+    for (int r = 0; r < 16; ++r) peers[r] = nullptr;
+    peers[0] = dm->D;
+    if (ctx->world > 1) {
+        int all_ok = 0;
+        RID_TRY(rid_peer_pointers(ctx, dm->D, peers, &all_ok));
+        if (!all_ok) return RID_OK;
+    }
     PFN_encodeTiled encode = get_encode();
     if (!encode) return RID_OK;
     const int Kp = (int)round_up((size_t)G, I8_BK);
-    const int tiles_m = (N + I8_BM - 1) / I8_BM, tiles_n = (N + I8_BN - 1) / I8_BN;
+    const int nloc = dm->row1 - dm->row0;
+    const int tiles_m = (N + I8_BM - 1) / I8_BM, tiles_n = (N + I8_BN - 1) / I8_BN, tiles_loc = (nloc + I8_BM - 1) / I8_BM;
     const size_t plane_rows = std::max((size_t)tiles_m * I8_BM, (size_t)tiles_n * I8_BN);
     const size_t planes_bytes = 4 * plane_rows * (size_t)Kp;
     int8_t *planes = nullptr;
@@ -376,6 +407,7 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     // rounding of z to 27 bits:  2^-54 (256 U0 U1 + U0^2)  +  2^-27 V W1     (U_s = max 2^-e |d_s|, V = max 2^-e, W1 = max |z|_1)
     const double bound = ldexp(256.0 * h[0] * h[1] + h[0] * h[0], -54) + ldexp(h[2] * h[3], -27);
     if (bound_out) *bound_out = bound;
+    // (every rank quantises all rows, so every rank sees the same statistics and takes the same branch)
     if (!(bound <= 8e-7)) { cleanup(); return RID_OK; } // + 2^-28 quantisation of D stays under the 1e-6 bar
 
     CUtensorMap tmA, tmB;
@@ -392,21 +424,42 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     I8Params P;
     P.N = N; P.nkb = Kp / I8_BK; P.D = dm->D; P.ld = dm->ld; P.plane_rows = (int)plane_rows; P.zero_var = zero_var;
     P.rowscale = rowscale; P.inv_step = 1.0 / dm->step;
+    P.row0 = dm->row0; P.nloc = nloc; P.world = ctx->world; P.rank = ctx->rank;
+    {
+        int r0, r1;
+        rid_shard_rows(N, 0, ctx->world, &r0, &r1);
+        P.per = ctx->world > 1 ? std::max(r1 - r0, 1) : std::max(N, 1);
+    }
+    for (int r = 0; r < 16; ++r) P.peer[r] = (u32 *)peers[r];
+    if (ctx->world == 1) P.peer[0] = dm->D;
     if (cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) {
         cudaGetLastError(); cleanup(); return RID_OK;
     }
     // pad columns [N, ld) of every row are never touched by the tiles: clear them
-    cudaMemset2DAsync(dm->D + N, dm->ld * sizeof(u32), 0, (dm->ld - (size_t)N) * sizeof(u32), (size_t)N, ctx->stream);
-    dim3 grid((unsigned)tiles_n, (unsigned)tiles_m);
+    if (nloc > 0 && dm->ld > (size_t)N)
+        cudaMemset2DAsync(dm->D + N, dm->ld * sizeof(u32), 0, (dm->ld - (size_t)N) * sizeof(u32), (size_t)nloc, ctx->stream);
+    // nobody may start storing mirror tiles into a peer before that peer has cleared its pad columns
+    if (ctx->world > 1) RID_TRY(rid_barrier(ctx));
+    dim3 grid((unsigned)tiles_n, (unsigned)std::max(tiles_loc, 1));
     cudaEvent_t pe = rid_prof_begin(ctx);
-    k_gram_i8<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
-    ctx->launches++;
+    if (nloc > 0) {
+        k_gram_i8<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
+        ctx->launches++;
+    }
     // work: int8 multiply-adds actually issued x 2 (13 digit products per computed tile)
     double tiles_done = 0;
-    for (int bm = 0; bm < tiles_m; ++bm)
-        for (int bn = 0; bn < tiles_n; ++bn) tiles_done += (bn * I8_BN + I8_BN > bm * I8_BM);
+    for (int bm = 0; bm < tiles_loc; ++bm)
+        for (int bn = 0; bn < tiles_n; ++bn) {
+            const int i0 = P.row0 + bm * I8_BM, j0 = bn * I8_BN;
+            const int b1 = std::min(j0 / P.per, P.world - 1), b2 = std::min(std::min(j0 + I8_BN - 1, N - 1) / P.per, P.world - 1);
+            tiles_done += (i8_pair_mine(P.rank, b1, P.world, i0, j0) || i8_pair_mine(P.rank, b2, P.world, i0, j0));
+        }
+    (void)tiles_m;
     rid_prof_end(ctx, pe, RID_PROF_GRAM_I8, tiles_done * 13.0 * 2.0 * I8_BM * I8_BN * (double)Kp, (double)N * dm->ld * 4.0);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // peers have written mirror tiles into this rank's shard: nobody may go on before every kernel is done
+    if (e == cudaSuccess && ctx->world > 1 && rid_barrier(ctx) != RID_OK) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) {
