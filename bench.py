@@ -271,7 +271,7 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ctx.event_elapsed_ms(0, 1)
     launches = ctx.launches - l0
-    prof = {k: ctx.profile_get(k) for k in ("gram", "gram_i8", "scan_swap", "scan_build", "scan_group", "prep", "compact")}
+    prof = {k: ctx.profile_get(k) for k in ("gram", "gram_i8", "scan_swap", "scan_delta", "scan_build", "scan_group", "prep", "compact")}
     ctx.profile(False)
     clk = clocks.stop()
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)

@@ -71,7 +71,7 @@ void rid_pool_trim(rid_ctx *ctx);
 
 // kinds for rid_ctx_profile_get
 enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,
-       RID_PROF_COMPACT = 5, RID_PROF_GRAM_I8 = 6, RID_PROF_NKINDS = 7 };
+       RID_PROF_COMPACT = 5, RID_PROF_GRAM_I8 = 6, RID_PROF_SCAN_DELTA = 7, RID_PROF_NKINDS = 8 };
 
 // RAII-less helpers: call prof_begin right before the launch and prof_end right after it.
 cudaEvent_t rid_prof_begin(rid_ctx *ctx);

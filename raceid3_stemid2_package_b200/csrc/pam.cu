@@ -24,6 +24,9 @@
 #include "common.cuh"
 
 // ----------------------------------------------------------------------------------------------------------
+#define K2MAX 4096   // incremental SWAP keys rows by (old group, new group): k*k <= K2MAX, i.e. k <= 64
+#define CNT_HIST 4096
+
 struct PamState {
     u64 td;       // total deviation at the last SWAP decision (fixed point)
     u64 td_build; // total deviation after BUILD
@@ -80,6 +83,15 @@ struct PamWs {
     int *subset_cells = nullptr; // [N] cell by position (== subset unless compact)
     int *colmap = nullptr;       // [N] compact column of a cell, or -1
     int *src_rows = nullptr;     // [nloc] shard row of each owned subset row (compaction source)
+    // incremental SWAP: previous assignment of the owned rows, the list of rows whose assignment changed (old / new
+    // caps and groups, sorted by the (old group, new group) pair) and a delta accumulator with acc's layout
+    u32 *o_capP = nullptr, *o_capQ = nullptr;
+    int *o_grp = nullptr;
+    int *d_row = nullptr, *d_key = nullptr;
+    u32 *d_po = nullptr, *d_qo = nullptr, *d_pn = nullptr, *d_qn = nullptr;
+    int *hist2 = nullptr; // [3 * K2MAX]: counts, bases, cursors of the pair keys
+    u64 *acc2 = nullptr;
+    int *cnt_hist = nullptr; // [CNT_HIST] changed-row counts of the delta passes (profiling)
     int *chg_count = nullptr; // rows whose cap changed in the last BUILD step
     int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
@@ -90,8 +102,8 @@ struct PamWs {
 static void ws_free_groups(PamWs *w)
 {
     cudaFree(w->med); cudaFree(w->medpos); cudaFree(w->hist); cudaFree(w->grp_sum); cudaFree(w->grp_cnt);
-    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc); cudaFree(w->chg_hist);
-    w->chg_hist = nullptr;
+    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc); cudaFree(w->chg_hist); cudaFree(w->acc2);
+    w->chg_hist = nullptr; w->acc2 = nullptr;
     w->med = w->medpos = w->hist = w->grp_cnt = w->grp_arg = nullptr;
     w->grp_sum = w->grp_min = w->acc = nullptr;
 }
@@ -105,6 +117,8 @@ void rid_pam_ws_free(PamWs *w, rid_ctx *ctx)
     cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
     cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state); cudaFree(w->chg_count);
     cudaFree(w->subset_cells); cudaFree(w->colmap); cudaFree(w->src_rows);
+    cudaFree(w->o_capP); cudaFree(w->o_capQ); cudaFree(w->o_grp); cudaFree(w->d_row); cudaFree(w->d_key);
+    cudaFree(w->d_po); cudaFree(w->d_qo); cudaFree(w->d_pn); cudaFree(w->d_qn); cudaFree(w->hist2); cudaFree(w->cnt_hist);
     ws_free_groups(w);
     delete w;
 }
@@ -139,6 +153,17 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->dscratch, 8 * sizeof(double)));
         RID_CUDA(cudaMalloc(&w->state, sizeof(PamState)));
         RID_CUDA(cudaMalloc(&w->chg_count, sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->o_capP, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->o_capQ, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->o_grp, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->d_row, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->d_key, nl * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->d_po, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->d_qo, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->d_pn, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->d_qn, nl * sizeof(u32)));
+        RID_CUDA(cudaMalloc(&w->hist2, 3 * K2MAX * sizeof(int)));
+        RID_CUDA(cudaMalloc(&w->cnt_hist, CNT_HIST * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->subset_cells, N * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->colmap, N * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->src_rows, nl * sizeof(int)));
@@ -155,6 +180,7 @@ static int ws_get(rid_dmat *dm, int k, PamWs **out)
         RID_CUDA(cudaMalloc(&w->grp_arg, kc * sizeof(int)));
         RID_CUDA(cudaMalloc(&w->chg_hist, kc * sizeof(int)));
         cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * dm->ld) * sizeof(u64));
+        if (e == cudaSuccess) e = cudaMalloc(&w->acc2, (4 + (size_t)(kc + 1) * dm->ld) * sizeof(u64));
         if (e != cudaSuccess) {
             rid_set_error("out of device memory for %d group accumulators", kc);
             return RID_ERR_NOMEM;
@@ -327,6 +353,156 @@ k_scan(const u32 *__restrict__ D, size_t ld, const int *__restrict__ s_row,
         if (WITH_P) red_add_u64(SP + col + c, accP[c]);
         if (WITH_Q) red_add_u64(AQ + (size_t)cur_g * ld + col + c, accQ[c]);
     }
+}
+
+// ---- incremental SWAP ------------------------------------------------------------------------------------------
+// After a swap only the rows whose (nearest, second nearest) pair changed contribute differently to SP / AQ.  For those
+// rows the pass below subtracts the old contribution and adds the new one:
+//     SP[h]      += min(d, dn_new) - min(d, dn_old)
+//     AQ[g_old][h] -= min(d, ds_old) - min(d, dn_old)          AQ[g_new][h] += min(d, ds_new) - min(d, dn_new)
+// in wrap-around 64-bit integer arithmetic (exact), so SP / AQ stay equal to what a full pass would give.
+__global__ void k_diff_count(const u32 *__restrict__ nP, const u32 *__restrict__ nQ, const int *__restrict__ nG,
+                             const u32 *__restrict__ oP, const u32 *__restrict__ oQ, const int *__restrict__ oG, int nls,
+                             int k, int *hist2, const PamState *st)
+{
+    if (st->done) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls && (nP[t] != oP[t] || nQ[t] != oQ[t] || nG[t] != oG[t])) atomicAdd(&hist2[oG[t] * k + nG[t]], 1);
+}
+
+__global__ void k_prefix2(int *hist2, int k2, int *total, const PamState *st)
+{
+    if (st->done) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < k2; ++c) {
+            hist2[K2MAX + c] = run;
+            hist2[2 * K2MAX + c] = 0;
+            run += hist2[c];
+        }
+        *total = run;
+    }
+}
+
+__global__ void k_diff_scatter(const int *__restrict__ rows, const u32 *__restrict__ nP, const u32 *__restrict__ nQ,
+                               const int *__restrict__ nG, const u32 *__restrict__ oP, const u32 *__restrict__ oQ,
+                               const int *__restrict__ oG, int nls, int k, int *hist2, int *d_row, int *d_key, u32 *d_po,
+                               u32 *d_qo, u32 *d_pn, u32 *d_qn, const PamState *st)
+{
+    if (st->done) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls && (nP[t] != oP[t] || nQ[t] != oQ[t] || nG[t] != oG[t])) {
+        int key = oG[t] * k + nG[t];
+        int dst = hist2[K2MAX + key] + atomicAdd(&hist2[2 * K2MAX + key], 1);
+        d_row[dst] = rows[t];
+        d_key[dst] = key;
+        d_po[dst] = oP[t]; d_qo[dst] = oQ[t];
+        d_pn[dst] = nP[t]; d_qn[dst] = nQ[t];
+    }
+}
+
+template <int FLUSH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_delta(const u32 *__restrict__ D, size_t ld, const int *__restrict__ d_row, const int *__restrict__ d_key,
+             const u32 *__restrict__ d_po, const u32 *__restrict__ d_qo, const u32 *__restrict__ d_pn,
+             const u32 *__restrict__ d_qn, const int *__restrict__ nrows_dev, int rows_per_chunk, int k,
+             u64 *__restrict__ SP, u64 *__restrict__ AQ, const PamState *st)
+{
+    if (st->done) return;
+    __shared__ int sh_row[SCAN_MAXROWS];
+    __shared__ int sh_key[SCAN_MAXROWS];
+    __shared__ u32 sh_po[SCAN_MAXROWS], sh_qo[SCAN_MAXROWS], sh_pn[SCAN_MAXROWS], sh_qn[SCAN_MAXROWS];
+    const int n = *nrows_dev;
+    const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    const bool active = col < ld;
+    const u32 *base = D + col;
+    long long accS[4] = {0, 0, 0, 0};
+    u64 accO[4] = {0, 0, 0, 0}, accN[4] = {0, 0, 0, 0};
+    int s32[4] = {0, 0, 0, 0};
+    u32 o32[4] = {0, 0, 0, 0}, n32[4] = {0, 0, 0, 0};
+    int cur = -1;
+    bool any = false;
+    for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < n; chunk += gridDim.y) {
+        const int r_begin = chunk * rows_per_chunk;
+        const int nr = min(n - r_begin, rows_per_chunk);
+        const int nr8 = (nr + 7) & ~7;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
+            bool ok = i < nr;
+            int src = r_begin + (ok ? i : nr - 1);
+            sh_row[i] = ok ? d_row[src] : -1;
+            sh_key[i] = d_key[src];
+            sh_po[i] = ok ? d_po[src] : 0u; sh_qo[i] = ok ? d_qo[src] : 0u;
+            sh_pn[i] = ok ? d_pn[src] : 0u; sh_qn[i] = ok ? d_qn[src] : 0u;
+        }
+        __syncthreads();
+        if (!active) continue;
+        any = true;
+        if (cur < 0) cur = sh_key[0];
+        for (int r = 0; r < nr8; r += 8) {
+            uint4 d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int lr = sh_row[r + u];
+                d[u] = lr >= 0 ? ld_stream(base + (size_t)lr * ld) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int key = sh_key[r + u];
+                if (key != cur) { // uniform across the CTA
+                    const int go = cur / k, gn = cur - go * k;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        accS[c] += s32[c]; s32[c] = 0;
+                        accO[c] += o32[c]; o32[c] = 0;
+                        accN[c] += n32[c]; n32[c] = 0;
+                        red_add_u64(AQ + (size_t)go * ld + col + c, 0ull - accO[c]);
+                        red_add_u64(AQ + (size_t)gn * ld + col + c, accN[c]);
+                        accO[c] = 0; accN[c] = 0;
+                    }
+                    cur = key;
+                }
+                const u32 po = sh_po[r + u], qo = sh_qo[r + u], pn = sh_pn[r + u], qn = sh_qn[r + u];
+                const u32 dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const u32 a = min(dv[c], po), b = min(dv[c], pn);
+                    s32[c] += (int)(b - a); // |b - a| <= q_max
+                    o32[c] += min(dv[c], qo) - a;
+                    n32[c] += min(dv[c], qn) - b;
+                }
+                if ((u % (FLUSH / 2)) == FLUSH / 2 - 1) { // the signed partial holds half as many rows
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { accS[c] += s32[c]; s32[c] = 0; }
+                }
+                if ((u % FLUSH) == FLUSH - 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        accO[c] += o32[c]; o32[c] = 0;
+                        accN[c] += n32[c]; n32[c] = 0;
+                    }
+                }
+            }
+        }
+    }
+    if (!any) return;
+    const int go = cur / k, gn = cur - go * k;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        red_add_u64(SP + col + c, (u64)accS[c]);
+        red_add_u64(AQ + (size_t)go * ld + col + c, 0ull - accO[c]);
+        red_add_u64(AQ + (size_t)gn * ld + col + c, accN[c]);
+    }
+}
+
+// acc[0] = delta[0] (the new TD), acc[4..] += delta[4..]   (wrap-around adds: exact)
+__global__ void k_acc_add(u64 *acc, const u64 *__restrict__ delta, size_t n, const PamState *st)
+{
+    if (st->done) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (i == 0) acc[0] = delta[0];
+    for (size_t t = 4 + i; t < n; t += stride) acc[t] += delta[t];
 }
 
 // nearest / second-nearest medoid of every owned subset row (cstat + the dysma/dysmb refresh of bswap):
@@ -976,13 +1152,19 @@ static int pam_begin(rid_dmat *dm, PamWs *w)
 }
 
 // one assign pass: caps, groups, TD -> acc[0] (all-reduced).  ngroups = k accumulators are zeroed too.
-static int pam_assign(rid_dmat *dm, PamWs *w, int k, int check_done)
+static int pam_assign(rid_dmat *dm, PamWs *w, int k, int check_done, u64 *acc = nullptr)
 {
     rid_ctx *ctx = dm->ctx;
-    RID_TRY(zero_acc(dm, w, k, check_done));
+    if (!acc) acc = w->acc;
+    {
+        size_t n = 4 + (size_t)(1 + k) * w->ld;
+        int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+        blocks = std::max(blocks, nblk(3 * w->kcap, 256));
+        LAUNCH(ctx, k_zero, blocks, 256, 0, acc, n, w->hist, 3 * w->kcap, w->state, check_done);
+    }
     if (w->nls)
         LAUNCH(ctx, k_assign, nblk(w->nls, 128), 128, 2 * k * sizeof(int), w->mat, w->ld, w->rows, w->nls,
-               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, w->acc, w->state, check_done);
+               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, acc, w->state, check_done);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -998,6 +1180,58 @@ static int sort_rows_by_group(rid_dmat *dm, PamWs *w, int k, int check_done)
     return RID_OK;
 }
 
+// One incremental SWAP iteration (all kernels are no-ops once state.done is set).
+static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
+{
+    rid_ctx *ctx = dm->ctx;
+    const size_t nacc = 4 + (size_t)(1 + k) * w->ld;
+    if (w->nls) {
+        RID_CUDA(cudaMemcpyAsync(w->o_capP, w->capP, (size_t)w->nls * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->o_capQ, w->capQ, (size_t)w->nls * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->o_grp, w->grp, (size_t)w->nls * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    RID_TRY(pam_assign(dm, w, k, 1, w->acc2)); // zeroes acc2, new caps / groups, TD -> acc2[0]
+    RID_CUDA(cudaMemsetAsync(w->hist2, 0, (size_t)k * k * sizeof(int), ctx->stream));
+    RID_CUDA(cudaMemsetAsync(w->chg_count, 0, sizeof(int), ctx->stream));
+    if (w->nls) {
+        LAUNCH(ctx, k_diff_count, nblk(w->nls, 256), 256, 0, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ, w->o_grp,
+               w->nls, k, w->hist2, w->state);
+        LAUNCH(ctx, k_prefix2, 1, 32, 0, w->hist2, k * k, w->chg_count, w->state);
+        LAUNCH(ctx, k_diff_scatter, nblk(w->nls, 256), 256, 0, w->rows, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ,
+               w->o_grp, w->nls, k, w->hist2, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn, w->state);
+        int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
+        int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
+        int rpc = (w->nls + want_y - 1) / want_y;
+        rpc = std::min(std::max((rpc + 7) & ~7, 8), 256); // six per-row arrays live in shared memory
+        int chunks = (w->nls + rpc - 1) / rpc;
+        dim3 grid(strips, std::min(chunks, want_y * 2));
+        u64 *SP2 = w->acc2 + 4, *AQ2 = SP2 + w->ld;
+        cudaEvent_t pe = rid_prof_begin(ctx);
+        auto d8 = k_scan_delta<8>;
+        auto d2 = k_scan_delta<2>;
+        if (dm->bits <= 28)
+            LAUNCH(ctx, d8, grid, SCAN_THREADS, 0, w->mat, w->ld, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn,
+                   w->chg_count, rpc, k, SP2, AQ2, w->state);
+        else
+            LAUNCH(ctx, d2, grid, SCAN_THREADS, 0, w->mat, w->ld, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn,
+                   w->chg_count, rpc, k, SP2, AQ2, w->state);
+        rid_prof_end(ctx, pe, RID_PROF_SCAN_DELTA, 0.0, 0.0);
+        if (ctx->prof_on && *n_delta < CNT_HIST)
+            RID_CUDA(cudaMemcpyAsync(w->cnt_hist + *n_delta, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->prof_on) ++*n_delta;
+    }
+    RID_TRY(rid_allreduce_u64(ctx, w->acc2, nacc));
+    {
+        int blocks = (int)std::min<size_t>((nacc + 255) / 256, (size_t)ctx->sm_count * 8);
+        LAUNCH(ctx, k_acc_add, blocks, 256, 0, w->acc, w->acc2, nacc, w->state);
+    }
+    auto sel_swap = k_select<false>;
+    LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
+           w->is_med, w->blockbest, w->state, 1);
+    RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
 // SWAP until no improving swap is left.  Medoids (k of them) must be installed in w->med / is_med.
 // On return: state.td_build = TD before the first swap, state.td = final TD, w->grp / capP / capQ describe the
 // final medoids for the owned rows.
@@ -1008,8 +1242,13 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
     double bytes = (double)w->nls * (double)w->ld * 4.0;
     int batch = bytes > 2.0e9 ? 1 : (bytes > 2.0e8 ? 2 : 8);
     bool first = true;
+    const bool incremental = k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL");
+    if (incremental) batch = std::max(batch, 2);
+    int n_delta = 0;
+    const size_t prof_start = ctx->prof.size();
     for (;;) {
         for (int b = 0; b < batch; ++b) {
+            if (incremental && !first) { RID_TRY(pam_swap_delta_iteration(dm, w, k, &n_delta)); continue; }
             int chk = first ? 0 : 1;
             RID_TRY(pam_assign(dm, w, k, chk));
             if (first) {
@@ -1033,6 +1272,8 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
                        w->med, w->medpos, w->is_med, w->blockbest, w->state, chk);
                 RID_CUDA(cudaGetLastError());
             }
+            // every later iteration only rescans the rows whose (nearest, second nearest) pair changed
+            while (incremental && ++b < batch) RID_TRY(pam_swap_delta_iteration(dm, w, k, &n_delta));
         }
         RID_CUDA(cudaMemcpyAsync(h_state, w->state, sizeof(PamState), cudaMemcpyDeviceToHost, ctx->stream));
         RID_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1041,6 +1282,19 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
             break;
         }
         if (h_state->done) break;
+    }
+    if (ctx->prof_on && n_delta > 0) {
+        // credit the delta passes with the rows they really rescanned
+        int cnt = std::min(n_delta, CNT_HIST);
+        std::vector<int> hist(cnt);
+        RID_CUDA(cudaMemcpy(hist.data(), w->cnt_hist, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+        int j = 0;
+        for (size_t i = prof_start; i < ctx->prof.size() && j < cnt; ++i)
+            if (ctx->prof[i].kind == RID_PROF_SCAN_DELTA) {
+                ctx->prof[i].work = (double)hist[j] * (double)w->m * 4.0;
+                ctx->prof[i].traffic = (double)hist[j] * (double)w->ld * 4.0;
+                ++j;
+            }
     }
     return RID_OK;
 }

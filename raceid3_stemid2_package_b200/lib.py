@@ -137,7 +137,7 @@ class Context:
     def launches(self) -> int:
         return int(load().rid_ctx_launches(self._h))
 
-    PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4, "compact": 5, "gram_i8": 6}
+    PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4, "compact": 5, "gram_i8": 6, "scan_delta": 7}
 
     def profile(self, enable: bool = True):
         _check(load().rid_ctx_profile(self._h, 1 if enable else 0))
