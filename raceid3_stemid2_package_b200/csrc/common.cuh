@@ -63,6 +63,7 @@ struct rid_ctx {
 // Returns RID_OK with *all_ok = 1 only if every rank could map every peer.
 int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok);
 int rid_barrier(rid_ctx *ctx);
+int rid_allgather(rid_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 
 // cudaMalloc/cudaFree through the context's reuse pool (exact-size match)
 cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes);
@@ -91,6 +92,7 @@ struct rid_dmat {
     u32 *D = nullptr;       // (row1-row0) x ld, fixed point: value = q * step
     int bits = 28;          // q <= 2^bits  (28: correlation distances, 31: general)
     double step = 0.0;      // value of one quantisation step
+    size_t alloc_rows = 0;  // rows allocated (== the shard size of rank 0 when world > 1, so that shards all-gather)
     int has_na = 0;
     std::vector<unsigned char> na_cell; // host copy: 1 if the cell's row/col is NA
     PamWs *ws = nullptr;

@@ -199,7 +199,7 @@ cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
 void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
 {
     if (!p) return;
-    if (bytes < ((size_t)16 << 20) || ctx->pool.size() >= 6) { cudaFree(p); return; }
+    if (bytes < ((size_t)16 << 20) || ctx->pool.size() >= 16) { cudaFree(p); return; }
     ctx->pool.push_back({p, bytes});
 }
 
@@ -313,6 +313,17 @@ static int ensure_scratch(rid_ctx *ctx)
         RID_CUDA(cudaMalloc(&ctx->scratch, 4096));
         RID_CUDA(cudaMemset(ctx->scratch, 0, 4096));
     }
+    return RID_OK;
+}
+
+int rid_allgather(rid_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank)
+{
+    if (ctx->world == 1) {
+        if (send != recv) RID_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+        return RID_OK;
+    }
+    if (!ctx->nccl->AllGather) { rid_set_error("ncclAllGather is not available"); return RID_ERR_CUDA; }
+    RID_NCCL(ctx->nccl, ctx->nccl->AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
     return RID_OK;
 }
 

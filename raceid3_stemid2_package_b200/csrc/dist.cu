@@ -404,7 +404,16 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
     shard_rows(N, ctx->rank, ctx->world, &dm->row0, &dm->row1);
     dm->ld = round_up((size_t)N, 128);
     size_t nloc = (size_t)(dm->row1 - dm->row0);
-    cudaError_t e = rid_pool_alloc(ctx, (void **)&dm->D, std::max<size_t>(nloc, 1) * dm->ld * sizeof(u32));
+    if (ctx->world > 1) { // every shard is allocated at the size of rank 0's (equal counts for ncclAllGather)
+        int r0, r1;
+        shard_rows(N, 0, ctx->world, &r0, &r1);
+        dm->alloc_rows = (size_t)std::max(r1 - r0, 1);
+    } else {
+        dm->alloc_rows = std::max<size_t>(nloc, 1);
+    }
+    cudaError_t e = rid_pool_alloc(ctx, (void **)&dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
+    if (e == cudaSuccess && dm->alloc_rows > nloc) // rows nobody owns (last rank): keep them defined
+        cudaMemsetAsync(dm->D + nloc * dm->ld, 0, (dm->alloc_rows - nloc) * dm->ld * sizeof(u32), ctx->stream);
     if (e != cudaSuccess) {
         rid_set_error("cannot allocate %.2f GB for the distance-matrix shard (%zu x %zu): %s",
                       (double)nloc * dm->ld * 4 / 1e9, nloc, dm->ld, cudaGetErrorString(e));
@@ -421,7 +430,7 @@ extern "C" int rid_dmat_free(rid_dmat *dm)
     cudaSetDevice(dm->ctx->device);
     cudaStreamSynchronize(dm->ctx->stream);
     rid_pam_ws_free(dm->ws, dm->ctx);
-    rid_pool_free(dm->ctx, dm->D, std::max<size_t>((size_t)(dm->row1 - dm->row0), 1) * dm->ld * sizeof(u32));
+    rid_pool_free(dm->ctx, dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
     delete dm;
     return RID_OK;
 }

@@ -1445,20 +1445,90 @@ extern "C" int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int
     return rid_time_end(dm->ctx);
 }
 
+// ---- multi-GPU scheduling of independent PAM runs ------------------------------------------------------------------
+// Bootstrap replicates (and the k values of the sweep) are independent problems.  When the whole matrix fits on every
+// GPU next to its shard, the shards are all-gathered once over NVLink and each rank runs its share of the problems on
+// the replica at single-GPU efficiency (no per-step all-reduce, no latency-bound 1/world-sized passes); otherwise all
+// ranks cooperate on every problem through the row shards.  Results are identical either way (exact integer sums).
+struct FullReplica {
+    rid_dmat full;
+    size_t bytes = 0;
+    int saved_world = 1, saved_rank = 0;
+    bool active = false;
+};
+
+static int replica_begin(rid_dmat *dm, FullReplica *R)
+{
+    rid_ctx *ctx = dm->ctx;
+    R->active = false;
+    if (ctx->world == 1 || getenv("RID_NO_REPLICA")) return RID_OK;
+    const size_t bytes = (size_t)ctx->world * dm->alloc_rows * dm->ld * sizeof(u32);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // replica + a compact bootstrap copy (~0.45 N^2 words) + accumulators + slack
+    const size_t need = bytes + (size_t)(0.45 * (double)dm->N * (double)dm->ld * 4.0) + ((size_t)4 << 30);
+    int miss = free_b >= need ? 0 : 1;
+    void *buf = nullptr;
+    if (!miss && rid_pool_alloc(ctx, &buf, bytes) != cudaSuccess) { cudaGetLastError(); miss = 1; buf = nullptr; }
+    PamWs *w;
+    RID_TRY(ws_get(dm, 1, &w));
+    int *flag = (int *)w->dscratch;
+    RID_CUDA(cudaMemcpyAsync(flag, &miss, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_TRY(rid_allreduce_i32(ctx, flag, 1));
+    RID_CUDA(cudaMemcpyAsync(&miss, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (miss) { // some rank cannot hold the replica: everybody cooperates
+        if (buf) rid_pool_free(ctx, buf, bytes);
+        return RID_OK;
+    }
+    RID_TRY(rid_allgather(ctx, dm->D, buf, dm->alloc_rows * dm->ld * sizeof(u32)));
+    R->full = rid_dmat();
+    R->full.ctx = ctx;
+    R->full.N = dm->N;
+    R->full.row0 = 0;
+    R->full.row1 = dm->N;
+    R->full.ld = dm->ld;
+    R->full.D = (u32 *)buf;
+    R->full.alloc_rows = (size_t)ctx->world * dm->alloc_rows;
+    R->full.bits = dm->bits;
+    R->full.step = dm->step;
+    R->full.has_na = dm->has_na;
+    R->full.na_cell = dm->na_cell;
+    R->bytes = bytes;
+    R->saved_world = ctx->world;
+    R->saved_rank = ctx->rank;
+    R->active = true;
+    return RID_OK;
+}
+// local phases run with the context switched to "one GPU"; collectives need the real world back
+static void replica_local(FullReplica *R, bool on)
+{
+    if (!R->active) return;
+    rid_ctx *ctx = R->full.ctx;
+    ctx->world = on ? 1 : R->saved_world;
+    ctx->rank = on ? 0 : R->saved_rank;
+}
+static void replica_end(FullReplica *R)
+{
+    if (!R->active) return;
+    replica_local(R, false);
+    rid_ctx *ctx = R->full.ctx;
+    cudaStreamSynchronize(ctx->stream);
+    rid_pam_ws_free(R->full.ws, ctx);
+    R->full.ws = nullptr;
+    rid_pool_free(ctx, R->full.D, R->bytes);
+    R->active = false;
+}
+
 // clusGapExt's k loop.  BUILD is greedy and does not depend on k, so BUILD(k) is the first k picks of
 // BUILD(Kmax): run it once and start SWAP(k) from the k-prefix (identical results, Kmax instead of
 // Kmax(Kmax+1)/2 BUILD passes).
-extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW)
+static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW, int nshare, int myshare)
 {
-    if (!dm || !logW || Kmax < 1) { rid_set_error("rid_gap_sweep: bad arguments"); return RID_ERR_ARG; }
-    if (subset == nullptr) m = dm->N;
-    if (Kmax >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); return RID_ERR_ARG; }
-    RID_TRY(pam_check_na(dm, subset, m));
     rid_ctx *ctx = dm->ctx;
     PamWs *w;
     RID_TRY(ws_get(dm, Kmax, &w));
     RID_TRY(pam_set_subset(dm, w, subset, m, true));
-    RID_TRY(rid_time_begin(ctx));
     RID_TRY(pam_begin(dm, w));
     RID_TRY(pam_build(dm, w, 0, Kmax));
     std::vector<int> order(Kmax);
@@ -1469,6 +1539,8 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
     RID_CUDA(cudaMemcpy(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice));
     int rc = RID_OK;
     for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
+        logW[k - 1] = 0.0;
+        if ((k - 1) % nshare != myshare) continue; // another rank's k
         double W = 0.0;
         if (k == 1) {
             rc = cudaMemsetAsync(w->lab_pos, 0, (size_t)m * sizeof(int), ctx->stream) == cudaSuccess ? RID_OK : RID_ERR_CUDA;
@@ -1485,6 +1557,34 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
         logW[k - 1] = log(W);
     }
     cudaFree(d_order);
+    return rc;
+}
+
+extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW)
+{
+    if (!dm || !logW || Kmax < 1) { rid_set_error("rid_gap_sweep: bad arguments"); return RID_ERR_ARG; }
+    if (subset == nullptr) m = dm->N;
+    if (Kmax >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); return RID_ERR_ARG; }
+    RID_TRY(pam_check_na(dm, subset, m));
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(rid_time_begin(ctx));
+    FullReplica R;
+    RID_TRY(replica_begin(dm, &R));
+    replica_local(&R, true);
+    // on a replica every rank repeats the (cheap, shared) BUILD and takes every world-th k of the sweep
+    int rc = gap_sweep_on(R.active ? &R.full : dm, subset, m, Kmax, logW, R.active ? R.saved_world : 1,
+                          R.active ? R.saved_rank : 0);
+    replica_local(&R, false);
+    if (R.active && rc == RID_OK) {
+        double *d_lw = nullptr;
+        if (cudaMalloc(&d_lw, (size_t)Kmax * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
+        if (rc == RID_OK && cudaMemcpyAsync(d_lw, logW, (size_t)Kmax * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
+        if (rc == RID_OK) rc = rid_allreduce_f64(ctx, d_lw, (size_t)Kmax);
+        if (rc == RID_OK && (cudaMemcpyAsync(logW, d_lw, (size_t)Kmax * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                             cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = RID_ERR_CUDA;
+        cudaFree(d_lw);
+    }
+    replica_end(&R);
     if (rc != RID_OK) return rc;
     return rid_time_end(ctx);
 }
@@ -1499,25 +1599,35 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     rid_ctx *ctx = dm->ctx;
     int N = dm->N;
     RID_TRY(rid_time_begin(ctx));
+    FullReplica R;
+    RID_TRY(replica_begin(dm, &R));
+    rid_dmat *work = R.active ? &R.full : dm; // the matrix the PAM runs read
+    const int nshare = R.active ? R.saved_world : 1, myshare = R.active ? R.saved_rank : 0;
+    replica_local(&R, true);
     std::vector<int> med_pos(k);
-    RID_TRY(pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr));
-    if (medoids) for (int c = 0; c < k; ++c) medoids[c] = med_pos[c]; // positions == cells for the full set
-    // c1 labels by cell (0-based) on the device
+    int rc = pam_run(work, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr);
     int *d_part = nullptr, *d_tab = nullptr;
-    RID_CUDA(cudaMalloc(&d_part, (size_t)N * sizeof(int)));
-    RID_CUDA(cudaMalloc(&d_tab, (size_t)k * k * sizeof(int)));
-    std::vector<int> p0(N);
-    for (int i = 0; i < N; ++i) p0[i] = partition[i] - 1;
-    RID_CUDA(cudaMemcpy(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-    PamWs *w = dm->ws;
+    if (rc == RID_OK && (cudaMalloc(&d_part, (size_t)N * sizeof(int)) != cudaSuccess ||
+                         cudaMalloc(&d_tab, (size_t)k * k * sizeof(int)) != cudaSuccess)) {
+        rid_set_error("rid_clusterboot: out of device memory");
+        rc = RID_ERR_NOMEM;
+    }
+    if (rc == RID_OK) {
+        if (medoids) for (int c = 0; c < k; ++c) medoids[c] = med_pos[c]; // positions == cells for the full set
+        std::vector<int> p0(N);
+        for (int i = 0; i < N; ++i) p0[i] = partition[i] - 1; // c1 labels by cell (0-based) on the device
+        if (cudaMemcpy(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) rc = RID_ERR_CUDA;
+    }
     std::vector<int> tab((size_t)k * k), blab, bmed(k);
     const int *sp = samples;
-    int rc = RID_OK;
-    for (int b = 0; b < B && rc == RID_OK; ++b) {
+    for (int b = 0; b < B && rc == RID_OK; sp += sample_len[b], ++b) {
         int m = sample_len[b];
+        for (int j = 0; j < k; ++j) bootresult[(size_t)b * k + j] = 0.0;
+        if (b % nshare != myshare) continue; // another rank's replicate
         blab.resize(m);
-        rc = pam_run(dm, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr);
+        rc = pam_run(work, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr);
         if (rc != RID_OK) break;
+        PamWs *w = work->ws;
         // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
         cudaMemsetAsync(d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
         LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset_cells, w->lab_pos, m, d_part, k, d_tab);
@@ -1539,10 +1649,22 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             }
             bootresult[(size_t)b * k + j] = best;
         }
-        sp += m;
     }
     cudaFree(d_part);
     cudaFree(d_tab);
+    replica_local(&R, false);
+    if (R.active && rc == RID_OK && B > 0) {
+        // every rank holds the columns of its own replicates and zeros elsewhere: one sum makes them whole
+        double *d_br = nullptr;
+        const size_t nb = (size_t)k * B;
+        if (cudaMalloc(&d_br, nb * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
+        if (rc == RID_OK && cudaMemcpyAsync(d_br, bootresult, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
+        if (rc == RID_OK) rc = rid_allreduce_f64(ctx, d_br, nb);
+        if (rc == RID_OK && (cudaMemcpyAsync(bootresult, d_br, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                             cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = RID_ERR_CUDA;
+        cudaFree(d_br);
+    }
+    replica_end(&R);
     if (rc != RID_OK) return rc;
     return rid_time_end(ctx);
 }
