@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--cln", type=int, default=30)
     ap.add_argument("--sat", type=int, default=0)
     ap.add_argument("--clustnr", type=int, default=30)
-    ap.add_argument("--bootnr", type=int, default=4)
+    ap.add_argument("--bootnr", type=int, default=50)
     ap.add_argument("--seed", type=int, default=1004)
     ap.add_argument("--cpu-cells", type=int, default=1200, help="cells in the CPU sample")
     ap.add_argument("--cpu-bootnr", type=int, default=2)

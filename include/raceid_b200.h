@@ -110,6 +110,11 @@ int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const int *sample_l
 int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_idx, int *cluster_ids, int *n_clusters);
 int rid_refresh(rid_dmat *dm, const int *medoid_idx, int k, int *labels);
 
+/* ---- row-wise nearest neighbours: apply(D, 1, function(x) head(order(x), K)) — R/RaceID.R:774,1123,
+ * R/VarID_functions.R:549, R/StemID.R:192 ("next" row of SURVEY §8f).  idx: K x N column-major (cell c's K neighbours
+ * contiguous, 0-based, ties to the lower index like order()); dist (nullable): the matching distances. */
+int rid_knn(rid_dmat *dm, int K, int *idx, double *dist);
+
 /* ---- W.k (R/RaceID_utils.R:39-53) for a given partition; used by tests and by callers of clusGapExt ---- */
 int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W);
 

@@ -247,6 +247,13 @@ extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
     for (auto &r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
     ctx->prof.clear();
     ctx->prof_on = enable ? 1 : 0;
+    // create the events up front: cudaEventCreate inside the timed region costs more than the kernels it brackets
+    if (enable)
+        while (ctx->prof_pool.size() < 65536) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            ctx->prof_pool.push_back(e);
+        }
     return RID_OK;
 }
 

@@ -206,17 +206,21 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             umma_commit(&tmem_full_bar);     // all accumulators final
         }
-    } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
+    }
+    __syncwarp();
+    {
+        // ===== epilogue, all 8 warps: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
+        // warp w may touch TMEM lanes 32*(w%4)..+31; warps w and w+4 share a lane quarter and split the 96 columns
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp - 4;          // TMEM lane quarter this warp may touch
+        const int q = warp & 3;
         const int r = q * 32 + lane;     // tile row = TMEM lane
         const int gi = i0 + r;
         const bool row_ok = gi < P.row0 + P.nloc;
         const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
         const bool zr = row_ok ? P.zero_var[gi] : false;
-        for (int c0 = 0; c0 < I8_BN; c0 += 16) {
+        const int cbeg = (warp >> 2) * (I8_BN / 2);
+        for (int c0 = cbeg; c0 < cbeg + I8_BN / 2; c0 += 16) {
             int a2[16], a3[16], a4[16], a5[16], a6[16];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             tmem_ld16(ta + 0 * I8_BN, a2);
@@ -248,12 +252,18 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 qv[c] = v;
             }
-            // direct store: 16 consecutive columns of row gi
+            // direct store: 16 consecutive columns of row gi (64-byte aligned: j0 and c0 are multiples of 16)
             if (row_ok) {
                 u32 *dst = P.D + (size_t)(gi - P.row0) * P.ld + j0 + c0;
+                if ((size_t)(j0 + c0 + 16) <= P.ld) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
+                    for (int c = 0; c < 16; c += 4)
+                        *reinterpret_cast<uint4 *>(dst + c) = make_uint4(qv[c], qv[c + 1], qv[c + 2], qv[c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
+                }
             }
             // mirror store: column gi of rows j0+c0..+15; a warp's 32 lanes write 128 contiguous bytes
 #pragma unroll

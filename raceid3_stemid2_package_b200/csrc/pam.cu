@@ -1738,3 +1738,152 @@ extern "C" int rid_refresh(rid_dmat *dm, const int *medoid_idx, int k, int *labe
     for (int i = 0; i < N; ++i) labels[i] = remap[labels[i]];
     return RID_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------------
+// Row-wise nearest neighbours over the resident matrix: apply(D, 1, function(x) head(order(x), K)) as used at
+// reference R/RaceID.R:774 (compdist's knn branch), :1123 (compfr), R/VarID_functions.R:549 (pruneKnn), R/StemID.R:192.
+// order() is stable, so ties go to the lower cell index.  One CTA per owned row: exact radix select of the K-th
+// smallest 32-bit distance (12 + 12 + 8 bits, three histogram passes over the row), then an index-ordered pick of the
+// ties, then a rank sort of the K winners.
+// ----------------------------------------------------------------------------------------------------------
+#define KNN_THREADS 256
+#define KNN_MAXK 256
+
+__device__ __forceinline__ int knn_block_excl_scan(int v, int *sh, int *total)
+{
+    // exclusive prefix sum over the CTA's threads (KNN_THREADS), result per thread; *total = sum
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) sh[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < KNN_THREADS / 32 ? sh[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < KNN_THREADS / 32) sh[lane] = s; // inclusive over warps
+    }
+    __syncthreads();
+    int base = w ? sh[w - 1] : 0;
+    *total = sh[KNN_THREADS / 32 - 1];
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn(const u32 *__restrict__ D, size_t ld, int row0, int nloc, int N, int K, double step, int *__restrict__ idx_out,
+      double *__restrict__ dist_out)
+{
+    __shared__ int hist[4096];
+    __shared__ int sh_scan[KNN_THREADS / 32];
+    __shared__ u32 sel_v[KNN_MAXK];
+    __shared__ int sel_i[KNN_MAXK];
+    __shared__ u32 s_prefix;
+    __shared__ int s_need, s_cnt;
+    const int lrow = blockIdx.x;
+    if (lrow >= nloc) return;
+    const u32 *row = D + (size_t)lrow * ld;
+
+    // ---- radix select: the K-th smallest value v* and how many entries are strictly below it ----
+    u32 prefix = 0;   // bits fixed so far
+    int need = K;     // rank still to find inside the current prefix bucket
+    const int shifts[3] = {20, 8, 0}, widths[3] = {12, 12, 8};
+    u32 mask = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int nb = 1 << widths[pass];
+        for (int i = threadIdx.x; i < nb; i += KNN_THREADS) hist[i] = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < N; j += KNN_THREADS) {
+            u32 v = row[j];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shifts[pass]) & (nb - 1)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0, b = 0;
+            for (; b < nb; ++b) {
+                if (run + hist[b] >= need) break;
+                run += hist[b];
+            }
+            s_prefix = prefix | ((u32)b << shifts[pass]);
+            s_need = need - run;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        need = s_need;
+        mask |= (u32)(nb - 1) << shifts[pass];
+        __syncthreads();
+    }
+    const u32 vstar = prefix; // K-th smallest value; `need` of the entries equal to it are wanted (lowest indices)
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    // ---- everything below v*, in any order (sorted afterwards) ----
+    for (int j = threadIdx.x; j < N; j += KNN_THREADS) {
+        u32 v = row[j];
+        if (v < vstar) {
+            int p = atomicAdd(&s_cnt, 1);
+            sel_v[p] = v;
+            sel_i[p] = j;
+        }
+    }
+    __syncthreads();
+    const int nless = s_cnt;
+    // ---- the first `need` entries equal to v*, by index ----
+    int taken = 0;
+    for (int j0 = 0; j0 < N && taken < need; j0 += KNN_THREADS) {
+        const int j = j0 + threadIdx.x;
+        const int hit = (j < N && row[j] == vstar) ? 1 : 0;
+        int total;
+        const int off = knn_block_excl_scan(hit, sh_scan, &total);
+        if (hit && taken + off < need) {
+            sel_v[nless + taken + off] = vstar;
+            sel_i[nless + taken + off] = j;
+        }
+        taken += total;
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- rank sort of the K winners by (value, index) ----
+    const int g = row0 + lrow;
+    for (int t = threadIdx.x; t < K; t += KNN_THREADS) {
+        const u32 v = sel_v[t];
+        const int i = sel_i[t];
+        int rank = 0;
+        for (int u = 0; u < K; ++u) rank += (sel_v[u] < v) || (sel_v[u] == v && sel_i[u] < i);
+        idx_out[(size_t)g * K + rank] = i;
+        if (dist_out) dist_out[(size_t)g * K + rank] = v == RID_Q_NA ? __longlong_as_double(0x7ff8000000000000LL) : (double)v * step;
+    }
+}
+
+extern "C" int rid_knn(rid_dmat *dm, int K, int *idx, double *dist)
+{
+    if (!dm || !idx || K < 1 || K > KNN_MAXK || K > dm->N) {
+        rid_set_error("rid_knn: K must be in 1..min(N, %d)", KNN_MAXK);
+        return RID_ERR_ARG;
+    }
+    rid_ctx *ctx = dm->ctx;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    const int N = dm->N, nloc = dm->row1 - dm->row0;
+    const size_t n = (size_t)N * K;
+    int *d_idx = nullptr;
+    double *d_dist = nullptr;
+    RID_CUDA(cudaMalloc(&d_idx, n * sizeof(int)));
+    if (dist) RID_CUDA(cudaMalloc(&d_dist, n * sizeof(double)));
+    RID_TRY(rid_time_begin(ctx));
+    RID_CUDA(cudaMemsetAsync(d_idx, 0, n * sizeof(int), ctx->stream));
+    if (dist) RID_CUDA(cudaMemsetAsync(d_dist, 0, n * sizeof(double), ctx->stream));
+    if (nloc) LAUNCH(ctx, k_knn, nloc, KNN_THREADS, 0, dm->D, dm->ld, dm->row0, nloc, N, K, dm->step, d_idx, d_dist);
+    RID_CUDA(cudaGetLastError());
+    RID_TRY(rid_allreduce_i32(ctx, d_idx, n)); // disjoint rows per rank
+    if (dist) RID_TRY(rid_allreduce_f64(ctx, d_dist, n));
+    RID_CUDA(cudaMemcpyAsync(idx, d_idx, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist) RID_CUDA(cudaMemcpyAsync(dist, d_dist, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = rid_time_end(ctx);
+    cudaFree(d_idx);
+    cudaFree(d_dist);
+    return rc;
+}

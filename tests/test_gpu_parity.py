@@ -217,6 +217,25 @@ def test_gap_sweep_within_disp_medoids_refresh(ctx, oracle):
     dm.free()
 
 
+def test_knn_matches_stable_order(ctx):
+    """rid_knn == apply(D, 1, function(x) head(order(x), K)) (R/RaceID.R:774): stable order, ties to the lower index."""
+    x, _ = _features(seed=12, G=80, N=700, C=4)
+    x[:, 300] = x[:, 20]
+    x[:, 301] = x[:, 20]
+    dm = ctx.dist(x, "spearman")
+    Dg = dm.as_matrix()
+    for K in (1, 11, 64):
+        idx, dist = dm.knn(K, with_dist=True)
+        ref = np.argsort(Dg, axis=1, kind="stable")[:, :K]
+        assert np.array_equal(idx, ref)
+        assert np.array_equal(dist, np.take_along_axis(Dg, ref, axis=1))
+    coarse = ctx.from_matrix(np.round(Dg * 8) / 8)  # massive ties
+    Dc = coarse.as_matrix()
+    assert np.array_equal(coarse.knn(25), np.argsort(Dc, axis=1, kind="stable")[:, :25])
+    coarse.free()
+    dm.free()
+
+
 def test_clusterboot_identical(ctx, oracle):
     from raceid3_stemid2_package_b200.scseq import bootstrap_samples
 
