@@ -61,7 +61,7 @@ int rid_shard_rows(int N, int rank, int world, int *row0, int *row1);
 /* Measurement hooks (bench.py): per-kernel CUDA-event timing on the library's own stream.
  * kind: 0 Gram/DMMA distance kernel (work = flops), 1 SWAP scan, 2 BUILD scan, 3 grouped column sums (W.k, medoids,
  * silhouette), 4 prep, 5 subset compaction, 6 int8 tcgen05 distance kernel (work = int8 ops), 7 incremental SWAP pass (work = algorithmic bytes; traffic = bytes requested from memory). */
-int rid_ctx_profile(rid_ctx *ctx, int enable);
+int rid_ctx_profile(rid_ctx *ctx, int kind_mask /* bit k = record kind k; -1 = all; 0 = stop */);
 int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, double *ms, double *work, double *traffic);
 /* Ceilings measured on the spot: issue rate of the FP64 tensor pipe (DMMA m8n8k4), TFLOP/s, and a read-only
  * 128-bit streaming loop over `gib` GiB of HBM, GB/s (MEASURED_PEAKS.json holds a copy figure and a bf16 figure only). */

@@ -75,7 +75,7 @@ enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_P
        RID_PROF_COMPACT = 5, RID_PROF_GRAM_I8 = 6, RID_PROF_SCAN_DELTA = 7, RID_PROF_NKINDS = 8 };
 
 // RAII-less helpers: call prof_begin right before the launch and prof_end right after it.
-cudaEvent_t rid_prof_begin(rid_ctx *ctx);
+cudaEvent_t rid_prof_begin(rid_ctx *ctx, int kind);
 void rid_prof_end(rid_ctx *ctx, cudaEvent_t a, int kind, double work, double traffic);
 
 int rid_allreduce_u64(rid_ctx *ctx, u64 *buf, size_t count);

@@ -222,9 +222,9 @@ static cudaEvent_t prof_event(rid_ctx *ctx)
     return e;
 }
 
-cudaEvent_t rid_prof_begin(rid_ctx *ctx)
+cudaEvent_t rid_prof_begin(rid_ctx *ctx, int kind)
 {
-    if (!ctx->prof_on) return nullptr;
+    if (!((ctx->prof_on >> kind) & 1)) return nullptr;
     cudaEvent_t a = prof_event(ctx);
     cudaEventRecord(a, ctx->stream);
     return a;
@@ -232,13 +232,13 @@ cudaEvent_t rid_prof_begin(rid_ctx *ctx)
 
 void rid_prof_end(rid_ctx *ctx, cudaEvent_t a, int kind, double work, double traffic)
 {
-    if (!ctx->prof_on || !a) return;
+    if (!a) return;
     cudaEvent_t b = prof_event(ctx);
     cudaEventRecord(b, ctx->stream);
     ctx->prof.push_back({kind, a, b, work, traffic});
 }
 
-// enable != 0: start collecting (clears what was collected); enable == 0: stop
+// enable: bit mask of kernel kinds to record (-1 = all; clears what was collected); 0: stop
 extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
 {
     if (!ctx) return RID_ERR_ARG;
@@ -246,14 +246,20 @@ extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
     ctx->prof.clear();
-    ctx->prof_on = enable ? 1 : 0;
+    ctx->prof_on = enable; // bit k set = record kernels of kind k (enable = -1: every kind)
     // create the events up front: cudaEventCreate inside the timed region costs more than the kernels it brackets
-    if (enable)
-        while (ctx->prof_pool.size() < 65536) {
+    if (enable) {
+        const size_t want = enable == -1 ? 40960 : 2048;
+        while (ctx->prof_pool.size() < want) {
             cudaEvent_t e = nullptr;
-            if (cudaEventCreate(&e) != cudaSuccess) break;
+            if (cudaEventCreateWithFlags(&e, cudaEventDefault) != cudaSuccess) break;
             ctx->prof_pool.push_back(e);
         }
+    } else {
+        // tens of thousands of live events slow every later synchronisation down: give them back
+        for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+        ctx->prof_pool.clear();
+    }
     return RID_OK;
 }
 

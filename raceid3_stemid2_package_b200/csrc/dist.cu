@@ -500,7 +500,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     if (prep_smem > 48 * 1024)
         DCHK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
     {
-        cudaEvent_t pe = rid_prof_begin(ctx);
+        cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_PREP);
         LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
         rid_prof_end(ctx, pe, RID_PROF_PREP, (double)G * N * 16.0, (double)G * N * 32.0);
     }
@@ -582,7 +582,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
             DCHK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM));
             dim3 grid((unsigned)(Np / GM_BN), (unsigned)((P.nloc + GM_BM - 1) / GM_BM));
             if (P.sym) grid = dim3((unsigned)((long long)P.tiles * (P.tiles + 1) / 2), 1u);
-            cudaEvent_t pe = rid_prof_begin(ctx);
+            cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_GRAM);
             LAUNCH(ctx, k_gram_dmma, grid, GM_THREADS, GM_SMEM, P);
             // work: flops actually issued (tiles computed x 2*128*128*G); the symmetric path issues about half of
             // the algorithmic 2*N*N*G and must not be credited with the tiles it did not compute

@@ -451,7 +451,7 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     // nobody may start storing mirror tiles into a peer before that peer has cleared its pad columns
     if (ctx->world > 1) RID_TRY(rid_barrier(ctx));
     dim3 grid((unsigned)tiles_n, (unsigned)std::max(tiles_loc, 1));
-    cudaEvent_t pe = rid_prof_begin(ctx);
+    cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_GRAM_I8);
     if (nloc > 0) {
         k_gram_i8<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
         ctx->launches++;

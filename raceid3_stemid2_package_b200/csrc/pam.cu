@@ -1005,7 +1005,7 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
                 // SP (BUILD step 0) is accumulated by the same pass
                 RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
                 dim3 grid((unsigned)((w->nls + COMPACT_ROWS - 1) / COMPACT_ROWS), (unsigned)((ldc + 511) / 512));
-                cudaEvent_t pe = rid_prof_begin(ctx);
+                cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->nls, w->colmap, w->cbuf, ldc, m,
                        w->acc + 4);
                 rid_prof_end(ctx, pe, RID_PROF_COMPACT, (double)w->nls * ((double)N + (double)m) * 4.0,
@@ -1062,7 +1062,7 @@ static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP,
     dim3 grid(strips, std::min(chunks, want_y * 2));
     u64 *SP = w->acc + 4, *AQ = SP + w->ld;
     // algorithmic bytes: every distance of the (rows x subset) block once; traffic: whole rows are read
-    cudaEvent_t pe = rid_prof_begin(ctx);
+    cudaEvent_t pe = rid_prof_begin(ctx, prof_kind);
     auto scan8 = k_scan<MODE, 8>;
     auto scan2 = k_scan<MODE, 2>;
     if (dm->bits <= 28)
@@ -1119,11 +1119,11 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         if (w->nls)
             LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, w->mat, w->ld, w->rows, w->nls, w->capP,
                    w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
-        if (ctx->prof_on)
+        if ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1)
             RID_CUDA(cudaMemcpyAsync(w->chg_hist + s, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         RID_CUDA(cudaGetLastError());
     }
-    if (ctx->prof_on && k_to > k_from) {
+    if (((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) && k_to > k_from) {
         // credit the incremental passes with the rows they really rescanned
         std::vector<int> hist(k_to);
         RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)k_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1206,7 +1206,7 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
         int chunks = (w->nls + rpc - 1) / rpc;
         dim3 grid(strips, std::min(chunks, want_y * 2));
         u64 *SP2 = w->acc2 + 4, *AQ2 = SP2 + w->ld;
-        cudaEvent_t pe = rid_prof_begin(ctx);
+        cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_DELTA);
         auto d8 = k_scan_delta<8>;
         auto d2 = k_scan_delta<2>;
         if (dm->bits <= 28)
@@ -1216,9 +1216,9 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
             LAUNCH(ctx, d2, grid, SCAN_THREADS, 0, w->mat, w->ld, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn,
                    w->chg_count, rpc, k, SP2, AQ2, w->state);
         rid_prof_end(ctx, pe, RID_PROF_SCAN_DELTA, 0.0, 0.0);
-        if (ctx->prof_on && *n_delta < CNT_HIST)
+        if (((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) && *n_delta < CNT_HIST)
             RID_CUDA(cudaMemcpyAsync(w->cnt_hist + *n_delta, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-        if (ctx->prof_on) ++*n_delta;
+        if ((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) ++*n_delta;
     }
     RID_TRY(rid_allreduce_u64(ctx, w->acc2, nacc));
     {
@@ -1283,7 +1283,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
         }
         if (h_state->done) break;
     }
-    if (ctx->prof_on && n_delta > 0) {
+    if (((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) && n_delta > 0) {
         // credit the delta passes with the rows they really rescanned
         int cnt = std::min(n_delta, CNT_HIST);
         std::vector<int> hist(cnt);

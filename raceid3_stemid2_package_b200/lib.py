@@ -140,8 +140,18 @@ class Context:
 
     PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4, "compact": 5, "gram_i8": 6, "scan_delta": 7}
 
-    def profile(self, enable: bool = True):
-        _check(load().rid_ctx_profile(self._h, 1 if enable else 0))
+    def profile(self, kinds=True):
+        """kinds: True = every kernel kind, False/None = off, or a list of kind names (see PROF_KINDS) — recording only
+        the kernels a roofline needs keeps the timed region free of tens of thousands of CUDA events."""
+        if kinds is True:
+            mask = -1
+        elif not kinds:
+            mask = 0
+        else:
+            mask = 0
+            for k in kinds:
+                mask |= 1 << self.PROF_KINDS[k]
+        _check(load().rid_ctx_profile(self._h, mask))
 
     def profile_get(self, kind: str) -> dict:
         n, ms, work, tr = C.c_longlong(), C.c_double(), C.c_double(), C.c_double()
