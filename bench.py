@@ -258,7 +258,8 @@ def main():
         step(True)
     barrier()
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:  # one sampler per job: eight concurrent nvidia-smi pollers slow every rank's driver calls down
+        clocks.start()
     # inside the timed region only the kernels the roofline objects need are bracketed with CUDA events (~100 per step);
     # the full per-kind breakdown comes from one extra, untimed step below
     ctx.profile(["gram", "gram_i8", "scan_swap"])

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <future>
 #include <vector>
 
 #include "common.cuh"
@@ -44,7 +45,23 @@ struct Cand {
     int p, mp, slot;
 };
 
+struct HostSubset {
+    int m = 0, N = 0;
+    bool want_compact = false; // a proper subset large enough to be worth a compact copy
+    int err = 0;
+    char errmsg[96] = {0};
+    std::vector<int> cells;    // cell by position
+    std::vector<int> pos_of;   // [N] position by cell or -1
+    std::vector<int> src;      // owned subset rows (cell order) as rows of the shard
+    std::vector<int> rows_pos; // their positions
+    std::vector<int> iota;     // 0..nls-1 (rows of the compact copy)
+    std::vector<int> subset_c; // compact column by position
+    std::vector<int> pos_c;    // position by compact column
+    std::vector<int> ccells;   // cell by compact column (the sorted subset)
+};
+
 struct PamWs {
+    HostSubset hs; // tables of the current subset when nobody prepared them ahead
     int N = 0;
     size_t ld = 0;
     int nloc = 0; // owned rows
@@ -96,7 +113,6 @@ struct PamWs {
     int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
-    std::vector<int> h_subset, h_rows, h_rows_pos, h_pos_of, h_cells, h_colmap, h_src;
 };
 
 static void ws_free_groups(PamWs *w)
@@ -914,51 +930,70 @@ static int pam_check_na(rid_dmat *dm, const int *subset, int m)
     return RID_OK;
 }
 
-// Install the subset (positions -> cells) and the list of owned subset rows.
-// want_compact: the caller will make many passes (PAM): if the subset is a proper subset, copy D[subset, subset] into
-// a compact matrix once (columns in sorted-cell order; tie-breaking still follows the POSITIONS) so that every later
-// pass reads only the distances it needs instead of whole rows of the resident matrix.
+// ---- subset installation -----------------------------------------------------------------------------------------
+// The host tables of a subset depend only on (N, owned row range, subset): they can be prepared on another thread while
+// the GPU is still busy with the previous bootstrap replicate.
 #define RID_COMPACT_MIN_BYTES ((size_t)1 << 20)
-static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool want_compact)
+static void host_subset_prepare(HostSubset *H, int N, int row0, int row1, const int *subset, int m, bool want_compact)
 {
-    rid_ctx *ctx = dm->ctx;
-    int N = dm->N;
+    H->err = 0;
+    H->m = m;
+    H->N = N;
     if (m < 1 || m > N) {
-        rid_set_error("subset size %d out of range", m);
-        return RID_ERR_ARG;
+        H->err = RID_ERR_ARG;
+        snprintf(H->errmsg, sizeof(H->errmsg), "subset size %d out of range", m);
+        return;
     }
-    w->h_cells.resize(m);
-    w->h_pos_of.assign(N, -1);
+    H->cells.resize(m);
+    H->pos_of.assign(N, -1);
     for (int p = 0; p < m; ++p) {
         int h = subset ? subset[p] : p;
-        if (h < 0 || h >= N) {
-            rid_set_error("subset index %d out of range", h);
-            return RID_ERR_ARG;
+        if (h < 0 || h >= N || H->pos_of[h] != -1) {
+            H->err = RID_ERR_ARG;
+            snprintf(H->errmsg, sizeof(H->errmsg), h < 0 || h >= N ? "subset index %d out of range" : "subset holds cell %d twice", h);
+            return;
         }
-        if (w->h_pos_of[h] != -1) {
-            rid_set_error("subset holds cell %d twice", h);
-            return RID_ERR_ARG;
-        }
-        w->h_cells[p] = h;
-        w->h_pos_of[h] = p;
+        H->cells[p] = h;
+        H->pos_of[h] = p;
     }
-    w->m = m;
-    bool compact = want_compact && m < N && (size_t)m * (size_t)m * sizeof(u32) >= RID_COMPACT_MIN_BYTES;
+    H->want_compact = want_compact && m < N && (size_t)m * (size_t)m * sizeof(u32) >= RID_COMPACT_MIN_BYTES;
     // owned subset rows in cell order (any order works: all sums are exact integers)
-    w->h_rows.clear(); w->h_rows_pos.clear(); w->h_src.clear();
-    if (compact) {
-        // compact column of a cell = its rank among the subset's cells
-        w->h_colmap.assign(N, -1);
-        int sidx = 0;
+    H->src.clear(); H->rows_pos.clear();
+    for (int h = row0; h < row1; ++h)
+        if (H->pos_of[h] >= 0) {
+            H->src.push_back(h - row0);
+            H->rows_pos.push_back(H->pos_of[h]);
+        }
+    if (H->want_compact) {
+        // compact column of a cell = its rank among the subset's cells; positions index compact columns
+        H->ccells.resize(m);
+        H->subset_c.resize(m);
+        H->pos_c.resize(m);
+        int c = 0;
         for (int h = 0; h < N; ++h)
-            if (w->h_pos_of[h] >= 0) w->h_colmap[h] = sidx++;
-        for (int h = dm->row0; h < dm->row1; ++h)
-            if (w->h_pos_of[h] >= 0) {
-                w->h_rows.push_back((int)w->h_src.size()); // compact local row = running index
-                w->h_src.push_back(h - dm->row0);
-                w->h_rows_pos.push_back(w->h_pos_of[h]);
+            if (H->pos_of[h] >= 0) {
+                H->ccells[c] = h;
+                H->subset_c[H->pos_of[h]] = c;
+                H->pos_c[c] = H->pos_of[h];
+                ++c;
             }
-        w->nls = (int)w->h_rows.size();
+        H->iota.resize(H->src.size());
+        for (size_t t = 0; t < H->iota.size(); ++t) H->iota[t] = (int)t;
+    }
+}
+
+// want_compact: the caller will make many passes (PAM): a proper subset is copied once into a compact matrix
+// D[subset, subset] (columns in sorted-cell order; tie-breaking still follows the POSITIONS) so that every later pass
+// reads only the distances it needs instead of whole rows of the resident matrix.
+static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H)
+{
+    rid_ctx *ctx = dm->ctx;
+    const int N = dm->N, m = H.m;
+    if (H.err) { rid_set_error("%s", H.errmsg); return H.err; }
+    w->m = m;
+    w->nls = (int)H.src.size();
+    bool compact = H.want_compact;
+    if (compact) {
         const size_t ldc = round_up((size_t)m, 128);
         const size_t need = std::max<size_t>((size_t)w->nls, 1) * ldc * sizeof(u32);
         int ok = 1;
@@ -981,29 +1016,16 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
         }
         if (!ok) compact = false; // not enough memory somewhere: scan the resident matrix through the row list
         else {
-            // positions index compact columns: subset[p] = compact column, pos_of[compact column] = p
-            w->h_subset.resize(m);
-            std::vector<int> pos_c(m);
-            for (int p = 0; p < m; ++p) {
-                int c = w->h_colmap[w->h_cells[p]];
-                w->h_subset[p] = c;
-                pos_c[c] = p;
-            }
-            RID_CUDA(cudaMemcpyAsync(w->subset, w->h_subset.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->pos_of, pos_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            // compact column -> cell (the sorted subset); reuses the colmap device buffer
-            std::vector<int> ccells(m);
-            for (int h = 0; h < N; ++h)
-                if (w->h_colmap[h] >= 0) ccells[w->h_colmap[h]] = h;
-            RID_CUDA(cudaMemcpyAsync(w->colmap, ccells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaStreamSynchronize(ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->subset_cells, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->subset, H.subset_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->pos_of, H.pos_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->colmap, H.ccells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->subset_cells, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            // SP (BUILD step 0) is accumulated by the compaction pass
+            RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
             if (w->nls) {
-                RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                RID_CUDA(cudaMemcpyAsync(w->src_rows, w->h_src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                // SP (BUILD step 0) is accumulated by the same pass
-                RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->rows, H.iota.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->rows_pos, H.rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->src_rows, H.src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 dim3 grid((unsigned)((w->nls + COMPACT_ROWS - 1) / COMPACT_ROWS), (unsigned)((ldc + 511) / 512));
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->nls, w->colmap, w->cbuf, ldc, m,
@@ -1012,8 +1034,7 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
                              (double)w->nls * ((double)dm->ld + (double)ldc) * 4.0);
                 RID_CUDA(cudaGetLastError());
             }
-            if (!w->nls) RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
-            RID_CUDA(cudaStreamSynchronize(ctx->stream)); // pos_c is a local
+            // pageable host buffers: the async copies above have been staged by the time the calls return
             w->mat = w->cbuf;
             w->ld = ldc;
             w->compact = true;
@@ -1026,23 +1047,24 @@ static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool
     w->sp0_ready = false;
     w->mat = dm->D;
     w->ld = dm->ld;
-    w->h_rows.clear(); w->h_rows_pos.clear();
-    for (int h = dm->row0; h < dm->row1; ++h)
-        if (w->h_pos_of[h] >= 0) {
-            w->h_rows.push_back(h - dm->row0);
-            w->h_rows_pos.push_back(w->h_pos_of[h]);
-        }
-    w->nls = (int)w->h_rows.size();
-    RID_CUDA(cudaMemcpyAsync(w->subset, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_CUDA(cudaMemcpyAsync(w->subset_cells, w->h_cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_CUDA(cudaMemcpyAsync(w->pos_of, w->h_pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->subset, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->subset_cells, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->pos_of, H.pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (w->nls) {
-        RID_CUDA(cudaMemcpyAsync(w->rows, w->h_rows.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        RID_CUDA(cudaMemcpyAsync(w->rows_pos, w->h_rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->rows, H.src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->rows_pos, H.rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
-    // the host vectors are reused by the next call; make sure the copies are done
-    RID_CUDA(cudaStreamSynchronize(ctx->stream));
     return RID_OK;
+}
+
+static int pam_set_subset(rid_dmat *dm, PamWs *w, const int *subset, int m, bool want_compact, HostSubset *prepared = nullptr)
+{
+    if (prepared) return pam_install_subset(dm, w, *prepared);
+    host_subset_prepare(&w->hs, dm->N, dm->row0, dm->row1, subset, m, want_compact);
+    int rc = pam_install_subset(dm, w, w->hs);
+    // w->hs is reused by the next call: make sure the (pageable, hence already staged) copies are really done
+    if (rc == RID_OK) RID_CUDA(cudaStreamSynchronize(dm->ctx->stream));
+    return rc;
 }
 
 // nrows_ub: upper bound of the row count known on the host (grid sizing); nrows_dev: optional exact count on the
@@ -1367,7 +1389,7 @@ static void number_clusters(const std::vector<int> &slot_by_pos, int k, const st
 }
 
 static int pam_run(rid_dmat *dm, const int *subset, int m, int k, int *medoids, int *labels, double *objective,
-                   double *avg_sil, int *n_swaps)
+                   double *avg_sil, int *n_swaps, HostSubset *prepared = nullptr)
 {
     if (!dm) { rid_set_error("null distance matrix"); return RID_ERR_ARG; }
     if (subset == nullptr) m = dm->N;
@@ -1378,7 +1400,7 @@ static int pam_run(rid_dmat *dm, const int *subset, int m, int k, int *medoids, 
     RID_TRY(pam_check_na(dm, subset, m));
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
-    RID_TRY(pam_set_subset(dm, w, subset, m, true));
+    RID_TRY(pam_set_subset(dm, w, subset, m, true, prepared));
     RID_TRY(pam_begin(dm, w));
     RID_TRY(pam_build(dm, w, 0, k));
     PamState hs;
@@ -1619,13 +1641,33 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         if (cudaMemcpy(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) rc = RID_ERR_CUDA;
     }
     std::vector<int> tab((size_t)k * k), blab, bmed(k);
-    const int *sp = samples;
-    for (int b = 0; b < B && rc == RID_OK; sp += sample_len[b], ++b) {
-        int m = sample_len[b];
-        for (int j = 0; j < k; ++j) bootresult[(size_t)b * k + j] = 0.0;
-        if (b % nshare != myshare) continue; // another rank's replicate
+    // this rank's replicates; the host tables of the next one are prepared on a helper thread while the GPU works
+    std::vector<int> mine;
+    std::vector<const int *> ptr(B);
+    {
+        const int *sp = samples;
+        for (int b = 0; b < B; ++b) {
+            ptr[b] = sp;
+            sp += sample_len[b];
+            for (int j = 0; j < k; ++j) bootresult[(size_t)b * k + j] = 0.0;
+            if (b % nshare == myshare) mine.push_back(b);
+        }
+    }
+    HostSubset prep[2];
+    std::future<void> fut;
+    auto launch_prep = [&](size_t i) {
+        const int b = mine[i];
+        fut = std::async(std::launch::async, host_subset_prepare, &prep[i & 1], work->N, work->row0, work->row1, ptr[b],
+                         sample_len[b], true);
+    };
+    if (!mine.empty() && rc == RID_OK) launch_prep(0);
+    for (size_t i = 0; i < mine.size() && rc == RID_OK; ++i) {
+        const int b = mine[i], m = sample_len[b];
+        const int *sp = ptr[b];
+        fut.get();
+        if (i + 1 < mine.size()) launch_prep(i + 1);
         blab.resize(m);
-        rc = pam_run(work, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr);
+        rc = pam_run(work, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr, &prep[i & 1]);
         if (rc != RID_OK) break;
         PamWs *w = work->ws;
         // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
@@ -1650,6 +1692,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             bootresult[(size_t)b * k + j] = best;
         }
     }
+    if (fut.valid()) fut.wait();
     cudaFree(d_part);
     cudaFree(d_tab);
     replica_local(&R, false);
