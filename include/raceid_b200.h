@@ -78,6 +78,11 @@ int rid_ctx_event_elapsed_ms(rid_ctx *ctx, int slot_a, int slot_b, double *ms);
  * n_zero_var: number of zero-variance cells (cor() returns NA for them and warns; their rows/cols are NA). */
 int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric, int x_on_device, rid_dmat **out,
              int *n_zero_var);
+/* Same, fused with getfdata (R/RaceID.R:723-728, "next" row of SURVEY §8f-2): the filtered count matrix in the package's
+ * native dgCMatrix storage (CSC: row_idx/col_ptr/val over the kept cells, n_rows_all genes), counts[c] = the cell's
+ * total, feature_rows[g] = matrix row of feature g.  x = (val / counts[c]) * min(counts) + 0.1 is built on the device. */
+int rid_dist_csc(rid_ctx *ctx, const int *row_idx, const int *col_ptr, const double *val, int n_rows_all, int N,
+                 const int *feature_rows, int G, const double *counts, int metric, rid_dmat **out, int *n_zero_var);
 /* Adopt a distance matrix computed elsewhere (clustexp() only needs @distances, R/RaceID.R:903,907).
  * D: N x N column-major.  Like as.dist() the LOWER triangle is authoritative and is mirrored. */
 int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat **out);

@@ -784,3 +784,72 @@ extern "C" int rid_measure_read_peak(rid_ctx *ctx, double gib, double *gbs)
     rid_pool_free(ctx, buf, bytes);
     return RID_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------------
+// Fused getfdata -> prep from the package's native storage ("next" row of SURVEY §8f-2): the filtered count matrix is
+// a dgCMatrix (CSC: i, p, x); getfdata (R/RaceID.R:723-728) makes (ndata * min(counts))[genes, cells] + 0.1 dense on the
+// host and compdist transposes it twice (R/RaceID.R:764,769).  Here the CSC triplet goes to the device as is (about a
+// tenth of the dense bytes for UMI data) and one kernel writes the dense feature matrix the prep kernel reads.
+// ----------------------------------------------------------------------------------------------------------
+__global__ void k_csc_to_features(const int *__restrict__ row_idx, const int *__restrict__ col_ptr,
+                                  const double *__restrict__ val, const int *__restrict__ feat_of_row, int G,
+                                  const double *__restrict__ counts, double mincount, double *__restrict__ x)
+{
+    const int c = blockIdx.x;
+    double *col = x + (size_t)c * G;
+    for (int k = threadIdx.x; k < G; k += blockDim.x) col[k] = 0.1; // 0 * min(counts) + .1
+    __syncthreads();
+    const double cnt = counts[c];
+    for (int t = col_ptr[c] + threadIdx.x; t < col_ptr[c + 1]; t += blockDim.x) {
+        const int f = feat_of_row[row_idx[t]];
+        // ((expdata / counts) * min(counts)) + .1 in R's order, each step rounded (no FMA contraction)
+        if (f >= 0) col[f] = __dadd_rn(__dmul_rn(__ddiv_rn(val[t], cnt), mincount), 0.1);
+    }
+}
+
+extern "C" int rid_dist_csc(rid_ctx *ctx, const int *row_idx, const int *col_ptr, const double *val, int n_rows_all, int N,
+                            const int *feature_rows, int G, const double *counts, int metric, rid_dmat **out,
+                            int *n_zero_var)
+{
+    if (!ctx || !row_idx || !col_ptr || !val || !feature_rows || !counts || !out || N < 2 || G < 2 || n_rows_all < G) {
+        rid_set_error("rid_dist_csc: bad arguments");
+        return RID_ERR_ARG;
+    }
+    RID_CUDA(cudaSetDevice(ctx->device));
+    const size_t nnz = (size_t)col_ptr[N];
+    std::vector<int> feat(n_rows_all, -1);
+    for (int g = 0; g < G; ++g) {
+        if (feature_rows[g] < 0 || feature_rows[g] >= n_rows_all) { rid_set_error("feature row out of range"); return RID_ERR_ARG; }
+        feat[feature_rows[g]] = g;
+    }
+    double mincount = counts[0];
+    for (int c = 1; c < N; ++c) mincount = std::min(mincount, counts[c]);
+    int *d_i = nullptr, *d_p = nullptr, *d_f = nullptr;
+    double *d_v = nullptr, *d_c = nullptr, *d_x = nullptr;
+    const size_t x_bytes = (size_t)G * N * sizeof(double);
+    int rc = RID_OK;
+    auto done = [&](int code) {
+        cudaFree(d_i); cudaFree(d_p); cudaFree(d_f); cudaFree(d_v); cudaFree(d_c);
+        rid_pool_free(ctx, d_x, x_bytes);
+        return code;
+    };
+    if (cudaMalloc(&d_i, std::max<size_t>(nnz, 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_p, ((size_t)N + 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&d_f, (size_t)n_rows_all * sizeof(int)) != cudaSuccess || cudaMalloc(&d_v, std::max<size_t>(nnz, 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_c, (size_t)N * sizeof(double)) != cudaSuccess || rid_pool_alloc(ctx, (void **)&d_x, x_bytes) != cudaSuccess) {
+        rid_set_error("rid_dist_csc: out of device memory");
+        cudaGetLastError();
+        return done(RID_ERR_NOMEM);
+    }
+    cudaMemcpyAsync(d_i, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_p, col_ptr, ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_f, feat.data(), (size_t)n_rows_all * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_v, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_c, counts, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    LAUNCH(ctx, k_csc_to_features, N, 256, 0, d_i, d_p, d_v, d_f, G, d_c, mincount, d_x);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        rid_set_error("rid_dist_csc: building the feature matrix failed");
+        return done(RID_ERR_CUDA);
+    }
+    rc = rid_dist(ctx, d_x, G, N, metric, 1, out, n_zero_var);
+    return done(rc);
+}

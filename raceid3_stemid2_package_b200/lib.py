@@ -18,7 +18,7 @@ METRIC_CODES = {"pearson": 0, "spearman": 1, "logpearson": 2, "euclidean": 3}
 # every symbol include/raceid_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
-    "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
+    "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dist_csc", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
     "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn",
 ]
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
     L.rid_ctx_event_record.argtypes = [vp, C.c_int]
     L.rid_ctx_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rid_dist.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.rid_dist_csc.argtypes = [vp, ip, ip, dp, C.c_int, C.c_int, ip, C.c_int, dp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
     L.rid_dmat_from_host.argtypes = [vp, dp, C.c_int, C.POINTER(vp)]
     L.rid_dmat_free.argtypes = [vp]
     L.rid_dmat_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -202,6 +203,17 @@ class Context:
         h = C.c_void_p()
         nz = C.c_int(0)
         _check(load().rid_dist(self._h, _p(x), G, N, METRIC_CODES[metric], 0, C.byref(h), C.byref(nz)))
+        return DistMatrix(self, h, nz.value)
+
+    def dist_csc(self, indices, indptr, data, n_rows_all: int, feature_rows, counts, metric: str = "pearson") -> "DistMatrix":
+        """compdist straight from the filtered dgCMatrix (CSC over the kept cells): getfdata is fused on the device."""
+        i, p_, fr = _i32(indices), _i32(indptr), _i32(feature_rows)
+        v = np.ascontiguousarray(data, dtype=np.float64)
+        c = np.ascontiguousarray(counts, dtype=np.float64)
+        h = C.c_void_p()
+        nz = C.c_int(0)
+        _check(load().rid_dist_csc(self._h, _p(i), _p(p_), _p(v), n_rows_all, len(c), _p(fr), len(fr), _p(c),
+                                   METRIC_CODES[metric], C.byref(h), C.byref(nz)))
         return DistMatrix(self, h, nz.value)
 
     def from_matrix(self, D: np.ndarray) -> "DistMatrix":

@@ -217,6 +217,30 @@ def test_gap_sweep_within_disp_medoids_refresh(ctx, oracle):
     dm.free()
 
 
+def test_dist_from_csc_equals_dense_getfdata_path(ctx):
+    """rid_dist_csc (getfdata fused on the device, from the dgCMatrix triplet) == the dense getfdata -> rid_dist path."""
+    import raceid3_stemid2_package_b200 as rid
+    from scipy.sparse import csc_matrix
+
+    rng = np.random.default_rng(5)
+    counts_gc = rng.poisson(0.4, size=(400, 260)).astype(np.float64) * (1.0 + rng.random((400, 260)))
+    counts_gc[:, counts_gc.sum(0) == 0] = 1.0
+    sc = rid.SCseq(counts_gc)
+    sc = rid.filterdata(sc, mintotal=1, minexpr=1, minnumber=3)
+    feats = sc.cluster["features"]
+    assert len(feats) >= 10
+    x = rid.getfdata(sc, g=feats)
+    keep = np.asarray([i for i, c in enumerate(sc.cells_all) if c in set(sc.cell_names)])
+    sp = csc_matrix(counts_gc[:, keep])
+    frows = np.asarray([sc.genes_all.index(g) for g in sc.genes_all if g in set(feats)], dtype=np.int32)
+    for metric in ("pearson", "spearman"):
+        a = ctx.dist(x, metric)
+        b = ctx.dist_csc(sp.indices, sp.indptr, sp.data, counts_gc.shape[0], frows, sc.counts, metric)
+        assert np.array_equal(a.as_matrix(), b.as_matrix())
+        a.free()
+        b.free()
+
+
 def test_knn_matches_stable_order(ctx):
     """rid_knn == apply(D, 1, function(x) head(order(x), K)) (R/RaceID.R:774): stable order, ties to the lower index."""
     x, _ = _features(seed=12, G=80, N=700, C=4)
