@@ -262,7 +262,7 @@ def main():
         clocks.start()
     # inside the timed region only the kernels the roofline objects need are bracketed with CUDA events (~100 per step);
     # the full per-kind breakdown comes from one extra, untimed step below
-    ctx.profile(["gram", "gram_i8", "scan_swap"])
+    ctx.profile(["gram", "gram_i8", "scan_swap", "compact"])
     l0 = ctx.launches
     barrier()
     ctx.event_record(0)
@@ -329,6 +329,17 @@ def main():
                       "algorithmic_bytes_per_launch": sw["work"] / sw["launches"],
                       "requested_bytes_per_launch": sw["traffic"] / sw["launches"],
                       "share_of_step": sw["ms"] / step_ms_total})
+    cp = prof["compact"]
+    if cp["launches"]:
+        ach = cp["work"] / (cp["ms"] * 1e-3) / 1e9
+        roofs.append({"bound": "hbm", "kernel": "k_compact (D[bsamp,bsamp] copy of a bootstrap replicate, fused with BUILD step 0)",
+                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                      "peak_source": hbm_src, "launches": cp["launches"], "avg_launch_ms": cp["ms"] / cp["launches"],
+                      "algorithmic_bytes_per_launch": cp["work"] / cp["launches"],
+                      "requested_bytes_per_launch": cp["traffic"] / cp["launches"],
+                      "note": "bytes = rows read (subset rows x N x 4) + compact rows written (subset^2 x 4); ncu: DRAM "
+                              "bytes / requested = 1.03 (profiles/r1_final_ncu_k_compact.txt)",
+                      "share_of_step": cp["ms"] / step_ms_total})
     gm = prof["gram"]
     if gm["launches"]:
         ach = gm["work"] / (gm["ms"] * 1e-3) / 1e12

@@ -1621,13 +1621,15 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     rid_ctx *ctx = dm->ctx;
     int N = dm->N;
     RID_TRY(rid_time_begin(ctx));
+    // c1 = PAM on all cells: every rank scans its own row shard (1/world of the bytes), before any replica exists
+    std::vector<int> med_pos(k);
+    int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr);
+    if (rc != RID_OK) return rc;
     FullReplica R;
     RID_TRY(replica_begin(dm, &R));
-    rid_dmat *work = R.active ? &R.full : dm; // the matrix the PAM runs read
+    rid_dmat *work = R.active ? &R.full : dm; // the matrix the bootstrap PAM runs read
     const int nshare = R.active ? R.saved_world : 1, myshare = R.active ? R.saved_rank : 0;
     replica_local(&R, true);
-    std::vector<int> med_pos(k);
-    int rc = pam_run(work, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr);
     int *d_part = nullptr, *d_tab = nullptr;
     if (rc == RID_OK && (cudaMalloc(&d_part, (size_t)N * sizeof(int)) != cudaSuccess ||
                          cudaMalloc(&d_tab, (size_t)k * k * sizeof(int)) != cudaSuccess)) {

@@ -183,6 +183,67 @@ def test_pam_ties_duplicates_and_from_matrix(ctx, oracle):
     dm.free()
 
 
+def test_pam_edge_cases_and_swap_heavy_matrices(ctx, oracle):
+    """Tiny and degenerate inputs, k = n-1, and structure-free matrices where SWAP does many iterations (the incremental
+    delta passes carry almost all of the work there), on both fixed-point grids (28-bit for D <= 2, 31-bit otherwise)."""
+    rng = np.random.default_rng(11)
+    # n = 3 and n = 4, every legal k
+    for n in (3, 4):
+        A = rng.random((n, n))
+        D = np.round((A + A.T) * 16) / 16
+        np.fill_diagonal(D, 0.0)
+        dm = ctx.from_matrix(D)
+        for k in range(1, n):
+            _check_pam(dm, oracle, dm.as_matrix(), k)
+        dm.free()
+    # low-dimensional point clouds without cluster structure: SWAP needs 10-20 iterations (uniform line / exponential
+    # plane), on the 28-bit grid (scaled below 2) and on the 31-bit grid (large distances)
+    for name, pts, scale in (("line", rng.random((300, 1)), 1.9), ("plane", rng.exponential(size=(257, 2)), 400.0)):
+        D = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+        D = D / D.max() * scale
+        dm = ctx.from_matrix(D)
+        Dg = dm.as_matrix()
+        assert np.max(np.abs(Dg - D)) <= dm.step
+        total_swaps = 0
+        for k in (2, 10, 25):
+            total_swaps += _check_pam(dm, oracle, Dg, k)["n_swaps"]
+        assert total_swaps >= 15  # really exercises the incremental SWAP passes
+        sub = rng.permutation(len(D))[: len(D) // 2].astype(np.int32)
+        _check_pam(dm, oracle, Dg, 6, subset=sub)
+        lw = dm.gap_sweep(9)
+        assert np.max(np.abs(lw - oracle.gap_sweep(Dg, 9))) < 1e-12
+        dm.free()
+    # k = n - 1 on a structure-free matrix
+    A = rng.random((64, 64))
+    D = np.triu(A, 1)
+    D = D + D.T
+    dm = ctx.from_matrix(D)
+    _check_pam(dm, oracle, dm.as_matrix(), 63)
+    dm.free()
+    # subset of two cells, k = 1
+    D = np.array([[0, 1, 2, 3], [1, 0, 4, 5], [2, 4, 0, 6], [3, 5, 6, 0]], dtype=np.float64)
+    dm = ctx.from_matrix(D)
+    _check_pam(dm, oracle, dm.as_matrix(), 1, subset=np.array([3, 1], dtype=np.int32))
+    dm.free()
+
+
+def test_pam_all_ties(ctx, oracle):
+    """Every off-diagonal distance equal: every decision is a tie.  SWAP never improves; BUILD's later picks follow the
+    largest-index rule exactly.  (BUILD's FIRST pick on exactly tied row sums is where the FP64 oracle's rounding noise
+    may differ from the exact device sums — DESIGN.md §6 — so only objectives and the swap count are compared there.)"""
+    n = 40
+    D = np.full((n, n), 0.75)
+    np.fill_diagonal(D, 0.0)
+    dm = ctx.from_matrix(D)
+    for k in (1, 2, 5):
+        r = dm.pam(k)
+        ro = oracle.pam(D, k)
+        assert r["n_swaps"] == ro["n_swaps"] == 0
+        assert np.allclose(r["objective"], ro["objective"], atol=1e-13)
+        assert sorted(r["id_med"].tolist())[1:] == sorted(ro["id_med"].tolist())[1:] or k == 1
+    dm.free()
+
+
 def test_from_matrix_lower_triangle_rule_and_errors(ctx):
     from raceid3_stemid2_package_b200.lib import RaceIDError
 
