@@ -138,20 +138,57 @@ def run_reference(a):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region.  In-process NVML polling (one cheap call per 250 ms); a
+    polling `nvidia-smi -lms` process proved intrusive (it stretched driver calls of the timed step on some boxes) and is
+    only the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device):
         self.device = device
         self.rows = []
         self.proc = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self._thr = None
+        self.how = None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[0].isdigit() else self.device
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mx.append(float(mx))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for name, bit in self.BITS.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.25)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "500", "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "1000", "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -160,9 +197,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(1.0)
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
         for r in self.rows:
             p = [t.strip() for t in r.split(",")]
             if len(p) < 7:
@@ -177,7 +217,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [c for c in sm if c > 0]
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": self.how}
 
 
 # ---------------------------------------------------------------------------------------------------------------
