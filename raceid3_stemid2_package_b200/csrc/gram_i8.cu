@@ -70,6 +70,20 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar,
+                                               uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
 // version=1 | layout=SWIZZLE_128B(2)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
@@ -86,6 +100,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
@@ -112,6 +132,7 @@ struct I8Params {
     // row-block sharding: this rank owns rows [row0, row0+nloc); rank b owns [b*per, ...).  Every off-diagonal pair of
     // shards is computed by exactly one of its two owners, which stores the mirror image into the peer's shard (NVLink).
     int row0, nloc, world, rank, per;
+    int tiles_loc, tiles_n;
     u32 *peer[16];
 };
 
@@ -125,28 +146,49 @@ __device__ __host__ __forceinline__ bool i8_pair_mine(int me, int b, int world, 
     return (((i0 / 384) + (j0 / 384)) & 1) == (me < b ? 0 : 1);
 }
 
+// CL = 1: one CTA per tile.  CL = 2: 2 x 2 thread-block clusters; the two CTAs of a cluster row share their A panel and
+// the two CTAs of a cluster column their B panel: each loads HALF of either panel and TMA-multicasts it to its partner,
+// which halves the operand traffic out of L2 (the kernel's bottleneck).  A stage may be refilled only after this CTA and
+// both partners have consumed it, so every MMA commit arrives on three CTAs' "empty" barriers.
+template <int CL>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, I8Params P)
 {
-    // Tile order: consecutive CTAs walk I8_GROUP tile-rows for one tile-column before moving to the next column, so the
-    // ~148 CTAs in flight share 16 A panels and ~9 B panels out of L2 (the plain row-major order re-reads every B panel
-    // from HBM for every tile-row: 479 GB of DRAM reads per launch, L2 hit rate 53 %).
+    // Tile order: consecutive clusters walk I8_GROUP tile-rows for one tile-column before moving to the next column, so
+    // the ~148 CTAs in flight share 16 A panels and ~9 B panels out of L2 (the plain row-major order re-reads every B
+    // panel from HBM for every tile-row: 479 GB of DRAM reads per launch, L2 hit rate 53 %).
     int tile_m, tile_n;
+    const int cx = CL == 2 ? (int)(blockIdx.x & 1) : 0, cy = CL == 2 ? (int)(blockIdx.y & 1) : 0;
     {
-        const long long L = (long long)blockIdx.y * gridDim.x + blockIdx.x;
-        const long long per_group = (long long)I8_GROUP * gridDim.x;
+        const int gx = (int)gridDim.x / CL, gy = (int)gridDim.y / CL, grp_rows = I8_GROUP / CL;
+        const long long L = (long long)(blockIdx.y / CL) * gx + (blockIdx.x / CL);
+        const long long per_group = (long long)grp_rows * gx;
         const int grp = (int)(L / per_group);
-        const int rows_in_grp = min(I8_GROUP, (int)gridDim.y - grp * I8_GROUP);
+        const int rows_in_grp = min(grp_rows, gy - grp * grp_rows);
         const long long r = L - (long long)grp * per_group;
-        tile_m = grp * I8_GROUP + (int)(r % rows_in_grp);
-        tile_n = (int)(r / rows_in_grp);
+        tile_m = (grp * grp_rows + (int)(r % rows_in_grp)) * CL + cy;
+        tile_n = (int)(r / rows_in_grp) * CL + cx;
     }
     const int i0 = P.row0 + tile_m * I8_BM, j0 = tile_n * I8_BN; // global row / column of the tile origin
+    const bool tile_valid = tile_m < P.tiles_loc && tile_n < P.tiles_n;
     {
-        // a column tile may straddle two shards: compute it if either owner's pair is ours
-        const int b1 = min(j0 / P.per, P.world - 1), b2 = min(min(j0 + I8_BN - 1, P.N - 1) / P.per, P.world - 1);
-        if (!i8_pair_mine(P.rank, b1, P.world, i0, j0) && !i8_pair_mine(P.rank, b2, P.world, i0, j0)) return;
+        // a column tile may straddle two shards: compute it if either owner's pair is ours; a cluster runs if any of its
+        // tiles is needed (the decision must be the same in all of its CTAs)
+        bool need = false;
+#pragma unroll
+        for (int dy = 0; dy < CL; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < CL; ++dx) {
+                const int tm = tile_m - cy + dy, tn = tile_n - cx + dx;
+                if (tm >= P.tiles_loc || tn >= P.tiles_n) continue;
+                const int ii = P.row0 + tm * I8_BM, jj = tn * I8_BN;
+                const int b1 = min(jj / P.per, P.world - 1), b2 = min(min(jj + I8_BN - 1, P.N - 1) / P.per, P.world - 1);
+                need = need || i8_pair_mine(P.rank, b1, P.world, ii, jj) || i8_pair_mine(P.rank, b2, P.world, ii, jj);
+            }
+        if (!need) return;
     }
+    const uint16_t mask_a = CL == 2 ? (uint16_t)(0x3u << (2 * cy)) : (uint16_t)1;          // the CTAs sharing my A panel
+    const uint16_t mask_b = CL == 2 ? (uint16_t)((1u << cx) | (1u << (cx + 2))) : (uint16_t)1; // ... my B panel
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -160,7 +202,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL == 2 ? 3 : 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,6 +214,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL == 2) cluster_sync_all(); // every CTA's barriers exist before anybody multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -183,11 +226,19 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint32_t ph = (kb / I8_STAGES) & 1;
                 mbar_wait(&empty_bar[st], ph ^ 1); // passes immediately the first time round
                 uint8_t *sa = smem + (size_t)st * I8_STAGE_BYTES, *sb = sa + 4 * I8_A_PLANE;
-                mbar_expect_tx(&full_bar[st], I8_STAGE_BYTES);
+                mbar_expect_tx(&full_bar[st], I8_STAGE_BYTES); // bytes landing in THIS CTA (own halves + partners')
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    tma_load_2d(sa + s * I8_A_PLANE, &tmA, kb * I8_BK, s * P.plane_rows + i0, &full_bar[st]);
-                    tma_load_2d(sb + s * I8_B_PLANE, &tmB, kb * I8_BK, s * P.plane_rows + j0, &full_bar[st]);
+                    if (CL == 2) {
+                        // tmA / tmB are the half-panel boxes here: rows [64 cx, +64) of A, rows [48 cy, +48) of B
+                        tma_load_2d_mc(sa + s * I8_A_PLANE + cx * (I8_A_PLANE / 2), &tmA, kb * I8_BK,
+                                       s * P.plane_rows + i0 + cx * (I8_BM / 2), &full_bar[st], mask_a);
+                        tma_load_2d_mc(sb + s * I8_B_PLANE + cy * (I8_B_PLANE / 2), &tmB, kb * I8_BK,
+                                       s * P.plane_rows + j0 + cy * (I8_BN / 2), &full_bar[st], mask_b);
+                    } else {
+                        tma_load_2d(sa + s * I8_A_PLANE, &tmA, kb * I8_BK, s * P.plane_rows + i0, &full_bar[st]);
+                        tma_load_2d(sb + s * I8_B_PLANE, &tmB, kb * I8_BK, s * P.plane_rows + j0, &full_bar[st]);
+                    }
                 }
             }
         }
@@ -216,7 +267,9 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         }
                         started |= 1u << d;
                     }
-                umma_commit(&empty_bar[st]); // frees this stage once the MMAs above have read it
+                // frees this stage once the MMAs above have read it (in all CTAs that fill it, for a cluster)
+                if (CL == 2) umma_commit_mc(&empty_bar[st], (uint16_t)(mask_a | mask_b));
+                else umma_commit(&empty_bar[st]);
             }
             umma_commit(&tmem_full_bar);     // all accumulators final
         }
@@ -230,7 +283,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int q = warp & 3;
         const int r = q * 32 + lane;     // tile row = TMEM lane
         const int gi = i0 + r;
-        const bool row_ok = gi < P.row0 + P.nloc;
+        const bool row_ok = tile_valid && gi < P.row0 + P.nloc;
         const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
         const bool zr = row_ok ? P.zero_var[gi] : false;
         const int cbeg = (warp >> 2) * (I8_BN / 2);
@@ -283,7 +336,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const int gj = j0 + c0 + c;
-                if (gj < P.N && (size_t)gi < P.ld) {
+                if (tile_valid && gj < P.N && (size_t)gi < P.ld) {
                     const int ow = min(gj / P.per, P.world - 1);
                     P.peer[ow][(size_t)(gj - ow * P.per) * P.ld + gi] = row_ok ? qv[c] : 0u;
                 }
@@ -292,6 +345,7 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    if (CL == 2) cluster_sync_all(); // partners may still arrive on this CTA's barriers / multicast into its stages
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
@@ -437,7 +491,13 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     CUtensorMap tmA, tmB;
     cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)(4 * plane_rows)};
     cuuint64_t gstr[1] = {(cuuint64_t)Kp};
-    cuuint32_t boxA[2] = {I8_BK, I8_BM}, boxB[2] = {I8_BK, I8_BN}, estr[2] = {1, 1};
+    // RID_I8_CLUSTER=2 selects the 2 x 2 cluster / TMA-multicast variant (every CTA then loads half-panel boxes).  It is
+    // correct but measured SLOWER at cfg4 (199.6 ms vs 176 ms): halving the L2 operand traffic does not help because the
+    // kernel is bound by shared-memory bandwidth (13 digit products re-read their A and B panels: 146 B/clk of operand
+    // reads + 45 B/clk of TMA writes against 128 B/clk), and 4-CTA clusters strand SMs (148 is not a multiple of 4 per GPC).
+    const char *cl_env = getenv("RID_I8_CLUSTER");
+    const int CL = (cl_env && atoi(cl_env) == 2) ? 2 : 1;
+    cuuint32_t boxA[2] = {I8_BK, (cuuint32_t)(I8_BM / CL)}, boxB[2] = {I8_BK, (cuuint32_t)(I8_BN / CL)}, estr[2] = {1, 1};
     if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
         encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -456,7 +516,9 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     }
     for (int r = 0; r < 16; ++r) P.peer[r] = (u32 *)peers[r];
     if (ctx->world == 1) P.peer[0] = dm->D;
-    if (cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) {
+    P.tiles_loc = tiles_loc; P.tiles_n = tiles_n;
+    if (cudaFuncSetAttribute(k_gram_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gram_i8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) {
         cudaGetLastError(); cleanup(); return RID_OK;
     }
     // pad columns [N, ld) of every row are never touched by the tiles: clear them
@@ -464,10 +526,31 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
         cudaMemset2DAsync(dm->D + N, dm->ld * sizeof(u32), 0, (dm->ld - (size_t)N) * sizeof(u32), (size_t)nloc, ctx->stream);
     // nobody may start storing mirror tiles into a peer before that peer has cleared its pad columns
     if (ctx->world > 1) RID_TRY(rid_barrier(ctx));
-    dim3 grid((unsigned)tiles_n, (unsigned)std::max(tiles_loc, 1));
+    dim3 grid((unsigned)round_up((size_t)tiles_n, CL), (unsigned)round_up((size_t)std::max(tiles_loc, 1), CL));
     cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_GRAM_I8);
     if (nloc > 0) {
-        k_gram_i8<<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
+        if (CL == 2) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = I8_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 2;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, k_gram_i8<2>, tmA, tmB, P) != cudaSuccess) {
+                rid_set_error("k_gram_i8 cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                cleanup();
+                return RID_ERR_CUDA;
+            }
+        } else {
+            k_gram_i8<1><<<grid, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P);
+        }
         ctx->launches++;
     }
     // work: int8 multiply-adds actually issued x 2 (13 digit products per computed tile)

@@ -64,6 +64,20 @@ def test_dist_int8_tcgen05_path_matches_fp64_dmma_path(ctx, oracle, metric, shap
     assert Di[N // 2, 1] <= 4e-7
 
 
+def test_dist_int8_cluster_multicast_variant(ctx, monkeypatch):
+    """RID_I8_CLUSTER=2: 2 x 2 thread-block clusters with TMA multicast of the half panels — bit-identical output."""
+    x, _ = _features(seed=32, G=700, N=1500, C=5)
+    monkeypatch.setenv("RID_GRAM", "i8")
+    monkeypatch.setenv("RID_I8_CLUSTER", "1")
+    a = ctx.dist(x, "pearson")
+    Da = a.as_matrix()
+    a.free()
+    monkeypatch.setenv("RID_I8_CLUSTER", "2")
+    b = ctx.dist(x, "pearson")
+    assert np.array_equal(Da, b.as_matrix())
+    b.free()
+
+
 def test_dist_zero_variance_cell(ctx, oracle):
     x, _ = _features(seed=2, G=120, N=200)
     x[:, 9] = 3.25
