@@ -175,7 +175,7 @@ class ClockSampler:
                                 self.reasons.add(name)
                     except Exception:
                         pass
-                    self._stop.wait(0.25)
+                    self._stop.wait(0.5)
 
             self._thr = threading.Thread(target=loop, daemon=True)
             self._thr.start()
