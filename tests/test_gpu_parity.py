@@ -258,6 +258,42 @@ def test_pam_all_ties(ctx, oracle):
     dm.free()
 
 
+def test_argument_errors_surface_as_conditions(ctx):
+    """Degenerate / malformed inputs must fail loudly with the reference's messages, never compute on garbage."""
+    from raceid3_stemid2_package_b200.lib import RaceIDError
+
+    with pytest.raises(RaceIDError):
+        ctx.dist(np.ones((5, 1)) + np.arange(5)[:, None], "pearson")  # a single cell
+    with pytest.raises(RaceIDError):
+        ctx.dist(np.ones((1, 5)), "pearson")  # a single feature
+    with pytest.raises(ValueError):
+        ctx.dist(np.random.default_rng(0).random((4, 6)), "manhattan")
+    x, _ = _features(seed=3, G=40, N=60, C=3)
+    dm = ctx.dist(x, "pearson")
+    for bad_k in (0, 60, 61, -3):
+        with pytest.raises(RaceIDError, match="Number of clusters"):
+            dm.pam(bad_k)
+    with pytest.raises(RaceIDError, match="twice"):
+        dm.pam(2, subset=np.array([1, 2, 2, 5], dtype=np.int32))
+    with pytest.raises(RaceIDError, match="out of range"):
+        dm.pam(2, subset=np.array([1, 2, 60], dtype=np.int32))
+    with pytest.raises(RaceIDError):
+        dm.gap_sweep(60)
+    with pytest.raises(RaceIDError):
+        dm.knn(61)
+    with pytest.raises(RaceIDError):
+        dm.knn(0)
+    with pytest.raises(RaceIDError):
+        dm.refresh(np.array([0, 99], dtype=np.int32))
+    with pytest.raises(RaceIDError):
+        dm.within_disp(np.zeros(60, dtype=np.int32), 3)  # labels must be 1..k
+    with pytest.raises(RaceIDError, match="negative"):
+        ctx.from_matrix(np.array([[0.0, -1.0], [-1.0, 0.0]]))
+    # the matrix is still usable after every refused call
+    assert dm.pam(3)["clustering"].max() == 3
+    dm.free()
+
+
 def test_from_matrix_lower_triangle_rule_and_errors(ctx):
     from raceid3_stemid2_package_b200.lib import RaceIDError
 
