@@ -467,7 +467,12 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     double *xd = nullptr, *Z = nullptr, *nrm2 = nullptr, *dmax = nullptr;
     unsigned char *zv = nullptr;
     int rc = RID_OK;
-    const size_t z_bytes = Np * (size_t)Gp * sizeof(double), x_bytes = (size_t)G * N * sizeof(double);
+    // host input on several ranks: every rank uploads only its 1/world slice of the cells over PCIe and the slices are
+    // all-gathered over NVLink (the buffer is padded to world equal slices)
+    const size_t cells_per = ((size_t)N + ctx->world - 1) / ctx->world;
+    const bool sliced_upload = !x_on_device && ctx->world > 1 && !getenv("RID_FULL_UPLOAD");
+    const size_t z_bytes = Np * (size_t)Gp * sizeof(double);
+    const size_t x_bytes = (sliced_upload ? cells_per * ctx->world : (size_t)N) * (size_t)G * sizeof(double);
     auto fail = [&](int code) {
         rid_pool_free(ctx, Z, z_bytes); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
         if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
@@ -491,7 +496,15 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         xd = const_cast<double *>(x);
     } else {
         DCHK(rid_pool_alloc(ctx, (void **)&xd, x_bytes));
-        DCHK(cudaMemcpyAsync(xd, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (sliced_upload) {
+            const size_t c0 = std::min(cells_per * ctx->rank, (size_t)N), c1 = std::min(c0 + cells_per, (size_t)N);
+            const size_t slice = cells_per * (size_t)G * sizeof(double);
+            if (c1 > c0)
+                DCHK(cudaMemcpyAsync(xd + c0 * G, x + c0 * G, (c1 - c0) * (size_t)G * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = rid_allgather(ctx, (const char *)xd + slice * ctx->rank, xd, slice)) != RID_OK) return fail(rc);
+        } else {
+            DCHK(cudaMemcpyAsync(xd, x, (size_t)G * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     DCHK(cudaMemsetAsync(Z, 0, Np * (size_t)Gp * sizeof(double), ctx->stream));
     DCHK(cudaMemsetAsync(nrm2, 0, Np * sizeof(double), ctx->stream));

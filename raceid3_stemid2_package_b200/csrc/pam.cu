@@ -814,6 +814,109 @@ __global__ void k_silhouette(const int *__restrict__ subset, const int *__restri
     }
 }
 
+// ---- W.k for several partitions in ONE pass (the sweep) ---------------------------------------------------------------
+// S_q[h] = sum over rows j in h's cluster (under partition q) of D[j][h], for WB partitions at once: the matrix is read
+// once for WB values of k instead of once per k.  Labels are bytes; a thread keeps the labels of its 4 columns for the
+// WB partitions packed in WB registers and compares them with the row's labels four at a time (__vcmpeq4).
+#define WB 6
+__global__ void k_labels_by_column(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
+                                   unsigned char *__restrict__ lab_col)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) lab_col[subset[p]] = (unsigned char)lab_pos[p];
+}
+
+template <int FLUSH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_wk_batch(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows, const int *__restrict__ rows_pos,
+           const int *__restrict__ subset, int nrows, int rows_per_chunk,
+           const unsigned char *__restrict__ lab_col /* [WB][lab_pitch] by column */, size_t lab_pitch, int nq,
+           u64 *__restrict__ S /* [WB][ld] */)
+{
+    __shared__ int sh_row[SCAN_MAXROWS];
+    __shared__ unsigned char sh_lab[WB][SCAN_MAXROWS];
+    const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    const bool active = col < ld;
+    u32 clab[WB];
+#pragma unroll
+    for (int q = 0; q < WB; ++q)
+        clab[q] = (active && q < nq) ? *reinterpret_cast<const u32 *>(lab_col + (size_t)q * lab_pitch + col) : 0xFFFFFFFFu;
+    u64 acc[WB][4];
+    u32 p32[WB][4];
+#pragma unroll
+    for (int q = 0; q < WB; ++q)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[q][c] = 0; p32[q][c] = 0; }
+    bool any = false;
+    for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < nrows; chunk += gridDim.y) {
+        const int r_begin = chunk * rows_per_chunk;
+        const int nr = min(nrows - r_begin, rows_per_chunk);
+        const int nr8 = (nr + 7) & ~7;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) {
+            const bool ok = i < nr;
+            const int lr = ok ? rows[r_begin + i] : -1;
+            sh_row[i] = lr;
+#pragma unroll
+            for (int q = 0; q < WB; ++q) sh_lab[q][i] = 0xFE; // matches no column label (0xFF pads columns)
+        }
+        __syncthreads();
+        // the row's own labels: owned row slot -> position -> column id of the same cell
+        for (int i = threadIdx.x; i < nr; i += SCAN_THREADS) {
+            const size_t cid = (size_t)subset[rows_pos[r_begin + i]];
+#pragma unroll
+            for (int q = 0; q < WB; ++q)
+                if (q < nq) sh_lab[q][i] = lab_col[(size_t)q * lab_pitch + cid];
+        }
+        __syncthreads();
+        if (!active) continue;
+        any = true;
+        for (int r = 0; r < nr8; r += 8) {
+            uint4 d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int lr = sh_row[r + u];
+                d[u] = lr >= 0 ? ld_stream(D + (size_t)lr * ld + col) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int q = 0; q < WB; ++q) {
+                    const u32 eq = __vcmpeq4(clab[q], (u32)sh_lab[q][r + u] * 0x01010101u); // 0xFF per equal byte
+                    p32[q][0] += d[u].x & (0u - (eq & 1u));
+                    p32[q][1] += d[u].y & (0u - ((eq >> 8) & 1u));
+                    p32[q][2] += d[u].z & (0u - ((eq >> 16) & 1u));
+                    p32[q][3] += d[u].w & (0u - ((eq >> 24) & 1u));
+                }
+                if ((u % FLUSH) == FLUSH - 1) {
+#pragma unroll
+                    for (int q = 0; q < WB; ++q)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { acc[q][c] += p32[q][c]; p32[q][c] = 0; }
+                }
+            }
+        }
+    }
+    if (!any) return;
+#pragma unroll
+    for (int q = 0; q < WB; ++q)
+        if (q < nq)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) red_add_u64(S + (size_t)q * ld + col + c, acc[q][c]);
+}
+
+// T_c += S[h] for the cells h of cluster c; n_c
+__global__ void k_wdisp_cols(const int *__restrict__ subset, int m, const unsigned char *__restrict__ lab_col,
+                             const u64 *__restrict__ S, u64 *grp_sum, int *grp_cnt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        const int h = subset[p], c = lab_col[h];
+        atomicAdd(&grp_sum[c], S[h]);
+        atomicAdd(&grp_cnt[c], 1);
+    }
+}
+
 // deterministic sum of n doubles (fixed order) -> out[0]
 __global__ void k_sum_f64(const double *__restrict__ x, int n, double *out)
 {
@@ -1560,6 +1663,22 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     RID_CUDA(cudaMalloc(&d_order, (size_t)Kmax * sizeof(int)));
     RID_CUDA(cudaMemcpy(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice));
     int rc = RID_OK;
+    // Labels of every k this rank owns are kept by column (bytes); W.k is then evaluated for WB values of k per pass
+    // over the matrix instead of one pass per k.
+    const bool batched = Kmax <= 255 && !getenv("RID_WK_SINGLE");
+    const size_t lab_pitch = round_up(w->ld, 16);
+    unsigned char *d_lab = nullptr;
+    u64 *d_S = nullptr;
+    std::vector<int> ks;
+    if (batched) {
+        if (cudaMalloc(&d_lab, (size_t)Kmax * lab_pitch) != cudaSuccess || cudaMalloc(&d_S, (size_t)WB * w->ld * sizeof(u64)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(d_lab); cudaFree(d_S); cudaFree(d_order);
+            rid_set_error("rid_gap_sweep: out of device memory");
+            return RID_ERR_NOMEM;
+        }
+        cudaMemsetAsync(d_lab, 0xFF, (size_t)Kmax * lab_pitch, ctx->stream); // 0xFF = column outside the subset
+    }
     for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
         logW[k - 1] = 0.0;
         if ((k - 1) % nshare != myshare) continue; // another rank's k
@@ -1575,9 +1694,53 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
             std::vector<int> slot;
             if (rc == RID_OK) rc = pam_collect_labels(dm, w, slot);
         }
-        if (rc == RID_OK) rc = within_disp(dm, w, k, &W, nullptr);
-        logW[k - 1] = log(W);
+        if (rc != RID_OK) break;
+        if (batched) {
+            LAUNCH(ctx, k_labels_by_column, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, d_lab + (size_t)ks.size() * lab_pitch);
+            ks.push_back(k);
+        } else {
+            rc = within_disp(dm, w, k, &W, nullptr);
+            logW[k - 1] = log(W);
+        }
     }
+    for (size_t q0 = 0; batched && rc == RID_OK && q0 < ks.size(); q0 += WB) {
+        const int nq = (int)std::min<size_t>(WB, ks.size() - q0);
+        cudaMemsetAsync(d_S, 0, (size_t)WB * w->ld * sizeof(u64), ctx->stream);
+        if (w->nls) {
+            int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
+            int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
+            int rpc = std::min(std::max((((w->nls + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
+            dim3 grid(strips, std::min((w->nls + rpc - 1) / rpc, want_y * 2));
+            cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_GROUP);
+            auto k8 = k_wk_batch<8>;
+            auto k2 = k_wk_batch<2>;
+            if (dm->bits <= 28)
+                LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, w->mat, w->ld, w->rows, w->rows_pos, w->subset, w->nls, rpc, d_lab + q0 * lab_pitch, lab_pitch, nq, d_S);
+            else
+                LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, w->mat, w->ld, w->rows, w->rows_pos, w->subset, w->nls, rpc, d_lab + q0 * lab_pitch, lab_pitch, nq, d_S);
+            rid_prof_end(ctx, pe, RID_PROF_SCAN_GROUP, (double)w->nls * (double)w->m * 4.0, (double)w->nls * (double)w->ld * 4.0);
+        }
+        if (cudaGetLastError() != cudaSuccess) { rc = RID_ERR_CUDA; break; }
+        rc = rid_allreduce_u64(ctx, d_S, (size_t)WB * w->ld);
+        for (int q = 0; q < nq && rc == RID_OK; ++q) {
+            const int k = ks[q0 + q];
+            cudaMemsetAsync(w->grp_sum, 0, (size_t)k * sizeof(u64), ctx->stream);
+            cudaMemsetAsync(w->grp_cnt, 0, (size_t)k * sizeof(int), ctx->stream);
+            LAUNCH(ctx, k_wdisp_cols, nblk(m, 256), 256, 0, w->subset, m, d_lab + (q0 + q) * lab_pitch, d_S + (size_t)q * w->ld,
+                   w->grp_sum, w->grp_cnt);
+            std::vector<u64> hs(k);
+            std::vector<int> hc(k);
+            if (cudaMemcpyAsync(hs.data(), w->grp_sum, (size_t)k * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaMemcpyAsync(hc.data(), w->grp_cnt, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = RID_ERR_CUDA; break; }
+            long double tot = 0.0L;
+            for (int c = 0; c < k; ++c)
+                if (hc[c] > 0) tot += (long double)((double)((long double)hs[c] * (long double)dm->step / (long double)hc[c]));
+            logW[k - 1] = log(0.5 * (double)tot);
+        }
+    }
+    cudaFree(d_lab);
+    cudaFree(d_S);
     cudaFree(d_order);
     return rc;
 }
