@@ -110,3 +110,28 @@ IntegerVector rid_refresh_partition(SEXP dm, IntegerVector medoids) {
     rid_check(rid_refresh(DmatPtr(dm), md.begin(), md.size(), lab.begin()));
     return lab;
 }
+
+// apply(D, 1, function(x) head(order(x), K)) — compdist's knn branch (R/RaceID.R:774), compfr (:1123), pruneKnn, StemID
+// [[Rcpp::export]]
+IntegerMatrix rid_knn_call(SEXP dm, int K) {
+    int N = 0; rid_check(rid_dmat_info(DmatPtr(dm), &N, nullptr, nullptr, nullptr, nullptr));
+    IntegerMatrix idx(K, N);                         // K x N, like the matrix apply() returns
+    rid_check(rid_knn(DmatPtr(dm), K, idx.begin(), nullptr));
+    for (int t = 0; t < K * N; ++t) idx[t] += 1;     // R indices are 1-based
+    return idx;
+}
+
+// compdist straight from the filtered dgCMatrix (slots i, p, x of ndata[, kept cells]); getfdata is fused on the device
+// [[Rcpp::export]]
+SEXP rid_dist_csc_call(SEXP ctx, IntegerVector i, IntegerVector p, NumericVector x, int n_rows_all,
+                       IntegerVector feature_rows, NumericVector counts, std::string method) {
+    int metric = method == "pearson" ? RID_PEARSON : method == "spearman" ? RID_SPEARMAN
+               : method == "logpearson" ? RID_LOGPEARSON : method == "euclidean" ? RID_EUCLIDEAN : -1;
+    if (metric < 0) Rcpp::stop("metric has to be one of the following: spearman, pearson, logpearson, euclidean, kendall");
+    IntegerVector fr = feature_rows - 1;
+    rid_dmat* dm = nullptr; int nzero = 0;
+    rid_check(rid_dist_csc(CtxPtr(ctx), i.begin(), p.begin(), x.begin(), n_rows_all, counts.size(), fr.begin(), fr.size(),
+                           counts.begin(), metric, &dm, &nzero));
+    if (nzero) Rcpp::warning("the standard deviation is zero");
+    return DmatPtr(dm, true);
+}

@@ -371,6 +371,18 @@ def test_knn_matches_stable_order(ctx):
     dm.free()
 
 
+def test_gap_sweep_batched_equals_single_pass_per_k(ctx, monkeypatch):
+    """The sweep evaluates W.k for six partitions per pass; RID_WK_SINGLE=1 is the one-pass-per-k path."""
+    x, _ = _features(seed=14, G=90, N=900, C=7)
+    dm = ctx.dist(x, "logpearson")
+    sub = np.arange(0, 900, 2).astype(np.int32)[::-1].copy()
+    a, a_sub = dm.gap_sweep(14), dm.gap_sweep(8, subset=sub)
+    monkeypatch.setenv("RID_WK_SINGLE", "1")
+    b, b_sub = dm.gap_sweep(14), dm.gap_sweep(8, subset=sub)
+    assert np.array_equal(a, b) and np.array_equal(a_sub, b_sub)
+    dm.free()
+
+
 def test_clusterboot_identical(ctx, oracle):
     from raceid3_stemid2_package_b200.scseq import bootstrap_samples
 
