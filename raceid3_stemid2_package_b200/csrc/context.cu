@@ -199,7 +199,11 @@ cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
 void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
 {
     if (!p) return;
-    if (bytes < ((size_t)16 << 20) || ctx->pool.size() >= 16) { cudaFree(p); return; }
+    if (bytes < ((size_t)256 << 10)) { cudaFree(p); return; }
+    if (ctx->pool.size() >= 16) { // full: drop the buffer that has waited longest, the steady-state sizes stay cached
+        cudaFree(ctx->pool.front().p);
+        ctx->pool.erase(ctx->pool.begin());
+    }
     ctx->pool.push_back({p, bytes});
 }
 

@@ -466,6 +466,8 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     const size_t Np = round_up((size_t)N, 128);
     double *xd = nullptr, *Z = nullptr, *nrm2 = nullptr, *dmax = nullptr;
     unsigned char *zv = nullptr;
+    char *aux = nullptr; // nrm2[Np] | dmax[32] | zv[Np], one pooled buffer
+    const size_t aux_bytes = std::max<size_t>((Np + 32) * sizeof(double) + Np, (size_t)256 << 10);
     int rc = RID_OK;
     // host input on several ranks: every rank uploads only its 1/world slice of the cells over PCIe and the slices are
     // all-gathered over NVLink (the buffer is padded to world equal slices)
@@ -474,7 +476,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     const size_t z_bytes = Np * (size_t)Gp * sizeof(double);
     const size_t x_bytes = (sliced_upload ? cells_per * ctx->world : (size_t)N) * (size_t)G * sizeof(double);
     auto fail = [&](int code) {
-        rid_pool_free(ctx, Z, z_bytes); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+        rid_pool_free(ctx, Z, z_bytes); rid_pool_free(ctx, aux, aux_bytes);
         if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
         rid_dmat_free(dm);
         return code;
@@ -488,9 +490,8 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         }                                                                                                  \
     } while (0)
     DCHK(rid_pool_alloc(ctx, (void **)&Z, z_bytes));
-    DCHK(cudaMalloc(&nrm2, Np * sizeof(double)));
-    DCHK(cudaMalloc(&zv, Np));
-    DCHK(cudaMalloc(&dmax, sizeof(double)));
+    DCHK(rid_pool_alloc(ctx, (void **)&aux, aux_bytes));
+    nrm2 = (double *)aux; dmax = nrm2 + Np; zv = (unsigned char *)(dmax + 32);
     if ((rc = rid_time_begin(ctx)) != RID_OK) return fail(rc);
     if (x_on_device) {
         xd = const_cast<double *>(x);
@@ -613,7 +614,7 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     for (int i = 0; i < N; ++i) nz += dm->na_cell[i];
     dm->has_na = nz > 0;
     if (n_zero_var) *n_zero_var = nz;
-    rid_pool_free(ctx, Z, z_bytes); cudaFree(nrm2); cudaFree(zv); cudaFree(dmax);
+    rid_pool_free(ctx, Z, z_bytes); rid_pool_free(ctx, aux, aux_bytes);
     if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
     *out = dm;
     return RID_OK;

@@ -487,10 +487,11 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     int8_t *planes = nullptr;
     double *rowscale = nullptr, *stats = nullptr;
     if (rid_pool_alloc(ctx, (void **)&planes, planes_bytes) != cudaSuccess) { cudaGetLastError(); return RID_OK; }
-    auto cleanup = [&]() { rid_pool_free(ctx, planes, planes_bytes); cudaFree(rowscale); cudaFree(stats); };
-    if (cudaMalloc(&rowscale, plane_rows * sizeof(double)) != cudaSuccess || cudaMalloc(&stats, 4 * sizeof(double)) != cudaSuccess) {
-        cudaGetLastError(); cleanup(); return RID_OK;
-    }
+    char *aux = nullptr; // stats[32] | rowscale[plane_rows], one pooled buffer
+    const size_t aux_bytes = std::max<size_t>((plane_rows + 32) * sizeof(double), (size_t)256 << 10);
+    auto cleanup = [&]() { rid_pool_free(ctx, planes, planes_bytes); rid_pool_free(ctx, aux, aux_bytes); };
+    if (rid_pool_alloc(ctx, (void **)&aux, aux_bytes) != cudaSuccess) { cudaGetLastError(); aux = nullptr; cleanup(); return RID_OK; }
+    stats = (double *)aux; rowscale = stats + 32;
     cudaMemsetAsync(planes, 0, planes_bytes, ctx->stream);
     cudaMemsetAsync(rowscale, 0, plane_rows * sizeof(double), ctx->stream);
     cudaMemsetAsync(stats, 0, 4 * sizeof(double), ctx->stream);

@@ -113,12 +113,51 @@ struct PamWs {
     int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
+    // the two pooled slabs every device array above is carved from
+    char *slab = nullptr, *gslab = nullptr;
+    size_t slab_bytes = 0, gslab_bytes = 0;
 };
 
-static void ws_free_groups(PamWs *w)
+// All per-matrix work arrays live in two slabs taken from the context's buffer pool (one for the per-cell / per-row
+// arrays, one for the per-group arrays and accumulators): creating and dropping a workspace costs no cudaMalloc /
+// cudaFree once the pool is warm.  (Dozens of small cudaFree calls per clustexp() showed up as 0.1-0.5 s of host stalls
+// on some boxes.)
+template <class T> static inline void carve(char *&p, T *&dst, size_t count)
 {
-    cudaFree(w->med); cudaFree(w->medpos); cudaFree(w->hist); cudaFree(w->grp_sum); cudaFree(w->grp_cnt);
-    cudaFree(w->grp_min); cudaFree(w->grp_arg); cudaFree(w->acc); cudaFree(w->chg_hist); cudaFree(w->acc2);
+    dst = reinterpret_cast<T *>(p);
+    p += (count * sizeof(T) + 255) & ~(size_t)255;
+}
+
+static size_t ws_carve_base(PamWs *w, char *base)
+{
+    char *p = base;
+    const size_t N = (size_t)w->N, nl = (size_t)std::max(w->nloc, 1);
+    carve(p, w->subset, N); carve(p, w->pos_of, N); carve(p, w->is_med, N); carve(p, w->lab_pos, N);
+    carve(p, w->rows, nl); carve(p, w->rows_pos, nl); carve(p, w->capP, nl); carve(p, w->capQ, nl); carve(p, w->grp, nl);
+    carve(p, w->s_row, nl); carve(p, w->s_grp, nl); carve(p, w->s_capP, nl); carve(p, w->s_capQ, nl);
+    carve(p, w->blockbest, (size_t)w->maxblocks); carve(p, w->sil, N); carve(p, w->dscratch, 8);
+    carve(p, w->state, 1); carve(p, w->chg_count, 1);
+    carve(p, w->o_capP, nl); carve(p, w->o_capQ, nl); carve(p, w->o_grp, nl); carve(p, w->d_row, nl); carve(p, w->d_key, nl);
+    carve(p, w->d_po, nl); carve(p, w->d_qo, nl); carve(p, w->d_pn, nl); carve(p, w->d_qn, nl);
+    carve(p, w->hist2, (size_t)3 * K2MAX); carve(p, w->cnt_hist, (size_t)CNT_HIST);
+    carve(p, w->subset_cells, N); carve(p, w->colmap, N); carve(p, w->src_rows, nl);
+    return (size_t)(p - base);
+}
+
+static size_t ws_carve_groups(PamWs *w, char *base, int kc, size_t ld)
+{
+    char *p = base;
+    const size_t k = (size_t)kc, nacc = 4 + (k + 1) * ld;
+    carve(p, w->med, k); carve(p, w->medpos, k); carve(p, w->hist, 3 * k); carve(p, w->grp_sum, k); carve(p, w->grp_cnt, k);
+    carve(p, w->grp_min, k); carve(p, w->grp_arg, k); carve(p, w->chg_hist, k);
+    carve(p, w->acc, nacc); carve(p, w->acc2, nacc);
+    return (size_t)(p - base);
+}
+
+static void ws_free_groups(PamWs *w, rid_ctx *ctx)
+{
+    rid_pool_free(ctx, w->gslab, w->gslab_bytes);
+    w->gslab = nullptr; w->gslab_bytes = 0;
     w->chg_hist = nullptr; w->acc2 = nullptr;
     w->med = w->medpos = w->hist = w->grp_cnt = w->grp_arg = nullptr;
     w->grp_sum = w->grp_min = w->acc = nullptr;
@@ -126,81 +165,48 @@ static void ws_free_groups(PamWs *w)
 
 void rid_pam_ws_free(PamWs *w, rid_ctx *ctx)
 {
-    if (w && w->cbuf) rid_pool_free(ctx, w->cbuf, w->cbuf_bytes);
     if (!w) return;
-    cudaFree(w->subset); cudaFree(w->pos_of); cudaFree(w->is_med); cudaFree(w->lab_pos);
-    cudaFree(w->rows); cudaFree(w->rows_pos); cudaFree(w->capP); cudaFree(w->capQ); cudaFree(w->grp);
-    cudaFree(w->s_row); cudaFree(w->s_grp); cudaFree(w->s_capP); cudaFree(w->s_capQ);
-    cudaFree(w->blockbest); cudaFree(w->sil); cudaFree(w->dscratch); cudaFree(w->state); cudaFree(w->chg_count);
-    cudaFree(w->subset_cells); cudaFree(w->colmap); cudaFree(w->src_rows);
-    cudaFree(w->o_capP); cudaFree(w->o_capQ); cudaFree(w->o_grp); cudaFree(w->d_row); cudaFree(w->d_key);
-    cudaFree(w->d_po); cudaFree(w->d_qo); cudaFree(w->d_pn); cudaFree(w->d_qn); cudaFree(w->hist2); cudaFree(w->cnt_hist);
-    ws_free_groups(w);
+    if (w->cbuf) rid_pool_free(ctx, w->cbuf, w->cbuf_bytes);
+    rid_pool_free(ctx, w->slab, w->slab_bytes);
+    ws_free_groups(w, ctx);
     delete w;
 }
 
 static int ws_get(rid_dmat *dm, int k, PamWs **out)
 {
     PamWs *w = dm->ws;
-    RID_CUDA(cudaSetDevice(dm->ctx->device));
+    rid_ctx *ctx = dm->ctx;
+    RID_CUDA(cudaSetDevice(ctx->device));
     if (!w) {
         w = new PamWs();
         dm->ws = w;
         w->N = dm->N;
         w->ld = dm->ld;
         w->nloc = dm->row1 - dm->row0;
-        size_t N = (size_t)dm->N, nl = (size_t)std::max(w->nloc, 1);
-        RID_CUDA(cudaMalloc(&w->subset, N * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->pos_of, N * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->is_med, N));
-        RID_CUDA(cudaMalloc(&w->lab_pos, N * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->rows, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->rows_pos, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->capP, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->capQ, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->grp, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->s_row, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->s_grp, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->s_capP, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->s_capQ, nl * sizeof(u32)));
-        w->maxblocks = (int)((N + 255) / 256);
-        RID_CUDA(cudaMalloc(&w->blockbest, (size_t)w->maxblocks * sizeof(Cand)));
-        RID_CUDA(cudaMalloc(&w->sil, N * sizeof(double)));
-        RID_CUDA(cudaMalloc(&w->dscratch, 8 * sizeof(double)));
-        RID_CUDA(cudaMalloc(&w->state, sizeof(PamState)));
-        RID_CUDA(cudaMalloc(&w->chg_count, sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->o_capP, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->o_capQ, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->o_grp, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->d_row, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->d_key, nl * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->d_po, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->d_qo, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->d_pn, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->d_qn, nl * sizeof(u32)));
-        RID_CUDA(cudaMalloc(&w->hist2, 3 * K2MAX * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->cnt_hist, CNT_HIST * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->subset_cells, N * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->colmap, N * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->src_rows, nl * sizeof(int)));
+        w->maxblocks = (int)(((size_t)dm->N + 255) / 256);
+        w->slab_bytes = ws_carve_base(w, nullptr);
+        if (rid_pool_alloc(ctx, (void **)&w->slab, w->slab_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            rid_set_error("out of device memory for the PAM work arrays (%zu bytes)", w->slab_bytes);
+            dm->ws = nullptr;
+            delete w;
+            return RID_ERR_NOMEM;
+        }
+        ws_carve_base(w, w->slab);
     }
     if (k > w->kcap) {
-        ws_free_groups(w);
+        ws_free_groups(w, ctx);
+        w->kcap = 0;
         int kc = std::max(k, 32);
-        RID_CUDA(cudaMalloc(&w->med, kc * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->medpos, kc * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->hist, 3 * (size_t)kc * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->grp_sum, kc * sizeof(u64)));
-        RID_CUDA(cudaMalloc(&w->grp_cnt, kc * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->grp_min, kc * sizeof(u64)));
-        RID_CUDA(cudaMalloc(&w->grp_arg, kc * sizeof(int)));
-        RID_CUDA(cudaMalloc(&w->chg_hist, kc * sizeof(int)));
-        cudaError_t e = cudaMalloc(&w->acc, (4 + (size_t)(kc + 1) * dm->ld) * sizeof(u64));
-        if (e == cudaSuccess) e = cudaMalloc(&w->acc2, (4 + (size_t)(kc + 1) * dm->ld) * sizeof(u64));
-        if (e != cudaSuccess) {
+        w->gslab_bytes = ws_carve_groups(w, nullptr, kc, dm->ld);
+        if (rid_pool_alloc(ctx, (void **)&w->gslab, w->gslab_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            w->gslab = nullptr; w->gslab_bytes = 0;
+            ws_free_groups(w, ctx);
             rid_set_error("out of device memory for %d group accumulators", kc);
             return RID_ERR_NOMEM;
         }
+        ws_carve_groups(w, w->gslab, kc, dm->ld);
         w->kcap = kc;
     }
     *out = w;
