@@ -57,7 +57,13 @@ struct rid_ctx {
     struct IpcMap { unsigned char handle[64]; void *ptr; };
     std::vector<IpcMap> ipc;
     void *scratch = nullptr; // small device scratch (barriers, handle exchange)
+    // page-locked host staging (grow-only), e.g. the subset tables and result slots of the bootstrap pipeline
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
 };
+
+// page-locked host memory owned by the context (contents are not preserved when it grows)
+void *rid_pinned(rid_ctx *ctx, size_t bytes);
 
 // Collect the device pointers of every rank's buffer (peers mapped with CUDA IPC).  peers[rank] = mine.
 // Returns RID_OK with *all_ok = 1 only if every rank could map every peer.

@@ -142,6 +142,7 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     ctx->ipc.clear();
     rid_pool_trim(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -205,6 +206,16 @@ void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
         ctx->pool.erase(ctx->pool.begin());
     }
     ctx->pool.push_back({p, bytes});
+}
+
+void *rid_pinned(rid_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->pin_bytes) return ctx->pin;
+    if (ctx->pin) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pin); ctx->pin = nullptr; ctx->pin_bytes = 0; }
+    bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    if (cudaHostAlloc(&ctx->pin, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->pin = nullptr; return nullptr; }
+    ctx->pin_bytes = bytes;
+    return ctx->pin;
 }
 
 void rid_pool_trim(rid_ctx *ctx)

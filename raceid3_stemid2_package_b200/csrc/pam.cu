@@ -655,14 +655,16 @@ __device__ __forceinline__ Cand cand_reduce_block(Cand c, Cand *sh)
 template <bool BUILD>
 __global__ void __launch_bounds__(256)
 k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
-         const u64 *__restrict__ acc, size_t ld, int k, int *med, int *medpos, unsigned char *is_med,
-         Cand *blockbest, PamState *st, int check_done)
+         u64 *acc, size_t ld, int k, int *med, int *medpos, unsigned char *is_med,
+         Cand *blockbest, PamState *st, int check_done, u64 *sp_sub, int *zero_cnt)
 {
+    // sp_sub (incremental BUILD): SP[h] -= sp_sub[h] and sp_sub[h] = 0 on the way (every subset column is visited once);
+    // zero_cnt: a counter the next kernel fills again
     if (check_done && st->done) return;
     __shared__ Cand sh[32];
     __shared__ int sh_mp[1024];
     __shared__ bool is_last;
-    const u64 *SP = acc + 4;
+    u64 *SP = acc + 4;
     const u64 *AQ = SP + ld;
     if (!BUILD)
         for (int i = threadIdx.x; i < k && i < 1024; i += blockDim.x) sh_mp[i] = medpos[i];
@@ -672,8 +674,13 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
     best.val = ~0ull; best.p = BUILD ? -1 : INT_MAX; best.mp = INT_MAX; best.slot = -1;
     if (p < m) {
         int h = subset[p];
+        u64 sp = SP[h];
+        if (BUILD && sp_sub) {
+            sp -= sp_sub[h];
+            SP[h] = sp;
+            sp_sub[h] = 0ull;
+        }
         if (!is_med_c[h]) {
-            u64 sp = SP[h];
             if (BUILD) {
                 best.val = sp; best.p = p; best.mp = 0; best.slot = 0;
             } else {
@@ -707,6 +714,7 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
     c = cand_reduce_block<BUILD>(c, sh);
     if (threadIdx.x == 0) {
         st->ticket = 0u;
+        if (zero_cnt) *zero_cnt = 0;
         u64 td = acc[0];
         if (BUILD) {
             int h = subset[c.p];
@@ -1009,6 +1017,113 @@ k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows
         if (keep[c]) red_add_u64(SP0 + c0 + c, sum[c]);
 }
 
+// Symmetric variant for a complete matrix view (one GPU, or a full replica): D[subset, subset] is symmetric and its rows
+// and columns are the same sorted cell list, so only super-tiles on or above the diagonal are gathered from the
+// resident matrix (half the source bytes) and every off-diagonal super-tile is written twice: as it is, straight from
+// registers, and transposed through a swizzled shared-memory stage so that both writes are whole 128-byte lines.
+// BUILD's step-0 column sums come from the same registers: column sums of the tile for its own columns, row sums of
+// the tile for the columns of the mirrored tile.
+#define CS_S 512       // super-tile edge (compact rows and columns)
+#define CS_R 32        // rows staged per transposition
+#define CS_THREADS 256
+#define CS_SMEM (CS_S * CS_R * 4 + CS_S * 8 + CS_S * 4)
+__global__ void __launch_bounds__(CS_THREADS, 2)
+k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccells, u32 *__restrict__ out, size_t ldc,
+              int m, u64 *__restrict__ SP0)
+{
+    const int bj = blockIdx.x, bi = blockIdx.y;
+    if (bi > bj) return;
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    uint4 *tile = reinterpret_cast<uint4 *>(cs_smem);                   // [CS_S columns][8 chunks of 4 rows], swizzled
+    u64 *rowacc = reinterpret_cast<u64 *>(cs_smem + CS_S * CS_R * 4);   // [CS_S] row sums of the super-tile
+    int *sh_src = reinterpret_cast<int *>(rowacc + CS_S);               // [CS_S] source row of each tile row
+    const bool mirror = bi < bj;
+    const int tid = threadIdx.x;
+    const int I0 = bi * CS_S, J0 = bj * CS_S;
+    const int nr = min(CS_S, m - I0);
+    for (int i = tid; i < CS_S; i += CS_THREADS) {
+        sh_src[i] = ccells[I0 + min(i, nr - 1)];
+        rowacc[i] = 0ull;
+    }
+    __syncthreads();
+    const int t = tid & 127, h = tid >> 7;
+    const size_t c0 = (size_t)J0 + 4 * (size_t)t;
+    const bool col_in = c0 < ldc;
+    int src[4];
+    bool keep[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        keep[c] = c0 + c < (size_t)m;
+        src[c] = keep[c] ? ccells[c0 + c] : 0;
+    }
+    u64 sum[4] = {0, 0, 0, 0};
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int rs = 0; rs < nr; rs += CS_R) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int r = rs + 16 * h + 8 * g; // first of this thread's 8 rows, tile-relative
+            u32 v[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u32 *row = D + (size_t)sh_src[min(r + u, nr - 1)] * ld;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[u][c] = __ldg(row + src[c]);
+            }
+            u32 p32[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool row_in = r + u < nr;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[u][c] = (row_in && keep[c]) ? v[u][c] : 0u;
+                if (row_in && col_in)
+                    *reinterpret_cast<uint4 *>(out + (size_t)(I0 + r + u) * ldc + c0) = make_uint4(v[u][0], v[u][1], v[u][2], v[u][3]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) p32[c] += v[u][c];
+                if (u & 1) { // two rows of q < 2^31 fit 32 bits
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { sum[c] += p32[c]; p32[c] = 0; }
+                }
+            }
+            if (mirror) {
+                const int q0 = 4 * h + 2 * g; // chunk (4 rows) of v[0..3]; v[4..7] is the next one
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = 4 * t + c;
+                    tile[cc * 8 + (q0 ^ (t & 7))] = make_uint4(v[0][c], v[1][c], v[2][c], v[3][c]);
+                    tile[cc * 8 + ((q0 + 1) ^ (t & 7))] = make_uint4(v[4][c], v[5][c], v[6][c], v[7][c]);
+                }
+            }
+        }
+        if (mirror) { // (uniform over the CTA; a mirrored super-tile always has all CS_S rows)
+            __syncthreads();
+            u64 racc[4] = {0, 0, 0, 0};
+            const int q = lane & 7;
+#pragma unroll 4
+            for (int p = 0; p < CS_S / 32; ++p) {
+                const int cc = p * 32 + warp * 4 + (lane >> 3);
+                const uint4 x = tile[cc * 8 + (q ^ ((cc >> 2) & 7))];
+                if (J0 + cc < m) *reinterpret_cast<uint4 *>(out + (size_t)(J0 + cc) * ldc + I0 + rs + 4 * q) = x;
+                racc[0] += x.x; racc[1] += x.y; racc[2] += x.z; racc[3] += x.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                racc[j] += __shfl_xor_sync(0xffffffffu, racc[j], 8);
+                racc[j] += __shfl_xor_sync(0xffffffffu, racc[j], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<unsigned long long *>(&rowacc[rs + 4 * q + j]), (unsigned long long)racc[j]);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (keep[c]) red_add_u64(SP0 + c0 + c, sum[c]);
+    if (mirror)
+        for (int i = tid; i < CS_S; i += CS_THREADS) red_add_u64(SP0 + I0 + i, rowacc[i]);
+}
+
 // clusterboot: k x k contingency table of (c1 label of the resampled cell, bootstrap label)
 __global__ void k_contingency(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m,
                               const int *__restrict__ part_slot /* [N] c1 group by cell */, int k, int *tab)
@@ -1094,7 +1209,19 @@ static void host_subset_prepare(HostSubset *H, int N, int row0, int row1, const 
 // want_compact: the caller will make many passes (PAM): a proper subset is copied once into a compact matrix
 // D[subset, subset] (columns in sorted-cell order; tie-breaking still follows the POSITIONS) so that every later pass
 // reads only the distances it needs instead of whole rows of the resident matrix.
-static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H)
+// `pin`: optional page-locked arena of >= 8 N ints.  With it the table uploads are true asynchronous copies (the host
+// does not wait for the stream to drain, as it does when the driver stages pageable memory) and H may be rewritten
+// as soon as the call returns; the arena itself must stay untouched until the copies have run.
+static inline const int *stage_table(int *&pin, const std::vector<int> &v)
+{
+    if (!pin) return v.data();
+    int *dst = pin;
+    memcpy(dst, v.data(), v.size() * sizeof(int));
+    pin += v.size();
+    return dst;
+}
+
+static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = nullptr)
 {
     rid_ctx *ctx = dm->ctx;
     const int N = dm->N, m = H.m;
@@ -1125,22 +1252,40 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H)
         }
         if (!ok) compact = false; // not enough memory somewhere: scan the resident matrix through the row list
         else {
-            RID_CUDA(cudaMemcpyAsync(w->subset, H.subset_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->pos_of, H.pos_c.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->colmap, H.ccells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-            RID_CUDA(cudaMemcpyAsync(w->subset_cells, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->subset, stage_table(pin, H.subset_c), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->pos_of, stage_table(pin, H.pos_c), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->colmap, stage_table(pin, H.ccells), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            RID_CUDA(cudaMemcpyAsync(w->subset_cells, stage_table(pin, H.cells), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             // SP (BUILD step 0) is accumulated by the compaction pass
             RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
             if (w->nls) {
-                RID_CUDA(cudaMemcpyAsync(w->rows, H.iota.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                RID_CUDA(cudaMemcpyAsync(w->rows_pos, H.rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                RID_CUDA(cudaMemcpyAsync(w->src_rows, H.src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-                dim3 grid((unsigned)((w->nls + COMPACT_ROWS - 1) / COMPACT_ROWS), (unsigned)((ldc + 511) / 512));
+                RID_CUDA(cudaMemcpyAsync(w->rows, stage_table(pin, H.iota), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->rows_pos, stage_table(pin, H.rows_pos), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                RID_CUDA(cudaMemcpyAsync(w->src_rows, stage_table(pin, H.src), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                // complete view (rows == columns == the sorted subset): gather the upper triangle only and mirror it
+                const bool sym = w->nls == m && dm->row0 == 0 && dm->row1 == N && !getenv("RID_COMPACT_FULL");
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
-                LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->nls, w->colmap, w->cbuf, ldc, m,
-                       w->acc + 4);
-                rid_prof_end(ctx, pe, RID_PROF_COMPACT, (double)w->nls * ((double)N + (double)m) * 4.0,
-                             (double)w->nls * ((double)dm->ld + (double)ldc) * 4.0);
+                if (sym) {
+                    static bool attr_set = false;
+                    if (!attr_set) {
+                        RID_CUDA(cudaFuncSetAttribute(k_compact_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+                        attr_set = true;
+                    }
+                    const unsigned nb = (unsigned)((m + CS_S - 1) / CS_S);
+                    LAUNCH(ctx, k_compact_sym, dim3(nb, nb), CS_THREADS, CS_SMEM, dm->D, dm->ld, w->colmap, w->cbuf, ldc, m,
+                           w->acc + 4);
+                    // useful bytes: the upper triangle gathered once + the square written; requested: the source spans
+                    // of the gathered tiles (whole sectors: ~N/m source columns per compact column) + the square
+                    const double tri = 0.5 * (double)m * ((double)m + 1.0);
+                    rid_prof_end(ctx, pe, RID_PROF_COMPACT, (tri + (double)m * (double)m) * 4.0,
+                                 (tri * (double)N / (double)m + (double)m * (double)ldc) * 4.0);
+                } else {
+                    dim3 grid((unsigned)((w->nls + COMPACT_ROWS - 1) / COMPACT_ROWS), (unsigned)((ldc + 511) / 512));
+                    LAUNCH(ctx, k_compact, grid, 128, 0, dm->D, dm->ld, w->src_rows, w->nls, w->colmap, w->cbuf, ldc, m,
+                           w->acc + 4);
+                    rid_prof_end(ctx, pe, RID_PROF_COMPACT, (double)w->nls * ((double)N + (double)m) * 4.0,
+                                 (double)w->nls * ((double)dm->ld + (double)ldc) * 4.0);
+                }
                 RID_CUDA(cudaGetLastError());
             }
             // pageable host buffers: the async copies above have been staged by the time the calls return
@@ -1156,12 +1301,13 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H)
     w->sp0_ready = false;
     w->mat = dm->D;
     w->ld = dm->ld;
-    RID_CUDA(cudaMemcpyAsync(w->subset, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_CUDA(cudaMemcpyAsync(w->subset_cells, H.cells.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_CUDA(cudaMemcpyAsync(w->pos_of, H.pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int *h_cells = stage_table(pin, H.cells);
+    RID_CUDA(cudaMemcpyAsync(w->subset, h_cells, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->subset_cells, h_cells, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(w->pos_of, stage_table(pin, H.pos_of), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (w->nls) {
-        RID_CUDA(cudaMemcpyAsync(w->rows, H.src.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        RID_CUDA(cudaMemcpyAsync(w->rows_pos, H.rows_pos.data(), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->rows, stage_table(pin, H.src), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->rows_pos, stage_table(pin, H.rows_pos), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     return RID_OK;
 }
@@ -1238,15 +1384,15 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
             w->sp0_ready = false;
             RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
         } else {
-            RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream));
+            if (s == std::max(k_from, 1)) // the selection kernel leaves AQ0 zeroed for the next step
+                RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream));
             RID_TRY((launch_scan<2>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, w->chg_count, 0,
                                     RID_PROF_SCAN_BUILD)));
             RID_TRY(rid_allreduce_u64(ctx, AQ0, w->ld));
-            LAUNCH(ctx, k_sp_sub, nblk((int)w->ld, 256), 256, 0, SP, AQ0, w->ld);
         }
+        // picks the next medoid; for s > 0 it first applies SP -= AQ0 (and clears AQ0 and the changed-row counter)
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
-               w->is_med, w->blockbest, w->state, 0);
-        RID_CUDA(cudaMemsetAsync(w->chg_count, 0, sizeof(int), ctx->stream));
+               w->is_med, w->blockbest, w->state, 0, s > 0 ? AQ0 : (u64 *)nullptr, w->chg_count);
         if (w->nls)
             LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, w->mat, w->ld, w->rows, w->nls, w->capP,
                    w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
@@ -1358,7 +1504,7 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
     }
     auto sel_swap = k_select<false>;
     LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 1);
+           w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -1366,13 +1512,48 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
 // SWAP until no improving swap is left.  Medoids (k of them) must be installed in w->med / is_med.
 // On return: state.td_build = TD before the first swap, state.td = final TD, w->grp / capP / capQ describe the
 // final medoids for the owned rows.
-static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
+// The first SWAP iteration (full scan) and `ahead` incremental iterations, enqueued without any host round trip: every
+// kernel after the local optimum is a no-op (state.done).  One rank, 2 <= k, k*k <= K2MAX only.  The caller reads
+// state.done later and, in the rare case that more swaps were needed, resumes with pam_swap(..., resume = true).
+static int pam_swap_enqueue(rid_dmat *dm, PamWs *w, int k, int ahead, int *n_delta)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(pam_assign(dm, w, k, 0));
+    LAUNCH(ctx, k_capture_td_build, 1, 1, 0, w->state, w->acc);
+    RID_TRY(sort_rows_by_group(dm, w, k, 0));
+    RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, 0, RID_PROF_SCAN_SWAP)));
+    auto sel_swap = k_select<false>;
+    LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr);
+    RID_CUDA(cudaGetLastError());
+    for (int i = 0; i < ahead; ++i) RID_TRY(pam_swap_delta_iteration(dm, w, k, n_delta));
+    return RID_OK;
+}
+
+static int pam_credit_delta_passes(rid_ctx *ctx, PamWs *w, size_t prof_start, int n_delta)
+{
+    if (!((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) || n_delta <= 0) return RID_OK;
+    // credit the delta passes with the rows they really rescanned
+    int cnt = std::min(n_delta, CNT_HIST);
+    std::vector<int> hist(cnt);
+    RID_CUDA(cudaMemcpy(hist.data(), w->cnt_hist, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+    int j = 0;
+    for (size_t i = prof_start; i < ctx->prof.size() && j < cnt; ++i)
+        if (ctx->prof[i].kind == RID_PROF_SCAN_DELTA) {
+            ctx->prof[i].work = (double)hist[j] * (double)w->m * 4.0;
+            ctx->prof[i].traffic = (double)hist[j] * (double)w->ld * 4.0;
+            ++j;
+        }
+    return RID_OK;
+}
+
+static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resume = false)
 {
     rid_ctx *ctx = dm->ctx;
     // how many iterations to enqueue between host checks: per-iteration work is ~ nls*ld*4 bytes
     double bytes = (double)w->nls * (double)w->ld * 4.0;
     int batch = bytes > 2.0e9 ? 1 : (bytes > 2.0e8 ? 2 : 8);
-    bool first = true;
+    bool first = !resume;
     const bool incremental = k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL");
     if (incremental) batch = std::max(batch, 2);
     int n_delta = 0;
@@ -1400,7 +1581,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
                 RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
                 auto sel_swap = k_select<false>;
                 LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
-                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk);
+                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk, (u64 *)nullptr, (int *)nullptr);
                 RID_CUDA(cudaGetLastError());
             }
             // every later iteration only rescans the rows whose (nearest, second nearest) pair changed
@@ -1414,19 +1595,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state)
         }
         if (h_state->done) break;
     }
-    if (((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) && n_delta > 0) {
-        // credit the delta passes with the rows they really rescanned
-        int cnt = std::min(n_delta, CNT_HIST);
-        std::vector<int> hist(cnt);
-        RID_CUDA(cudaMemcpy(hist.data(), w->cnt_hist, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
-        int j = 0;
-        for (size_t i = prof_start; i < ctx->prof.size() && j < cnt; ++i)
-            if (ctx->prof[i].kind == RID_PROF_SCAN_DELTA) {
-                ctx->prof[i].work = (double)hist[j] * (double)w->m * 4.0;
-                ctx->prof[i].traffic = (double)hist[j] * (double)w->ld * 4.0;
-                ++j;
-            }
-    }
+    RID_TRY(pam_credit_delta_passes(ctx, w, prof_start, n_delta));
     return RID_OK;
 }
 
@@ -1831,12 +2000,112 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         fut = std::async(std::launch::async, host_subset_prepare, &prep[i & 1], work->N, work->row0, work->row1, ptr[b],
                          sample_len[b], true);
     };
+    auto jaccard_row = [&](const int *t, int b) {
+        std::vector<long long> ca(k, 0), cb(k, 0);
+        for (int a = 0; a < k; ++a)
+            for (int c = 0; c < k; ++c) { ca[a] += t[(size_t)a * k + c]; cb[c] += t[(size_t)a * k + c]; }
+        for (int j = 0; j < k; ++j) {
+            double best = 0.0;
+            for (int c = 0; c < k; ++c) {
+                long long inter = t[(size_t)j * k + c], uni = ca[j] + cb[c] - inter;
+                double cj = uni == 0 ? 0.0 : (double)inter / (double)uni; // clujaccard(zerobyzero=0)
+                if (cj > best) best = cj;
+            }
+            bootresult[(size_t)b * k + j] = best;
+        }
+    };
+    // Replicates are independent.  With the whole matrix on this GPU they run as a two-deep pipeline: a replicate is
+    // enqueued from start to finish (tables from page-locked memory, compaction, BUILD, the first SWAP scan plus a few
+    // incremental iterations that turn into no-ops at the optimum, labels, contingency table, result copies) without
+    // one host round trip, in its own workspace, while the host already prepares and enqueues the next one; results
+    // are picked up two replicates later.  A host hiccup shorter than a replicate no longer idles the GPU.
+    const int ahead = getenv("RID_BOOT_AHEAD") ? std::max(0, atoi(getenv("RID_BOOT_AHEAD"))) : 6;
+    bool pipelined = rc == RID_OK && work->ctx->world == 1 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") &&
+                     !getenv("RID_BOOT_SYNC") && !mine.empty();
+    struct Slot {
+        rid_dmat view;
+        rid_dmat *dm = nullptr;
+        cudaEvent_t ev = nullptr;
+        int *pin = nullptr, *h_tab = nullptr, *d_tab = nullptr;
+        PamState *h_state = nullptr;
+        int b = -1, m = 0, n_delta = 0;
+        size_t prof_start = 0;
+    } slot[2];
+    int depth = 2;
+    // slot layout (ints): subset tables [8 N] | PamState [64, 8-byte aligned] | contingency table [k k]
+    const size_t tab_off = (((size_t)8 * N + 1) & ~(size_t)1) + 64;
+    const size_t slot_ints = (tab_off + (size_t)k * k + 1) & ~(size_t)1;
+    if (pipelined) {
+        int *pin = (int *)rid_pinned(ctx, 2 * slot_ints * sizeof(int));
+        int *dt = nullptr;
+        if (!pin || cudaMalloc(&dt, 2 * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
+        for (int s2 = 0; s2 < 2 && pipelined; ++s2) {
+            Slot &S = slot[s2];
+            S.pin = pin + s2 * slot_ints;
+            S.h_tab = S.pin + tab_off;
+            S.h_state = (PamState *)(S.pin + tab_off - 64);
+            S.d_tab = dt + (size_t)s2 * k * k;
+            if (cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
+            if (s2 == 0) S.dm = work;
+            else { S.view = *work; S.view.ws = nullptr; S.dm = &S.view; }
+        }
+        if (!pipelined && dt) cudaFree(dt);
+    }
+    auto tabulate = [&](Slot &S, PamWs *w) { // device labels by position -> contingency table -> page-locked slot
+        cudaMemsetAsync(w->lab_pos, 0, (size_t)w->m * sizeof(int), ctx->stream);
+        if (w->nls) LAUNCH(ctx, k_labels_to_pos, nblk(w->nls, 256), 256, 0, w->rows_pos, w->grp, w->nls, w->lab_pos);
+        cudaMemsetAsync(S.d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
+        LAUNCH(ctx, k_contingency, nblk(S.m, 256), 256, 0, w->subset_cells, w->lab_pos, S.m, d_part, k, S.d_tab);
+        cudaMemcpyAsync(S.h_state, w->state, sizeof(PamState), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(S.h_tab, S.d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        return cudaEventRecord(S.ev, ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess ? RID_OK : RID_ERR_CUDA;
+    };
+    auto finish = [&](Slot &S) -> int { // wait for the slot's replicate and turn its table into Jaccard similarities
+        if (S.b < 0) return RID_OK;
+        PamWs *w = S.dm->ws;
+        if (cudaEventSynchronize(S.ev) != cudaSuccess) { rid_set_error("rid_clusterboot: %s", cudaGetErrorString(cudaGetLastError())); return RID_ERR_CUDA; }
+        if (!S.h_state->done) { // more swaps than were enqueued ahead: finish this replicate the synchronous way
+            PamState hs;
+            RID_TRY(pam_swap(S.dm, w, k, &hs, true));
+            RID_TRY(tabulate(S, w));
+            RID_CUDA(cudaEventSynchronize(S.ev));
+        }
+        RID_TRY(pam_credit_delta_passes(ctx, w, S.prof_start, S.n_delta));
+        jaccard_row(S.h_tab, S.b);
+        S.b = -1;
+        return RID_OK;
+    };
     if (!mine.empty() && rc == RID_OK) launch_prep(0);
     for (size_t i = 0; i < mine.size() && rc == RID_OK; ++i) {
         const int b = mine[i], m = sample_len[b];
         const int *sp = ptr[b];
         fut.get();
         if (i + 1 < mine.size()) launch_prep(i + 1);
+        if (pipelined) {
+            Slot &S = slot[depth == 2 ? (i & 1) : 0];
+            if ((rc = finish(S)) != RID_OK) break; // the replicate that used this slot two rounds ago
+            HostSubset &H = prep[i & 1];
+            if (k >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); rc = RID_ERR_ARG; break; }
+            if ((rc = pam_check_na(work, sp, m)) != RID_OK) break;
+            PamWs *w = nullptr;
+            if ((rc = ws_get(S.dm, k, &w)) != RID_OK) {
+                if (S.dm == work) break;
+                depth = 1; rc = RID_OK; // no room for a second workspace: one replicate at a time
+                Slot &S0 = slot[0];
+                if ((rc = finish(S0)) != RID_OK || (rc = ws_get(S0.dm, k, &w)) != RID_OK) break;
+            }
+            Slot &T = depth == 2 ? S : slot[0];
+            T.b = b; T.m = m; T.n_delta = 0; T.prof_start = ctx->prof.size();
+            if ((rc = pam_install_subset(T.dm, w, H, T.pin)) != RID_OK) break;
+            if (H.want_compact && !w->compact && depth == 2) depth = 1; // memory is short: stop double-buffering after this one
+            if ((rc = pam_begin(T.dm, w)) != RID_OK || (rc = pam_build(T.dm, w, 0, k)) != RID_OK ||
+                (rc = pam_swap_enqueue(T.dm, w, k, ahead, &T.n_delta)) != RID_OK || (rc = tabulate(T, w)) != RID_OK) break;
+            if (depth == 1 && &T != &slot[0]) { // drain the second slot and give its buffers back
+                if ((rc = finish(T)) != RID_OK) break;
+                rid_pam_ws_free(T.view.ws, ctx); T.view.ws = nullptr;
+            }
+            continue;
+        }
         blab.resize(m);
         rc = pam_run(work, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr, &prep[i & 1]);
         if (rc != RID_OK) break;
@@ -1850,18 +2119,16 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             rc = RID_ERR_CUDA;
             break;
         }
-        std::vector<long long> ca(k, 0), cb(k, 0);
-        for (int a = 0; a < k; ++a)
-            for (int c = 0; c < k; ++c) { ca[a] += tab[(size_t)a * k + c]; cb[c] += tab[(size_t)a * k + c]; }
-        for (int j = 0; j < k; ++j) {
-            double best = 0.0;
-            for (int c = 0; c < k; ++c) {
-                long long inter = tab[(size_t)j * k + c], uni = ca[j] + cb[c] - inter;
-                double cj = uni == 0 ? 0.0 : (double)inter / (double)uni; // clujaccard(zerobyzero=0)
-                if (cj > best) best = cj;
-            }
-            bootresult[(size_t)b * k + j] = best;
+        jaccard_row(tab.data(), b);
+    }
+    if (pipelined) {
+        for (int s2 = 0; s2 < 2; ++s2) {
+            if (rc == RID_OK) rc = finish(slot[s2]);
+            if (slot[s2].ev) cudaEventDestroy(slot[s2].ev);
         }
+        cudaStreamSynchronize(ctx->stream);
+        if (slot[1].view.ws) { rid_pam_ws_free(slot[1].view.ws, ctx); slot[1].view.ws = nullptr; }
+        cudaFree(slot[0].d_tab);
     }
     if (fut.valid()) fut.wait();
     cudaFree(d_part);

@@ -137,15 +137,20 @@ def test_pam_identical_to_oracle_on_device_matrix(ctx, oracle, metric):
     dm.free()
 
 
-def test_subset_runs_use_compact_copy_and_stay_identical(ctx, oracle):
+@pytest.mark.parametrize("metric,gather", [("pearson", "triangle"), ("pearson", "rows"), ("euclidean", "triangle")])
+def test_subset_runs_use_compact_copy_and_stay_identical(ctx, oracle, metric, gather, monkeypatch):
     """Subsets large enough (m*m*4 >= 1 MB) are clustered on a compacted copy D[subset, subset] whose columns are in
-    sorted-cell order; positions (the order of `subset`) must still drive every tie-break and the label numbering."""
+    sorted-cell order; positions (the order of `subset`) must still drive every tie-break and the label numbering.
+    The copy is built from the upper triangle of the source and mirrored (k_compact_sym; 512-wide super-tiles, here
+    2 and 3 per side with ragged edges) or, with RID_COMPACT_FULL=1 / on a row shard, from whole rows (k_compact)."""
     from raceid3_stemid2_package_b200.scseq import bootstrap_samples
 
+    if gather == "rows":
+        monkeypatch.setenv("RID_COMPACT_FULL", "1")
     x, _ = _features(seed=21, G=120, N=1500, C=5)
     x[:, 700] = x[:, 3]
     x[:, 1400] = x[:, 3]  # duplicate cells => exact ties inside the subset
-    dm = ctx.dist(x, "pearson")
+    dm = ctx.dist(x, metric)
     Dg = dm.as_matrix()
     samples = bootstrap_samples(1500, 3, 4242)
     for sub in samples:
@@ -383,20 +388,33 @@ def test_gap_sweep_batched_equals_single_pass_per_k(ctx, monkeypatch):
     dm.free()
 
 
-def test_clusterboot_identical(ctx, oracle):
+@pytest.mark.parametrize("schedule", ["pipelined", "pipelined_resume", "synchronous"])
+def test_clusterboot_identical(ctx, oracle, schedule, monkeypatch):
+    """Replicates run as a two-deep asynchronous pipeline (SWAP iterations enqueued ahead, results picked up later).
+    RID_BOOT_AHEAD=0 makes every replicate that swaps at all take the resume path; RID_BOOT_SYNC=1 is the one-at-a-time
+    schedule (the one multi-rank row shards use).  The point cloud on a curve needs several swaps per run."""
     from raceid3_stemid2_package_b200.scseq import bootstrap_samples
 
+    if schedule == "pipelined_resume":
+        monkeypatch.setenv("RID_BOOT_AHEAD", "0")
+    if schedule == "synchronous":
+        monkeypatch.setenv("RID_BOOT_SYNC", "1")
     x, _ = _features(seed=10, G=150, N=300, C=4)
-    dm = ctx.dist(x, "spearman")
-    Dg = dm.as_matrix()
-    samples = bootstrap_samples(300, 6, 17000)
-    r = dm.clusterboot(4, samples)
-    ro = oracle.clusterboot(Dg, 4, samples)
-    assert np.array_equal(r["partition"], ro["partition"])
-    assert np.array_equal(r["id_med"], ro["id_med"])
-    assert np.array_equal(r["bootresult"], ro["bootresult"])
-    assert np.allclose(r["bootmean"], ro["bootmean"], atol=1e-15)
-    dm.free()
+    rng = np.random.default_rng(5)
+    t = np.sort(rng.uniform(0, 1, 700))
+    curve = np.stack([t, np.sin(7 * t), np.cos(3 * t) * t]).astype(np.float64) + rng.normal(0, 0.01, (3, 700))
+    for xx, metric, k, B in ((x, "spearman", 4, 6), (curve, "euclidean", 9, 7)):
+        n = xx.shape[1]
+        dm = ctx.dist(xx, metric)
+        Dg = dm.as_matrix()
+        samples = bootstrap_samples(n, B, 17000)
+        r = dm.clusterboot(k, samples)
+        ro = oracle.clusterboot(Dg, k, samples)
+        assert np.array_equal(r["partition"], ro["partition"])
+        assert np.array_equal(r["id_med"], ro["id_med"])
+        assert np.array_equal(r["bootresult"], ro["bootresult"])
+        assert np.allclose(r["bootmean"], ro["bootmean"], atol=1e-15)
+        dm.free()
 
 
 @pytest.mark.parametrize("name", ["cfg1_intestinalDataSmall.npz", "cfg2_intestinalData.npz"])
