@@ -57,6 +57,11 @@ struct rid_ctx {
     struct IpcMap { unsigned char handle[64]; void *ptr; };
     std::vector<IpcMap> ipc;
     void *scratch = nullptr; // small device scratch (barriers, handle exchange)
+    // tile list of the persistent distance kernel (device), cached per problem shape
+    void *i8_tiles = nullptr;
+    long long i8_tiles_key[6] = {-1, -1, -1, -1, -1, -1};
+    long long i8_ntiles = 0;
+    size_t i8_tiles_bytes = 0;
     // page-locked host staging (grow-only), e.g. the subset tables and result slots of the bootstrap pipeline
     void *pin = nullptr;
     size_t pin_bytes = 0;

@@ -143,6 +143,7 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     rid_pool_trim(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->i8_tiles) cudaFree(ctx->i8_tiles);
     if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

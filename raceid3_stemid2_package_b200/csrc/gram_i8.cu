@@ -115,6 +115,31 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------
+#define I8_IDESC_MN(m, n) ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((n) >> 3) << 17) | ((uint32_t)((m) >> 4) << 24))
+#define I8_PEER_MASK 0xFEFFFFFFu // clears the CTA-pair peer bit of a shared::cluster address: "the even CTA's copy"
+
+// TMA load issued by either CTA of a pair into its OWN shared memory, completing on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint32_t leader_bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -146,6 +171,78 @@ __device__ __host__ __forceinline__ bool i8_pair_mine(int me, int b, int world, 
     const int d = (b - me + world) % world;
     if (2 * d != world) return 2 * d < world;
     return (((i0 / 384) + (j0 / 384)) & 1) == (me < b ? 0 : 1);
+}
+
+// ===== epilogue of one 128 x 96 tile, all 8 warps of the CTA =====
+__device__ __forceinline__ void i8_epilogue(const I8Params &P, uint32_t tmem_base, uint64_t *tmem_full_bar, int warp, int lane,
+                                            int i0, int j0, bool tile_valid)
+{
+    // ===== epilogue, all 8 warps: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
+    // warp w may touch TMEM lanes 32*(w%4)..+31; warps w and w+4 share a lane quarter and split the 96 columns
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int r = q * 32 + lane;     // tile row = TMEM lane
+    const int gi = i0 + r;
+    const bool row_ok = tile_valid && gi < P.row0 + P.nloc;
+    const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
+    const bool zr = row_ok ? P.zero_var[gi] : false;
+    const int cbeg = (warp >> 2) * (I8_BN / 2);
+    for (int c0 = cbeg; c0 < cbeg + I8_BN / 2; c0 += 16) {
+        int a2[16], a3[16], a4[16], a5[16], a6[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        tmem_ld16(ta + 0 * I8_BN, a2);
+        tmem_ld16(ta + 1 * I8_BN, a3);
+        tmem_ld16(ta + 2 * I8_BN, a4);
+        tmem_ld16(ta + 3 * I8_BN, a5);
+        tmem_ld16(ta + 4 * I8_BN, a6);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        u32 qv[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int gj = j0 + c0 + c;
+            u32 v = 0u;
+            if (row_ok && gj < P.N) {
+                if (gj == gi) {
+                    v = zr ? RID_Q_NA : 0u;
+                } else if (zr || P.zero_var[gj]) {
+                    v = RID_Q_NA;
+                } else {
+                    long long acc = (long long)a6[c];
+                    acc = acc * 128 + a5[c];
+                    acc = acc * 128 + a4[c];
+                    acc = acc * 128 + a3[c];
+                    acc = acc * 128 + a2[c];
+                    double rr = (double)acc * rs_i * P.rowscale[gj];
+                    rr = fmin(1.0, fmax(-1.0, rr));
+                    v = (u32)__double2ull_rn((1.0 - rr) * P.inv_step);
+                }
+            }
+            qv[c] = v;
+        }
+        // direct store: 16 consecutive columns of row gi (64-byte aligned: j0 and c0 are multiples of 16)
+        if (row_ok) {
+            u32 *dst = P.D + (size_t)(gi - P.row0) * P.ld + j0 + c0;
+            if ((size_t)(j0 + c0 + 16) <= P.ld) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    *reinterpret_cast<uint4 *>(dst + c) = make_uint4(qv[c], qv[c + 1], qv[c + 2], qv[c + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
+            }
+        }
+        // mirror store: column gi of rows j0+c0..+15; a warp's 32 lanes write 128 contiguous bytes
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int gj = j0 + c0 + c;
+            if (tile_valid && gj < P.N && (size_t)gi < P.ld) {
+                const int ow = min(gj / P.per, P.world - 1);
+                P.peer[ow][(size_t)(gj - ow * P.per) * P.ld + gi] = row_ok ? qv[c] : 0u;
+            }
+        }
+    }
 }
 
 // CL = 1: one CTA per tile.  CL = 2: 2 x 2 thread-block clusters; the two CTAs of a cluster row share their A panel and
@@ -298,78 +395,381 @@ k_gram_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     __syncwarp();
     {
-        // ===== epilogue, all 8 warps: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
-        // warp w may touch TMEM lanes 32*(w%4)..+31; warps w and w+4 share a lane quarter and split the 96 columns
-        mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;
-        const int r = q * 32 + lane;     // tile row = TMEM lane
-        const int gi = i0 + r;
-        const bool row_ok = tile_valid && gi < P.row0 + P.nloc;
-        const double rs_i = row_ok ? P.rowscale[gi] * 16384.0 : 0.0; // 128^2: the lowest kept diagonal is s+t = 2
-        const bool zr = row_ok ? P.zero_var[gi] : false;
-        const int cbeg = (warp >> 2) * (I8_BN / 2);
-        for (int c0 = cbeg; c0 < cbeg + I8_BN / 2; c0 += 16) {
-            int a2[16], a3[16], a4[16], a5[16], a6[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            tmem_ld16(ta + 0 * I8_BN, a2);
-            tmem_ld16(ta + 1 * I8_BN, a3);
-            tmem_ld16(ta + 2 * I8_BN, a4);
-            tmem_ld16(ta + 3 * I8_BN, a5);
-            tmem_ld16(ta + 4 * I8_BN, a6);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            u32 qv[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int gj = j0 + c0 + c;
-                u32 v = 0u;
-                if (row_ok && gj < P.N) {
-                    if (gj == gi) {
-                        v = zr ? RID_Q_NA : 0u;
-                    } else if (zr || P.zero_var[gj]) {
-                        v = RID_Q_NA;
-                    } else {
-                        long long acc = (long long)a6[c];
-                        acc = acc * 128 + a5[c];
-                        acc = acc * 128 + a4[c];
-                        acc = acc * 128 + a3[c];
-                        acc = acc * 128 + a2[c];
-                        double rr = (double)acc * rs_i * P.rowscale[gj];
-                        rr = fmin(1.0, fmax(-1.0, rr));
-                        v = (u32)__double2ull_rn((1.0 - rr) * P.inv_step);
-                    }
-                }
-                qv[c] = v;
-            }
-            // direct store: 16 consecutive columns of row gi (64-byte aligned: j0 and c0 are multiples of 16)
-            if (row_ok) {
-                u32 *dst = P.D + (size_t)(gi - P.row0) * P.ld + j0 + c0;
-                if ((size_t)(j0 + c0 + 16) <= P.ld) {
-#pragma unroll
-                    for (int c = 0; c < 16; c += 4)
-                        *reinterpret_cast<uint4 *>(dst + c) = make_uint4(qv[c], qv[c + 1], qv[c + 2], qv[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
-                }
-            }
-            // mirror store: column gi of rows j0+c0..+15; a warp's 32 lanes write 128 contiguous bytes
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int gj = j0 + c0 + c;
-                if (tile_valid && gj < P.N && (size_t)gi < P.ld) {
-                    const int ow = min(gj / P.per, P.world - 1);
-                    P.peer[ow][(size_t)(gj - ow * P.per) * P.ld + gi] = row_ok ? qv[c] : 0u;
-                }
-            }
-        }
+        i8_epilogue(P, tmem_base, &tmem_full_bar, warp, lane, i0, j0, tile_valid);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     if (CL == 2) cluster_sync_all(); // partners may still arrive on this CTA's barriers / multicast into its stages
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+// CTA-pair kernel: two CTAs on the two SMs of a TPC own a 256 x 96 output tile (128 rows each) and run ONE stream of
+// tcgen05.mma.cta_group::2 (M = 256) issued by the even CTA.  In pair mode the tensor cores of both SMs read the B
+// operand half from either SM's shared memory, so an N = 192 instruction (two digit products) costs each SM 4 KB of A
+// + 3 KB of B per K = 32 step instead of 4 + 6 KB: 118 B/clk of shared-memory traffic (operand reads + TMA writes)
+// instead of 152 B/clk against the 128 B/clk the SM sustains -- the single-CTA kernel's bound.
+// What each CTA stages per K block: its own 128 rows of the four A digit planes, and B "slots" whose two halves live
+// in the two CTAs:  P01 = plane 0 | plane 1,  P12 = plane 1 | plane 2,  P23 = plane 2 | plane 3 (even CTA | odd CTA),
+// H3 = rows 0..47 | rows 48..95 of plane 3.  The 13 digit products are the 7 instructions
+//   (A0,P23) (A1,P12) (A1,H3) (A3,P23) (A2,P01) (A2,P23) (A3,P01)
+// in an order in which both diagonals an N = 192 instruction touches are either both fresh or both started, so the very
+// first K step needs no special case.
+#define I8P_B_BYTES (3 * I8_B_PLANE + I8_B_PLANE / 2)   // 43008
+#define I8P_STAGE_BYTES (4 * I8_A_PLANE + I8P_B_BYTES)  // 108544
+#define I8P_SMEM (I8_STAGES * I8P_STAGE_BYTES + 1024)
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_gram_i8_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB48, I8Params P)
+{
+    const int cta = (int)(blockIdx.x & 1); // rank in the pair (cluster dims (2,1,1))
+    int tile_m, tile_n;
+    {
+        const int gx = P.tiles_n, gy = (P.tiles_loc + 1) / 2, grp_rows = I8_GROUP / 2;
+        const long long L = (long long)(blockIdx.x >> 1);
+        const long long per_group = (long long)grp_rows * gx;
+        const int grp = (int)(L / per_group);
+        const int rows_in_grp = min(grp_rows, gy - grp * grp_rows);
+        const long long r = L - (long long)grp * per_group;
+        tile_m = (grp * grp_rows + (int)(r % rows_in_grp)) * 2 + cta;
+        tile_n = (int)(r / rows_in_grp);
+    }
+    const int i0 = P.row0 + tile_m * I8_BM, j0 = tile_n * I8_BN;
+    const bool tile_valid = tile_m < P.tiles_loc && tile_n < P.tiles_n;
+    {
+        bool need = false; // the pair runs if either of its tiles is needed (same decision in both CTAs)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int tm = tile_m - cta + dy;
+            if (tm >= P.tiles_loc) continue;
+            const int ii = P.row0 + tm * I8_BM;
+            const int b1 = min(j0 / P.per, P.world - 1), b2 = min(min(j0 + I8_BN - 1, P.N - 1) / P.per, P.world - 1);
+            need = need || i8_pair_mine(P.rank, b1, P.world, ii, j0) || i8_pair_mine(P.rank, b2, P.world, ii, j0);
+        }
+        if (!need) return;
+    }
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB48) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) { // the same warp of BOTH CTAs allocates for the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // both CTAs' barriers exist before the partner's TMA / commits arrive on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own halves of the B slots; bytes are counted on the leader's barrier
+        if (lane == 0) {
+            for (int kb = 0; kb < P.nkb; ++kb) {
+                const int st = kb % I8_STAGES;
+                const uint32_t ph = (kb / I8_STAGES) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1);
+                uint8_t *sa = smem + (size_t)st * I8P_STAGE_BYTES, *sb = sa + 4 * I8_A_PLANE;
+                if (cta == 0) mbar_expect_tx(&full_bar[st], 2 * I8P_STAGE_BYTES);
+                const uint32_t lbar = smem_u32(&full_bar[st]) & I8_PEER_MASK;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    tma_load_2d_2sm(sa + s * I8_A_PLANE, &tmA, kb * I8_BK, s * P.plane_rows + i0, lbar);
+#pragma unroll
+                for (int slot = 0; slot < 3; ++slot) { // P01, P12, P23: plane (slot + cta), all 96 rows as two 48-row boxes
+                    const int row = (slot + cta) * P.plane_rows + j0;
+                    tma_load_2d_2sm(sb + slot * I8_B_PLANE, &tmB48, kb * I8_BK, row, lbar);
+                    tma_load_2d_2sm(sb + slot * I8_B_PLANE + I8_B_PLANE / 2, &tmB48, kb * I8_BK, row + I8_BN / 2, lbar);
+                }
+                tma_load_2d_2sm(sb + 3 * I8_B_PLANE, &tmB48, kb * I8_BK, 3 * P.plane_rows + j0 + cta * (I8_BN / 2), lbar); // H3
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the even CTA drives the tensor cores of both SMs =====
+        if (lane == 0 && cta == 0) {
+            constexpr uint32_t ID192 = I8_IDESC_MN(256, 2 * I8_BN), ID96 = I8_IDESC_MN(256, I8_BN);
+            for (int kb = 0; kb < P.nkb; ++kb) {
+                const int st = kb % I8_STAGES;
+                const uint32_t ph = (kb / I8_STAGES) & 1;
+                mbar_wait(&full_bar[st], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)st * I8P_STAGE_BYTES), sb = sa + 4 * I8_A_PLANE;
+                const uint64_t A0 = umma_desc_sw128(sa), A1 = umma_desc_sw128(sa + I8_A_PLANE),
+                               A2 = umma_desc_sw128(sa + 2 * I8_A_PLANE), A3 = umma_desc_sw128(sa + 3 * I8_A_PLANE);
+                const uint64_t P01 = umma_desc_sw128(sb), P12 = umma_desc_sw128(sb + I8_B_PLANE),
+                               P23 = umma_desc_sw128(sb + 2 * I8_B_PLANE), H3 = umma_desc_sw128(sb + 3 * I8_B_PLANE);
+                const uint32_t d0 = tmem_base, d1 = tmem_base + I8_BN, d2 = tmem_base + 2 * I8_BN, d3 = tmem_base + 3 * I8_BN;
+#pragma unroll
+                for (int kk = 0; kk < I8_BK / 32; ++kk) {
+                    const uint64_t koff = (uint64_t)(2 * kk); // +32 bytes inside the 128-byte swizzle atom
+                    const uint32_t acc = (kb == 0 && kk == 0) ? 0u : 1u;
+                    umma_i8_2sm(d0, A0 + koff, P23 + koff, acc, ID192); // (0,2) (0,3) -> diagonals 0, 1
+                    umma_i8_2sm(d0, A1 + koff, P12 + koff, 1u, ID192);  // (1,1) (1,2) -> 0, 1
+                    umma_i8_2sm(d2, A1 + koff, H3 + koff, acc, ID96);   // (1,3)       -> 2
+                    umma_i8_2sm(d3, A3 + koff, P23 + koff, acc, ID192); // (3,2) (3,3) -> 3, 4
+                    umma_i8_2sm(d0, A2 + koff, P01 + koff, 1u, ID192);  // (2,0) (2,1) -> 0, 1
+                    umma_i8_2sm(d2, A2 + koff, P23 + koff, 1u, ID192);  // (2,2) (2,3) -> 2, 3
+                    umma_i8_2sm(d1, A3 + koff, P01 + koff, 1u, ID192);  // (3,0) (3,1) -> 1, 2
+                }
+                umma_commit_2sm(&empty_bar[st]); // both CTAs may refill this stage once the MMAs above have read it
+            }
+            umma_commit_2sm(&tmem_full_bar);     // accumulators final, in both CTAs
+        }
+    }
+    __syncwarp();
+    i8_epilogue(P, tmem_base, &tmem_full_bar, warp, lane, i0, j0, tile_valid);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all(); // the partner may still read this CTA's operand halves / arrive on its barriers
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Persistent kernel (the default): one CTA per SM walks the tile list with stride gridDim.x.  TMEM holds exactly one
+// tile's five accumulators, so the epilogue cannot overlap the next tile's MMAs; what the single-shot kernels above
+// lose on top of that is removed here:
+//  * the TMA producer prefetches the next tile's first two K blocks BEFORE it joins the epilogue (no pipeline refill,
+//    no CTA launch / TMEM allocation / barrier setup per tile),
+//  * the six otherwise idle warps prepare the tile's column tables (scale exponent, NA flag, mirror pointer) in shared
+//    memory while the MMAs run, so the epilogue does no global loads and no divisions per element,
+//  * the epilogue is integer only.  Row scales are exact powers of two (2^-(e_i+27)) and the step of D is 2^-27, so
+//        q = rint((1 - r) 2^27),  r = acc 2^-(e_i+e_j+54)   ==>   q = 2^27 - RNE(acc >> (e_i+e_j+27)),
+//    an exact round-half-even shift of the 64-bit dot product: no int64 -> double conversion, no FP64 chain.
+// ----------------------------------------------------------------------------------------------------------
+// (tile_m, tile_n) of the L-th tile in launch order: groups of I8_GROUP tile rows, column-major inside a group, so that
+// the CTAs in flight share a handful of A and B panels out of L2.  Host and device use the same function.
+__device__ __host__ __forceinline__ bool i8_tile_at(const I8Params &P, long long L, int &tile_m, int &tile_n)
+{
+    const int gx = P.tiles_n, gy = P.tiles_loc;
+    const long long per_group = (long long)I8_GROUP * gx;
+    const int grp = (int)(L / per_group);
+    const int rows_in_grp = (I8_GROUP < gy - grp * I8_GROUP) ? I8_GROUP : gy - grp * I8_GROUP;
+    const long long r = L - (long long)grp * per_group;
+    tile_m = grp * I8_GROUP + (int)(r % rows_in_grp);
+    tile_n = (int)(r / rows_in_grp);
+    const int ii = P.row0 + tile_m * I8_BM, jj = tile_n * I8_BN;
+    const int je = (jj + I8_BN - 1 < P.N - 1) ? jj + I8_BN - 1 : P.N - 1;
+    const int b1 = (jj / P.per < P.world - 1) ? jj / P.per : P.world - 1, b2 = (je / P.per < P.world - 1) ? je / P.per : P.world - 1;
+    return i8_pair_mine(P.rank, b1, P.world, ii, jj) || i8_pair_mine(P.rank, b2, P.world, ii, jj);
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+k_gram_i8_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, I8Params P,
+                  const int2 *__restrict__ tiles, long long ntiles)
+{
+    // `tiles` lists only the tiles this rank computes, in launch order: CTA c takes entries c, c + gridDim.x, ...  All
+    // tiles cost the same, so the CTAs stay within one "wave" of gridDim.x consecutive entries of each other and keep
+    // the L2 locality of the order (striding over ALL tiles and skipping the unneeded ones lets CTAs drift apart:
+    // 321 GB of DRAM reads per launch instead of ~35 GB).
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[I8_STAGES], empty_bar[I8_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ u32 *col_ptr[I8_BN];   // mirror destination of column c: row (j0+c) of its owner's shard, or null
+    __shared__ int col_e[I8_BN];      // e_j + 27 of column j0+c (0: no such column)
+    __shared__ unsigned char col_na[I8_BN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = ntiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    int tile_m = 0, tile_n = 0;
+    long long L = blockIdx.x;
+    if (L < total) { const int2 t0 = tiles[L]; tile_m = t0.x; tile_n = t0.y; }
+    uint32_t it = 0;      // K blocks produced (warp 0) / consumed (warp 1) so far, over all tiles
+    uint32_t tcount = 0;  // tiles done by this CTA
+    int prefetched = 0;   // K blocks of the current tile already requested (producer)
+
+    auto produce = [&](int kb, int i0, int j0) {
+        const int st = it % I8_STAGES;
+        const uint32_t ph = (it / I8_STAGES) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t *sa = smem + (size_t)st * I8_STAGE_BYTES, *sb = sa + 4 * I8_A_PLANE;
+        mbar_expect_tx(&full_bar[st], I8_STAGE_BYTES);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            tma_load_2d(sa + s * I8_A_PLANE, &tmA, kb * I8_BK, s * P.plane_rows + i0, &full_bar[st]);
+            tma_load_2d(sb + s * I8_B_PLANE, &tmB, kb * I8_BK, s * P.plane_rows + j0, &full_bar[st]);
+        }
+        ++it;
+    };
+
+    while (L < total) {
+        int next_m = 0, next_n = 0;
+        const long long Ln = L + gridDim.x;
+        if (Ln < total) { const int2 t1 = tiles[Ln]; next_m = t1.x; next_n = t1.y; }
+        const int i0 = P.row0 + tile_m * I8_BM, j0 = tile_n * I8_BN;
+
+        if (warp == 0) {
+            // ===== TMA producer: the rest of this tile, then the head of the next one =====
+            if (lane == 0) {
+                for (int kb = prefetched; kb < P.nkb; ++kb) produce(kb, i0, j0);
+                prefetched = 0;
+                if (Ln < total) {
+                    const int ni0 = P.row0 + next_m * I8_BM, nj0 = next_n * I8_BN;
+                    for (; prefetched < min(I8_STAGES, P.nkb); ++prefetched) produce(prefetched, ni0, nj0);
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            if (lane == 0) {
+                for (int kb = 0; kb < P.nkb; ++kb) {
+                    const int st = it % I8_STAGES;
+                    const uint32_t ph = (it / I8_STAGES) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + (size_t)st * I8_STAGE_BYTES), sb = sa + 4 * I8_A_PLANE;
+                    const uint64_t A0 = umma_desc_sw128(sa), A1 = umma_desc_sw128(sa + I8_A_PLANE),
+                                   A2 = umma_desc_sw128(sa + 2 * I8_A_PLANE), A3 = umma_desc_sw128(sa + 3 * I8_A_PLANE);
+                    // B planes t and t+1 are adjacent: an N = 192 instruction multiplies one A plane with both
+                    const uint64_t B0 = umma_desc_sw128(sb), B1 = umma_desc_sw128(sb + I8_B_PLANE),
+                                   B2 = umma_desc_sw128(sb + 2 * I8_B_PLANE), B3 = umma_desc_sw128(sb + 3 * I8_B_PLANE);
+                    const uint32_t d0 = tmem_base, d1 = tmem_base + I8_BN, d2 = tmem_base + 2 * I8_BN, d3 = tmem_base + 3 * I8_BN;
+                    constexpr uint32_t ID192 = I8_IDESC_N(2 * I8_BN), ID96 = I8_IDESC_N(I8_BN);
+#pragma unroll
+                    for (int kk = 0; kk < I8_BK / 32; ++kk) {
+                        const uint64_t koff = (uint64_t)(2 * kk); // +32 bytes inside the 128-byte swizzle atom
+                        // order: both diagonals an N = 192 instruction touches are either both fresh or both started
+                        const uint32_t acc = (kb == 0 && kk == 0) ? 0u : 1u;
+                        umma_i8(d0, A0 + koff, B2 + koff, acc, ID192); // (0,2) (0,3) -> diagonals 0, 1
+                        umma_i8(d0, A1 + koff, B1 + koff, 1u, ID192);  // (1,1) (1,2) -> 0, 1
+                        umma_i8(d2, A1 + koff, B3 + koff, acc, ID96);  // (1,3)       -> 2
+                        umma_i8(d3, A3 + koff, B2 + koff, acc, ID192); // (3,2) (3,3) -> 3, 4
+                        umma_i8(d0, A2 + koff, B0 + koff, 1u, ID192);  // (2,0) (2,1) -> 0, 1
+                        umma_i8(d2, A2 + koff, B2 + koff, 1u, ID192);  // (2,2) (2,3) -> 2, 3
+                        umma_i8(d1, A3 + koff, B0 + koff, 1u, ID192);  // (3,0) (3,1) -> 1, 2
+                    }
+                    umma_commit(&empty_bar[st]);
+                    ++it;
+                }
+                umma_commit(&tmem_full_bar);
+            }
+        } else {
+            // ===== column tables of this tile (warps 2..7, while the MMAs run) =====
+            for (int c = (int)threadIdx.x - 64; c < I8_BN; c += I8_THREADS - 64) {
+                const int gj = j0 + c;
+                u32 *ptr = nullptr;
+                int e = 0;
+                unsigned char na = 0;
+                if (gj < P.N) {
+                    const int ow = min(gj / P.per, P.world - 1);
+                    ptr = P.peer[ow] + (size_t)(gj - ow * P.per) * P.ld;
+                    e = 1023 - (int)((__double2hiint(P.rowscale[gj]) >> 20) & 0x7ff);
+                    na = P.zero_var[gj];
+                }
+                col_ptr[c] = ptr; col_e[c] = e; col_na[c] = na;
+            }
+        }
+        __syncthreads(); // tables written; every role is through with this tile's mainloop issue
+
+        // ===== epilogue, all 8 warps: TMEM -> registers -> fixed-point distances -> global (tile + mirror) =====
+        mbar_wait(&tmem_full_bar, tcount & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const int q = warp & 3;
+            const int gi = i0 + q * 32 + lane; // tile row = TMEM lane
+            const bool row_ok = gi < P.row0 + P.nloc;
+            const int e_i = row_ok ? 1023 - (int)((__double2hiint(P.rowscale[gi]) >> 20) & 0x7ff) : 0;
+            const bool zr = row_ok ? P.zero_var[gi] : false;
+            u32 *drow = P.D + (size_t)(gi - P.row0) * P.ld + j0;
+            const bool mirror_ok = (size_t)gi < P.ld;
+            const int cbeg = (warp >> 2) * (I8_BN / 2);
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + I8_BN / 2; c0 += 16) {
+                int a2[16], a3[16], a4[16], a5[16], a6[16];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld16(ta + 0 * I8_BN, a2);
+                tmem_ld16(ta + 1 * I8_BN, a3);
+                tmem_ld16(ta + 2 * I8_BN, a4);
+                tmem_ld16(ta + 3 * I8_BN, a5);
+                tmem_ld16(ta + 4 * I8_BN, a6);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                u32 qv[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int gj = j0 + c0 + c;
+                    const int e_j = col_e[c0 + c];
+                    // sum_d a_d 128^(d-2):  (a6 128 + a5) 2^21 + (a4 128 + a3) 2^7 + a2
+                    const long long hi = (long long)a6[c] * 128 + a5[c], mid = (long long)a4[c] * 128 + a3[c];
+                    const long long acc = (hi << 21) + (mid << 7) + a2[c];
+                    // acc carries 14 more fraction bits than sum m_i m_j 2^-0 (the lowest kept diagonal is 128^2)
+                    const int sh = e_i + e_j - 27 - 14;
+                    long long t;
+                    if (sh <= 0) t = acc << min(-sh, 20);             // (only for rows of huge dynamic range; exact)
+                    else if (sh > 62) t = 0;
+                    else t = (acc + ((1ll << (sh - 1)) - 1) + ((acc >> sh) & 1)) >> sh; // round half to even
+                    const int ti = (int)max(min(t, (long long)(1 << 27)), -(long long)(1 << 27)); // clamp r to [-1, 1]
+                    u32 v = (u32)((1 << 27) - ti);
+                    if (gj == gi) v = 0u;
+                    if (zr || col_na[c0 + c]) v = RID_Q_NA;
+                    if (!row_ok || e_j == 0) v = 0u;
+                    qv[c] = v;
+                }
+                // direct store: 16 consecutive columns of row gi (64-byte aligned: j0 and c0 are multiples of 16)
+                if (row_ok) {
+                    u32 *dst = drow + c0;
+                    if ((size_t)(j0 + c0 + 16) <= P.ld) {
+#pragma unroll
+                        for (int c = 0; c < 16; c += 4)
+                            *reinterpret_cast<uint4 *>(dst + c) = make_uint4(qv[c], qv[c + 1], qv[c + 2], qv[c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if ((size_t)(j0 + c0 + c) < P.ld) dst[c] = qv[c];
+                    }
+                }
+                // mirror store: column gi of rows j0+c0..+15; a warp's 32 lanes write 128 contiguous bytes
+                if (mirror_ok) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        u32 *mp = col_ptr[c0 + c];
+                        if (mp) mp[gi] = qv[c];
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads(); // TMEM drained, tables free
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        L = Ln; tile_m = next_m; tile_n = next_n;
+        ++tcount;
+    }
+    if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
     }
 }
@@ -520,7 +920,14 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     // reads + 45 B/clk of TMA writes against 128 B/clk), and 4-CTA clusters strand SMs (148 is not a multiple of 4 per GPC).
     const char *cl_env = getenv("RID_I8_CLUSTER");
     const int CL = (cl_env && atoi(cl_env) == 2) ? 2 : 1;
-    cuuint32_t boxA[2] = {I8_BK, (cuuint32_t)(I8_BM / CL)}, boxB[2] = {I8_BK, (cuuint32_t)(I8_BN / CL)}, estr[2] = {1, 1};
+    // Default: the persistent single-CTA kernel.  RID_I8_PAIR=1 selects the CTA-pair (cta_group::2) kernel -- correct, but
+    // measured no faster than the single-shot single-CTA kernel at cfg4 (161.6 vs 158.8 ms): operand bandwidth out of
+    // shared memory is not what bounds these kernels, the serialised epilogue is.  RID_I8_PERSIST=0 selects the
+    // single-shot single-CTA kernel.
+    const char *pair_env = getenv("RID_I8_PAIR"), *pers_env = getenv("RID_I8_PERSIST");
+    const bool PAIR = CL == 1 && pair_env && atoi(pair_env) == 1;
+    const bool PERSIST = CL == 1 && !PAIR && !(pers_env && atoi(pers_env) == 0);
+    cuuint32_t boxA[2] = {I8_BK, (cuuint32_t)(I8_BM / CL)}, boxB[2] = {I8_BK, (cuuint32_t)(PAIR ? I8_BN / 2 : I8_BN / CL)}, estr[2] = {1, 1};
     if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
         encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes, gdim, gstr, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -540,7 +947,9 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     for (int r = 0; r < 16; ++r) P.peer[r] = (u32 *)peers[r];
     if (ctx->world == 1) P.peer[0] = dm->D;
     P.tiles_loc = tiles_loc; P.tiles_n = tiles_n;
-    if (cudaFuncSetAttribute(k_gram_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_gram_i8_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gram_i8_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gram_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_gram_i8<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) {
         cudaGetLastError(); cleanup(); return RID_OK;
     }
@@ -552,7 +961,52 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     dim3 grid((unsigned)round_up((size_t)tiles_n, CL), (unsigned)round_up((size_t)std::max(tiles_loc, 1), CL));
     cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_GRAM_I8);
     if (nloc > 0) {
-        if (CL == 2) {
+        if (PERSIST) {
+            // the list of tiles this rank computes, in launch order (cached: it depends on the shape only)
+            const long long key[6] = {N, dm->row0, nloc, ctx->world, ctx->rank, P.per};
+            if (memcmp(key, ctx->i8_tiles_key, sizeof(key)) != 0) {
+                std::vector<int2> list;
+                const long long all = (long long)tiles_n * tiles_loc;
+                list.reserve((size_t)(all / 2 + tiles_n + 16));
+                for (long long L = 0; L < all; ++L) {
+                    int tm, tn;
+                    if (i8_tile_at(P, L, tm, tn)) list.push_back(make_int2(tm, tn));
+                }
+                const size_t bytes = std::max<size_t>(list.size(), 1) * sizeof(int2);
+                if (bytes > ctx->i8_tiles_bytes) {
+                    if (ctx->i8_tiles) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->i8_tiles); ctx->i8_tiles = nullptr; ctx->i8_tiles_bytes = 0; }
+                    if (cudaMalloc(&ctx->i8_tiles, bytes) != cudaSuccess) { cudaGetLastError(); cleanup(); return RID_OK; }
+                    ctx->i8_tiles_bytes = bytes;
+                }
+                // (synchronous copy: `list` is a local)
+                if (cudaMemcpy(ctx->i8_tiles, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
+                    cudaGetLastError(); cleanup(); return RID_OK;
+                }
+                memcpy(ctx->i8_tiles_key, key, sizeof(key));
+                ctx->i8_ntiles = (long long)list.size();
+            }
+            const unsigned nct = (unsigned)std::max<long long>(1, std::min<long long>(ctx->i8_ntiles, (long long)ctx->sm_count));
+            k_gram_i8_persist<<<nct, I8_THREADS, I8_SMEM, ctx->stream>>>(tmA, tmB, P, (const int2 *)ctx->i8_tiles, ctx->i8_ntiles);
+        } else if (PAIR) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(2 * (size_t)((tiles_loc + 1) / 2) * (size_t)tiles_n));
+            cfg.blockDim = dim3(I8_THREADS);
+            cfg.dynamicSmemBytes = I8P_SMEM;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, k_gram_i8_2sm, tmA, tmB, P) != cudaSuccess) {
+                rid_set_error("k_gram_i8_2sm launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                cleanup();
+                return RID_ERR_CUDA;
+            }
+        } else if (CL == 2) {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = grid;

@@ -64,18 +64,27 @@ def test_dist_int8_tcgen05_path_matches_fp64_dmma_path(ctx, oracle, metric, shap
     assert Di[N // 2, 1] <= 4e-7
 
 
-def test_dist_int8_cluster_multicast_variant(ctx, monkeypatch):
-    """RID_I8_CLUSTER=2: 2 x 2 thread-block clusters with TMA multicast of the half panels — bit-identical output."""
+def test_dist_int8_kernel_variants_are_bit_identical(ctx, monkeypatch):
+    """The default is the persistent kernel (tile list, prefetch across tiles, integer epilogue).  The single-shot
+    single-CTA kernel (RID_I8_PERSIST=0, FP64 epilogue), the CTA-pair kernel (RID_I8_PAIR=1: tcgen05.mma.cta_group::2,
+    M = 256, B halves in the two CTAs) and the 2 x 2 cluster / TMA-multicast kernel (RID_I8_CLUSTER=2) must give the
+    same bits: all sums are exact integers and the two epilogues round the same way."""
     x, _ = _features(seed=32, G=700, N=1500, C=5)
+    x[:, 11] = 1.0  # NA row / column
     monkeypatch.setenv("RID_GRAM", "i8")
-    monkeypatch.setenv("RID_I8_CLUSTER", "1")
     a = ctx.dist(x, "pearson")
     Da = a.as_matrix()
     a.free()
-    monkeypatch.setenv("RID_I8_CLUSTER", "2")
-    b = ctx.dist(x, "pearson")
-    assert np.array_equal(Da, b.as_matrix())
-    b.free()
+    for env in ({"RID_I8_PERSIST": "0"}, {"RID_I8_PAIR": "1"}, {"RID_I8_CLUSTER": "2"}):
+        for k2, v in env.items():
+            monkeypatch.setenv(k2, v)
+        b = ctx.dist(x, "logpearson" if False else "pearson")
+        Db = b.as_matrix()
+        b.free()
+        for k2 in env:
+            monkeypatch.delenv(k2)
+        assert np.array_equal(np.isnan(Da), np.isnan(Db)), env
+        assert np.array_equal(Da[~np.isnan(Da)], Db[~np.isnan(Db)]), env
 
 
 def test_dist_zero_variance_cell(ctx, oracle):
