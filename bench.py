@@ -8,8 +8,9 @@ the reference-facing API (raceid3_stemid2_package_b200.compdist / clustexp -> C 
           barrier + synchronize on both sides, max over ranks)
   e2e   : seconds per step starting from a HOST (pinned) feature matrix: H2D copy inside the timed region, partition
           / jaccard / medoids read back to the host
-  roofline : the dominant kernel (the PAM SWAP scan, HBM-bound): algorithmic bytes / CUDA-event duration of its
-          launches inside the timed region, against MEASURED_PEAKS.json's hbm_gbs
+  roofline : the dominant kernel (k_scan, the PAM streaming pass of BUILD and SWAP, HBM-bound): algorithmic bytes /
+          CUDA-event duration of its launches inside the timed region, against MEASURED_PEAKS.json's hbm_gbs;
+          detail.roofline_all holds the same object for the compaction, incremental-SWAP and distance kernels
   cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's R/C path; R itself is not installed
           in this image) on a bounded sample of the same workload, extrapolated ~ N^2
 
@@ -52,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-bootnr", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--timed-kinds", default="gram,gram_i8,scan_swap,scan_build,scan_delta,compact",
+                    help="kernel kinds bracketed with CUDA events inside the timed region")
     return ap.parse_args()
 
 
@@ -300,9 +303,9 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:  # one sampler per job: eight concurrent nvidia-smi pollers slow every rank's driver calls down
         clocks.start()
-    # inside the timed region only the kernels the roofline objects need are bracketed with CUDA events (~100 per step);
-    # the full per-kind breakdown comes from one extra, untimed step below
-    ctx.profile(["gram", "gram_i8", "scan_swap", "compact"])
+    # inside the timed region the kernels of the roofline objects are bracketed with CUDA events (~1800 pairs per step at
+    # the defaults, pre-created); the per-kind breakdown of everything comes from one extra, untimed step below
+    ctx.profile([k for k in a.timed_kinds.split(",") if k])
     l0 = ctx.launches
     barrier()
     ctx.event_record(0)
@@ -359,26 +362,59 @@ def main():
                else "fallback 6650 GB/s (B200_PROFILING.md)")
     step_ms_total = ms_per_step * a.steps
     roofs = []
+    # DRAM bytes per algorithmic byte of the captured launches (ncu --set full; profiles/ncu_traffic_ratios.json)
+    try:
+        ratios = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_ratios.json")))
+    except Exception:
+        ratios = {}
+
+    def traffic_of(kernel, alg_bytes_per_launch):
+        r = ratios.get(kernel, {}).get("dram_per_algorithmic")
+        return alg_bytes_per_launch * r if r else None
+
     sw = prof["scan_swap"]
-    if sw["launches"]:
-        ach = sw["work"] / (sw["ms"] * 1e-3) / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k_scan<MODE=1> (PAM SWAP scan)", "achieved": ach, "peak": hbm_peak,
-                      "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                      "read_only_stream_gbs_measured_here": read_peak, "launches": sw["launches"],
-                      "avg_launch_ms": sw["ms"] / sw["launches"],
-                      "algorithmic_bytes_per_launch": sw["work"] / sw["launches"],
-                      "requested_bytes_per_launch": sw["traffic"] / sw["launches"],
-                      "share_of_step": sw["ms"] / step_ms_total})
+    # k_scan<MODE>: one streaming body, three instantiations (0: BUILD step 0, 1: SWAP / grouped sums, 2: incremental BUILD)
+    sc = {f: sum(prof[k][f] for k in ("scan_swap", "scan_build", "scan_group")) for f in ("launches", "ms", "work", "traffic")}
+    if sc["launches"]:
+        ach = sc["work"] / (sc["ms"] * 1e-3) / 1e9
+        roofs.append({"bound": "hbm", "kernel": "k_scan<MODE> (PAM streaming pass: BUILD steps, SWAP scan, grouped column sums)",
+                      "achieved": ach, "peak": hbm_peak,
+                      "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic_of("k_scan", sc["work"] / sc["launches"]),
+                      "peak_source": hbm_src,
+                      "read_only_stream_gbs_measured_here": read_peak, "launches": sc["launches"],
+                      "avg_launch_ms": sc["ms"] / sc["launches"],
+                      "algorithmic_bytes_per_launch": sc["work"] / sc["launches"],
+                      "requested_bytes_per_launch": sc["traffic"] / sc["launches"],
+                      "by_mode": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"],
+                                      "gbs": prof[k]["work"] / (prof[k]["ms"] * 1e-3) / 1e9 if prof[k]["ms"] else None}
+                                  for k in ("scan_swap", "scan_build", "scan_group")},
+                      "note": "bytes = rows scanned x subset size x 4, every distance read once per pass; the kernel only "
+                              "reads, so the measured copy bandwidth (read + write) understates its ceiling: "
+                              "read_only_stream_gbs_measured_here is the read-only streaming figure of this run; traffic = "
+                              "algorithmic bytes x the DRAM/algorithmic ratio of the ncu capture",
+                      "share_of_step": sc["ms"] / step_ms_total})
+    sd = prof["scan_delta"]
+    if sd["launches"] and sd["ms"] > 0:
+        ach = sd["work"] / (sd["ms"] * 1e-3) / 1e9
+        roofs.append({"bound": "hbm", "kernel": "k_scan_delta (incremental SWAP: rows whose nearest / second medoid changed)",
+                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                      "peak_source": hbm_src, "launches": sd["launches"], "avg_launch_ms": sd["ms"] / sd["launches"],
+                      "algorithmic_bytes_per_launch": sd["work"] / sd["launches"],
+                      "requested_bytes_per_launch": sd["traffic"] / sd["launches"],
+                      "note": "launches enqueued ahead of the local optimum are no-ops and count with ~2 us each",
+                      "share_of_step": sd["ms"] / step_ms_total})
     cp = prof["compact"]
     if cp["launches"]:
         ach = cp["work"] / (cp["ms"] * 1e-3) / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k_compact (D[bsamp,bsamp] copy of a bootstrap replicate, fused with BUILD step 0)",
-                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        roofs.append({"bound": "hbm", "kernel": "k_compact_sym (D[bsamp,bsamp] copy of a bootstrap replicate, fused with BUILD step 0)",
+                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                      "traffic": traffic_of("k_compact_sym", cp["work"] / cp["launches"]),
                       "peak_source": hbm_src, "launches": cp["launches"], "avg_launch_ms": cp["ms"] / cp["launches"],
                       "algorithmic_bytes_per_launch": cp["work"] / cp["launches"],
                       "requested_bytes_per_launch": cp["traffic"] / cp["launches"],
-                      "note": "bytes = rows read (subset rows x N x 4) + compact rows written (subset^2 x 4); ncu: DRAM "
-                              "bytes / requested = 1.03 (profiles/r1_final_ncu_k_compact.txt)",
+                      "note": "one GPU / full replica: algorithmic bytes = upper triangle of D[bsamp,bsamp] gathered once + the "
+                              "square written (1.5 m^2 x 4); requested = the 32-byte sectors those gathers touch (x N/m) + "
+                              "the square.  Row shards use k_compact (whole rows read: rows x (N + m) x 4)",
                       "share_of_step": cp["ms"] / step_ms_total})
     gm = prof["gram"]
     if gm["launches"]:
@@ -398,8 +434,10 @@ def main():
         ach = g8["work"] / (g8["ms"] * 1e-3) / 1e12
         bf16 = float(peaks.get("bf16_tflops", 1590.0))
         i8_peak = 2.0 * bf16  # int8 tcgen05 issues at twice the bf16 rate; the bf16 figure is the measured cuBLAS burst
-        roofs.append({"bound": "tensor", "kernel": "k_gram_i8 (tcgen05.mma kind::i8, exact Ozaki-split distance contraction)",
-                      "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak, "traffic": None,
+        roofs.append({"bound": "tensor", "kernel": "k_gram_i8_persist (tcgen05.mma kind::i8, exact Ozaki-split distance contraction)",
+                      "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak,
+                      "traffic": (ratios.get("k_gram_i8_persist", {}).get("dram_bytes_per_launch_cfg4")
+                                  if (N, G, world) == (100000, 3000, 1) else None),
                       "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (measured cuBLAS bf16 burst; int8 dense is 2x bf16 "
                                      "on sm_100: nominal 4500 TOP/s)" if "bf16_tflops" in peaks else
                                      "2 x fallback 1590 TFLOP/s bf16 (B200_PROFILING.md)",
@@ -442,7 +480,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64 (distance DMMA) + u32/u64 fixed point (PAM)", "data": "synthetic",
+                "vs_baseline": None, "dtype": "s8 x s8 -> s32 tensor cores, exact (distance; f64 DMMA for euclidean) + u32/u64 fixed point (PAM)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "seed": a.seed, "parallelism": f"row-block shard x{world}",
                            "l2": "inputs (distance matrix %.1f GB) larger than L2" % (N * N * 4 / 1e9)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,

@@ -265,7 +265,8 @@ extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
     ctx->prof_on = enable; // bit k set = record kernels of kind k (enable = -1: every kind)
     // create the events up front: cudaEventCreate inside the timed region costs more than the kernels it brackets
     if (enable) {
-        const size_t want = enable == -1 ? 40960 : 2048;
+        const bool many = enable != -1 && (enable & ((1 << RID_PROF_SCAN_BUILD) | (1 << RID_PROF_SCAN_DELTA)));
+        const size_t want = enable == -1 ? 40960 : (many ? 16384 : 2048);
         while (ctx->prof_pool.size() < want) {
             cudaEvent_t e = nullptr;
             if (cudaEventCreateWithFlags(&e, cudaEventDefault) != cudaSuccess) break;

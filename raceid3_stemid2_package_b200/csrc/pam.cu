@@ -113,6 +113,9 @@ struct PamWs {
     int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
+    // profiling: the range of records of the last BUILD whose work is still to be credited (pam_credit_build_passes)
+    size_t bc_start = 0, bc_end = 0;
+    int bc_from = 0, bc_to = 0;
     // the two pooled slabs every device array above is carved from
     char *slab = nullptr, *gslab = nullptr;
     size_t slab_bytes = 0, gslab_bytes = 0;
@@ -1366,7 +1369,27 @@ static int zero_acc(rid_dmat *dm, PamWs *w, int ngroups, int check_done)
 // BUILD: k greedy picks.  Step 0 is one full pass (SP[h] = sum_j D[j][h]); every later step rescans only the rows whose
 // nearest-medoid distance just dropped (about N/(s+1) of them) and corrects SP in place: ~N*H_k row reads instead of
 // N*k, with bit-identical picks because all sums are exact integers.
-static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
+// profiling only: credit the incremental BUILD passes recorded in [bc_start, bc_end) with the rows they really rescanned
+static int pam_credit_build_passes(rid_ctx *ctx, PamWs *w)
+{
+    if (!((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) || w->bc_to <= 0 || w->bc_end <= w->bc_start) return RID_OK;
+    std::vector<int> hist(w->bc_to);
+    RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)w->bc_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    int s = w->bc_from;
+    for (size_t i = w->bc_start; i < w->bc_end && i < ctx->prof.size(); ++i) {
+        if (ctx->prof[i].kind != RID_PROF_SCAN_BUILD) continue;
+        if (s > 0 && s - 1 < w->bc_to) {
+            ctx->prof[i].work = (double)hist[s - 1] * (double)w->m * 4.0;
+            ctx->prof[i].traffic = (double)hist[s - 1] * (double)w->ld * 4.0;
+        }
+        ++s;
+    }
+    w->bc_end = w->bc_start = 0;
+    return RID_OK;
+}
+
+static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to, bool defer_credit = false)
 {
     rid_ctx *ctx = dm->ctx;
     u64 *SP = w->acc + 4, *AQ0 = SP + w->ld;
@@ -1400,21 +1423,9 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
             RID_CUDA(cudaMemcpyAsync(w->chg_hist + s, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         RID_CUDA(cudaGetLastError());
     }
-    if (((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) && k_to > k_from) {
-        // credit the incremental passes with the rows they really rescanned
-        std::vector<int> hist(k_to);
-        RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)k_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        RID_CUDA(cudaStreamSynchronize(ctx->stream));
-        int s = k_from + (step0_fused ? 1 : 0);
-        for (size_t i = prof_start; i < ctx->prof.size(); ++i) {
-            if (ctx->prof[i].kind != RID_PROF_SCAN_BUILD) continue;
-            if (s > 0) {
-                ctx->prof[i].work = (double)hist[s - 1] * (double)w->m * 4.0;
-                ctx->prof[i].traffic = (double)hist[s - 1] * (double)w->ld * 4.0;
-            }
-            ++s;
-        }
-    }
+    w->bc_start = prof_start; w->bc_end = ctx->prof.size();
+    w->bc_from = k_from + (step0_fused ? 1 : 0); w->bc_to = k_to;
+    if (!defer_credit) RID_TRY(pam_credit_build_passes(ctx, w));
     return RID_OK;
 }
 
@@ -1458,7 +1469,9 @@ static int sort_rows_by_group(rid_dmat *dm, PamWs *w, int k, int check_done)
 }
 
 // One incremental SWAP iteration (all kernels are no-ops once state.done is set).
-static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
+// With do_select = false it only moves the accumulators and the assignment to the current medoid set (used by the
+// k-sweep to step from the BUILD medoids of one k to those of the next).
+static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta, bool do_select = true)
 {
     rid_ctx *ctx = dm->ctx;
     const size_t nacc = 4 + (size_t)(1 + k) * w->ld;
@@ -1502,10 +1515,29 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta)
         int blocks = (int)std::min<size_t>((nacc + 255) / 256, (size_t)ctx->sm_count * 8);
         LAUNCH(ctx, k_acc_add, blocks, 256, 0, w->acc, w->acc2, nacc, w->state);
     }
-    auto sel_swap = k_select<false>;
-    LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr);
+    if (do_select) {
+        auto sel_swap = k_select<false>;
+        LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
+               w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr);
+    }
     RID_CUDA(cudaGetLastError());
+    return RID_OK;
+}
+
+// First SWAP iteration up to (not including) the selection: assignment, TD of the BUILD medoids, full scan.  k >= 2.
+static int pam_swap_first_scan(rid_dmat *dm, PamWs *w, int k)
+{
+    rid_ctx *ctx = dm->ctx;
+    RID_TRY(pam_assign(dm, w, k, 0));
+    // objective["build"]: TD of the BUILD medoids
+    if (ctx->world > 1) RID_TRY(rid_allreduce_u64(ctx, w->acc, 4));
+    LAUNCH(ctx, k_capture_td_build, 1, 1, 0, w->state, w->acc);
+    // acc[0] now holds the global TD on every rank; the big all-reduce below would add it world times, so keep only
+    // this rank's share: rank 0 keeps it, the others restart from zero.
+    if (ctx->world > 1 && ctx->rank != 0) RID_CUDA(cudaMemsetAsync(w->acc, 0, sizeof(u64), ctx->stream));
+    RID_TRY(sort_rows_by_group(dm, w, k, 0));
+    RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, 0, RID_PROF_SCAN_SWAP)));
+    RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
     return RID_OK;
 }
 
@@ -1820,6 +1852,50 @@ static void replica_end(FullReplica *R)
     R->active = false;
 }
 
+// State of the BUILD medoids of the last k a rank handled in the sweep: accumulators (hdr | SP | AQ[k]) and assignment.
+struct SweepChain {
+    int chain_k = 0;
+    u64 *acc = nullptr;
+    u32 *capP = nullptr, *capQ = nullptr;
+    int *grp = nullptr;
+};
+
+// SWAP(k) of the sweep starts from the first k BUILD picks.  Their accumulators and assignment are kept from the previous
+// k of this rank and moved to the new medoid set by ONE delta pass over the rows whose (nearest, second nearest) pair
+// changes when the extra medoids are added, instead of a full scan per k.  Medoids must already be installed.
+static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamState *hs)
+{
+    rid_ctx *ctx = dm->ctx;
+    const size_t nl = (size_t)std::max(w->nls, 1);
+    const size_t nacc = 4 + (size_t)(1 + k) * w->ld;
+    int n_delta = 0;
+    const size_t prof_start = ctx->prof.size();
+    if (B.chain_k == 0) {
+        RID_TRY(pam_swap_first_scan(dm, w, k));
+    } else {
+        const size_t nold = 4 + (size_t)(1 + B.chain_k) * w->ld;
+        RID_CUDA(cudaMemcpyAsync(w->capP, B.capP, nl * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->capQ, B.capQ, nl * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->grp, B.grp, nl * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(w->acc, B.acc, nold * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+        // the accumulators of the groups added since chain_k start from zero
+        RID_CUDA(cudaMemsetAsync(w->acc + nold, 0, (nacc - nold) * sizeof(u64), ctx->stream));
+        RID_TRY(pam_swap_delta_iteration(dm, w, k, &n_delta, false));
+        LAUNCH(ctx, k_capture_td_build, 1, 1, 0, w->state, w->acc);
+    }
+    RID_CUDA(cudaMemcpyAsync(B.capP, w->capP, nl * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(B.capQ, w->capQ, nl * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(B.grp, w->grp, nl * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(B.acc, w->acc, nacc * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    B.chain_k = k;
+    auto sel_swap = k_select<false>;
+    LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr);
+    RID_CUDA(cudaGetLastError());
+    RID_TRY(pam_credit_delta_passes(ctx, w, prof_start, n_delta));
+    return pam_swap(dm, w, k, hs, true);
+}
+
 // clusGapExt's k loop.  BUILD is greedy and does not depend on k, so BUILD(k) is the first k picks of
 // BUILD(Kmax): run it once and start SWAP(k) from the k-prefix (identical results, Kmax instead of
 // Kmax(Kmax+1)/2 BUILD passes).
@@ -1854,6 +1930,21 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
         }
         cudaMemsetAsync(d_lab, 0xFF, (size_t)Kmax * lab_pitch, ctx->stream); // 0xFF = column outside the subset
     }
+    // state of the BUILD medoids of the last k this rank handled (see sweep_chain_step)
+    const bool chain = !getenv("RID_SWAP_FULL") && !getenv("RID_SWEEP_FULL");
+    SweepChain B;
+    char *b_buf = nullptr;
+    const size_t b_nl = (size_t)std::max(w->nls, 1);
+    const size_t b_nacc = 4 + (size_t)(1 + Kmax) * w->ld;
+    const size_t b_bytes = std::max<size_t>(((b_nacc * sizeof(u64) + 255) & ~(size_t)255) + 3 * ((b_nl * 4 + 255) & ~(size_t)255),
+                                            (size_t)256 << 10);
+    if (chain && rid_pool_alloc(ctx, (void **)&b_buf, b_bytes) == cudaSuccess) {
+        char *p = b_buf;
+        carve(p, B.acc, b_nacc); carve(p, B.capP, b_nl); carve(p, B.capQ, b_nl); carve(p, B.grp, b_nl);
+    } else {
+        cudaGetLastError();
+        b_buf = nullptr;
+    }
     for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
         logW[k - 1] = 0.0;
         if ((k - 1) % nshare != myshare) continue; // another rank's k
@@ -1865,7 +1956,13 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
             LAUNCH(ctx, k_set_medoids, 1, std::max(32, (k + 31) / 32 * 32), 0, d_order, k, w->med, w->medpos, w->pos_of,
                    w->is_med, w->state);
             PamState hs;
-            rc = pam_swap(dm, w, k, &hs);
+            const bool chain_ok = chain && b_buf && k * k <= K2MAX;
+            if (!chain_ok) {
+                B.chain_k = 0;
+                rc = pam_swap(dm, w, k, &hs);
+            } else {
+                rc = sweep_chain_step(dm, w, k, B, &hs);
+            }
             std::vector<int> slot;
             if (rc == RID_OK) rc = pam_collect_labels(dm, w, slot);
         }
@@ -1917,6 +2014,7 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     cudaFree(d_lab);
     cudaFree(d_S);
     cudaFree(d_order);
+    if (b_buf) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, b_buf, b_bytes); }
     return rc;
 }
 
@@ -2070,6 +2168,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             RID_TRY(tabulate(S, w));
             RID_CUDA(cudaEventSynchronize(S.ev));
         }
+        RID_TRY(pam_credit_build_passes(ctx, w));
         RID_TRY(pam_credit_delta_passes(ctx, w, S.prof_start, S.n_delta));
         jaccard_row(S.h_tab, S.b);
         S.b = -1;
@@ -2098,7 +2197,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             T.b = b; T.m = m; T.n_delta = 0; T.prof_start = ctx->prof.size();
             if ((rc = pam_install_subset(T.dm, w, H, T.pin)) != RID_OK) break;
             if (H.want_compact && !w->compact && depth == 2) depth = 1; // memory is short: stop double-buffering after this one
-            if ((rc = pam_begin(T.dm, w)) != RID_OK || (rc = pam_build(T.dm, w, 0, k)) != RID_OK ||
+            if ((rc = pam_begin(T.dm, w)) != RID_OK || (rc = pam_build(T.dm, w, 0, k, true)) != RID_OK ||
                 (rc = pam_swap_enqueue(T.dm, w, k, ahead, &T.n_delta)) != RID_OK || (rc = tabulate(T, w)) != RID_OK) break;
             if (depth == 1 && &T != &slot[0]) { // drain the second slot and give its buffers back
                 if ((rc = finish(T)) != RID_OK) break;

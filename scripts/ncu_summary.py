@@ -65,5 +65,41 @@ def rep(path, out):
                     f.write(f"{k:90s} {r[i]:>22s} {units[i]}\n")
 
 
+def ratios(path, out):
+    """DRAM bytes per algorithmic byte of the launches captured from scripts/ncu_targets.py (cfg4: N = 100000,
+    bootstrap sample 0 of seed 17000, m cells) -> profiles/ncu_traffic_ratios.json, read by bench.py for `traffic`."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import raceid3_stemid2_package_b200 as rid
+    N = 100000
+    m = len(rid.bootstrap_samples(N, 1, 17000)[0])
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr = rows[0]
+    ik, ir, iw, it = (hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+    res = {"_source": os.path.basename(path), "_workload": f"scripts/ncu_targets.py: N={N}, G=3000, subset m={m}"}
+    alg = {"k_scan": float(m) * m * 4, "k_compact_sym": (0.5 * m * (m + 1) + float(m) * m) * 4}
+    for r in rows[2:]:
+        name = re.sub(r"^void ", "", r[ik])
+        base = re.match(r"[A-Za-z0-9_]+", name).group(0)
+        try:
+            dram = float(r[ir]) * scale[rows[1][ir]] + float(r[iw]) * scale[rows[1][iw]]
+        except (ValueError, KeyError):
+            continue
+        if dram != dram or base in res:
+            continue
+        if base in alg:
+            if base == "k_scan" and abs(dram / alg[base] - 1.0) > 0.2:
+                continue  # an incremental pass (fewer rows): keep the full-size launches only
+            res[base] = {"dram_bytes_per_launch": dram, "algorithmic_bytes_per_launch": alg[base],
+                         "dram_per_algorithmic": dram / alg[base], "kernel": name[:80]}
+        elif base.startswith("k_gram_i8"):
+            res[base] = {"dram_bytes_per_launch_cfg4": dram, "kernel": name[:80]}
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "rep": rep, "ratios": ratios}[sys.argv[1]](sys.argv[2], sys.argv[3])

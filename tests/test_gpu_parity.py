@@ -394,6 +394,12 @@ def test_gap_sweep_batched_equals_single_pass_per_k(ctx, monkeypatch):
     monkeypatch.setenv("RID_WK_SINGLE", "1")
     b, b_sub = dm.gap_sweep(14), dm.gap_sweep(8, subset=sub)
     assert np.array_equal(a, b) and np.array_equal(a_sub, b_sub)
+    # SWAP(k) normally starts from accumulators carried over from the previous k by one delta pass (rows whose nearest /
+    # second-nearest medoid changes when the k-th BUILD pick is added); RID_SWEEP_FULL=1 rescans everything for every k
+    monkeypatch.delenv("RID_WK_SINGLE")
+    monkeypatch.setenv("RID_SWEEP_FULL", "1")
+    c, c_sub = dm.gap_sweep(14), dm.gap_sweep(8, subset=sub)
+    assert np.array_equal(a, c) and np.array_equal(a_sub, c_sub)
     dm.free()
 
 
