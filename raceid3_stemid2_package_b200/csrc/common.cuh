@@ -49,6 +49,10 @@ struct rid_ctx {
     struct ProfRec { int kind; cudaEvent_t a, b; double work; double traffic; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
+    // device-side work counters of the passes whose row count is only known on the device (never read back while a
+    // clustering call is in flight): [0] rows x subset size, [1] rows x pitch of the incremental BUILD passes,
+    // [2], [3] the same for the incremental SWAP passes
+    u64 *prof_dev = nullptr;
     cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // freed large device buffers kept for reuse (a 40 GB cudaMalloc/cudaFree pair per compdist() costs ~0.3 s)
     struct PoolBuf { void *p; size_t bytes; };

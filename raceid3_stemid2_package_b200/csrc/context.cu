@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <time.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -143,6 +145,7 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     rid_pool_trim(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->prof_dev) cudaFree(ctx->prof_dev);
     if (ctx->i8_tiles) cudaFree(ctx->i8_tiles);
     if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -181,6 +184,20 @@ int rid_time_end(rid_ctx *ctx)
 }
 
 // ---- device buffer reuse pool ---------------------------------------------------------------------------
+// RID_TRACE=1: every pool miss / eviction (a real cudaMalloc / cudaFree) is reported on stderr with its duration
+static bool rid_tracing()
+{
+    static int on = -1;
+    if (on < 0) on = getenv("RID_TRACE") ? 1 : 0;
+    return on == 1;
+}
+static double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
 {
     for (size_t i = 0; i < ctx->pool.size(); ++i)
@@ -189,21 +206,29 @@ cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
             ctx->pool.erase(ctx->pool.begin() + i);
             return cudaSuccess;
         }
+    const double t0 = rid_tracing() ? now_ms() : 0.0;
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess && !ctx->pool.empty()) {
         cudaGetLastError();
         rid_pool_trim(ctx); // give cached buffers back and retry
         e = cudaMalloc(p, bytes);
     }
+    if (rid_tracing()) fprintf(stderr, "[rid] pool miss: cudaMalloc %.1f MB took %.2f ms (%zu cached)\n", bytes / 1e6, now_ms() - t0, ctx->pool.size());
     return e;
 }
 
 void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
 {
     if (!p) return;
-    if (bytes < ((size_t)256 << 10)) { cudaFree(p); return; }
+    const double t0 = rid_tracing() ? now_ms() : 0.0;
+    if (bytes < ((size_t)256 << 10)) {
+        cudaFree(p);
+        if (rid_tracing()) fprintf(stderr, "[rid] small cudaFree %.3f MB took %.2f ms\n", bytes / 1e6, now_ms() - t0);
+        return;
+    }
     if (ctx->pool.size() >= 16) { // full: drop the buffer that has waited longest, the steady-state sizes stay cached
         cudaFree(ctx->pool.front().p);
+        if (rid_tracing()) fprintf(stderr, "[rid] pool full: cudaFree %.1f MB took %.2f ms\n", ctx->pool.front().bytes / 1e6, now_ms() - t0);
         ctx->pool.erase(ctx->pool.begin());
     }
     ctx->pool.push_back({p, bytes});
@@ -262,6 +287,8 @@ extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
     ctx->prof.clear();
+    if (enable && !ctx->prof_dev) RID_CUDA(cudaMalloc(&ctx->prof_dev, 4 * sizeof(u64)));
+    if (ctx->prof_dev) RID_CUDA(cudaMemsetAsync(ctx->prof_dev, 0, 4 * sizeof(u64), ctx->stream));
     ctx->prof_on = enable; // bit k set = record kernels of kind k (enable = -1: every kind)
     // create the events up front: cudaEventCreate inside the timed region costs more than the kernels it brackets
     if (enable) {
@@ -296,6 +323,14 @@ extern "C" int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, 
             RID_CUDA(cudaEventElapsedTime(&msf, r.a, r.b));
             ++n; t += msf; w += r.work; tr += r.traffic;
         }
+    if (ctx->prof_dev && (kind == RID_PROF_SCAN_BUILD || kind == RID_PROF_SCAN_DELTA)) {
+        // passes sized on the device: their work was counted there (cells -> bytes)
+        u64 h[4];
+        RID_CUDA(cudaMemcpy(h, ctx->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        const int o = kind == RID_PROF_SCAN_BUILD ? 0 : 2;
+        w += 4.0 * (double)h[o];
+        tr += 4.0 * (double)h[o + 1];
+    }
     if (launches) *launches = n;
     if (ms) *ms = t;
     if (work) *work = w;

@@ -26,7 +26,6 @@
 
 // ----------------------------------------------------------------------------------------------------------
 #define K2MAX 4096   // incremental SWAP keys rows by (old group, new group): k*k <= K2MAX, i.e. k <= 64
-#define CNT_HIST 4096
 
 struct PamState {
     u64 td;       // total deviation at the last SWAP decision (fixed point)
@@ -108,14 +107,9 @@ struct PamWs {
     u32 *d_po = nullptr, *d_qo = nullptr, *d_pn = nullptr, *d_qn = nullptr;
     int *hist2 = nullptr; // [3 * K2MAX]: counts, bases, cursors of the pair keys
     u64 *acc2 = nullptr;
-    int *cnt_hist = nullptr; // [CNT_HIST] changed-row counts of the delta passes (profiling)
     int *chg_count = nullptr; // rows whose cap changed in the last BUILD step
-    int *chg_hist = nullptr;  // [kcap] that count per BUILD step (profiling only)
     // host mirrors for the current subset
     int m = 0, nls = 0;
-    // profiling: the range of records of the last BUILD whose work is still to be credited (pam_credit_build_passes)
-    size_t bc_start = 0, bc_end = 0;
-    int bc_from = 0, bc_to = 0;
     // the two pooled slabs every device array above is carved from
     char *slab = nullptr, *gslab = nullptr;
     size_t slab_bytes = 0, gslab_bytes = 0;
@@ -142,7 +136,7 @@ static size_t ws_carve_base(PamWs *w, char *base)
     carve(p, w->state, 1); carve(p, w->chg_count, 1);
     carve(p, w->o_capP, nl); carve(p, w->o_capQ, nl); carve(p, w->o_grp, nl); carve(p, w->d_row, nl); carve(p, w->d_key, nl);
     carve(p, w->d_po, nl); carve(p, w->d_qo, nl); carve(p, w->d_pn, nl); carve(p, w->d_qn, nl);
-    carve(p, w->hist2, (size_t)3 * K2MAX); carve(p, w->cnt_hist, (size_t)CNT_HIST);
+    carve(p, w->hist2, (size_t)3 * K2MAX);
     carve(p, w->subset_cells, N); carve(p, w->colmap, N); carve(p, w->src_rows, nl);
     return (size_t)(p - base);
 }
@@ -152,7 +146,7 @@ static size_t ws_carve_groups(PamWs *w, char *base, int kc, size_t ld)
     char *p = base;
     const size_t k = (size_t)kc, nacc = 4 + (k + 1) * ld;
     carve(p, w->med, k); carve(p, w->medpos, k); carve(p, w->hist, 3 * k); carve(p, w->grp_sum, k); carve(p, w->grp_cnt, k);
-    carve(p, w->grp_min, k); carve(p, w->grp_arg, k); carve(p, w->chg_hist, k);
+    carve(p, w->grp_min, k); carve(p, w->grp_arg, k);
     carve(p, w->acc, nacc); carve(p, w->acc2, nacc);
     return (size_t)(p - base);
 }
@@ -161,7 +155,7 @@ static void ws_free_groups(PamWs *w, rid_ctx *ctx)
 {
     rid_pool_free(ctx, w->gslab, w->gslab_bytes);
     w->gslab = nullptr; w->gslab_bytes = 0;
-    w->chg_hist = nullptr; w->acc2 = nullptr;
+    w->acc2 = nullptr;
     w->med = w->medpos = w->hist = w->grp_cnt = w->grp_arg = nullptr;
     w->grp_sum = w->grp_min = w->acc = nullptr;
 }
@@ -395,7 +389,7 @@ __global__ void k_diff_count(const u32 *__restrict__ nP, const u32 *__restrict__
     if (t < nls && (nP[t] != oP[t] || nQ[t] != oQ[t] || nG[t] != oG[t])) atomicAdd(&hist2[oG[t] * k + nG[t]], 1);
 }
 
-__global__ void k_prefix2(int *hist2, int k2, int *total, const PamState *st)
+__global__ void k_prefix2(int *hist2, int k2, int *total, const PamState *st, u64 *prof_dev, int m, size_t ld)
 {
     if (st->done) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -406,6 +400,10 @@ __global__ void k_prefix2(int *hist2, int k2, int *total, const PamState *st)
             run += hist2[c];
         }
         *total = run;
+        if (prof_dev) { // rows the delta pass is about to rescan
+            atomicAdd((unsigned long long *)prof_dev + 2, (unsigned long long)run * (unsigned long long)m);
+            atomicAdd((unsigned long long *)prof_dev + 3, (unsigned long long)run * (unsigned long long)ld);
+        }
     }
 }
 
@@ -659,7 +657,7 @@ template <bool BUILD>
 __global__ void __launch_bounds__(256)
 k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
          u64 *acc, size_t ld, int k, int *med, int *medpos, unsigned char *is_med,
-         Cand *blockbest, PamState *st, int check_done, u64 *sp_sub, int *zero_cnt)
+         Cand *blockbest, PamState *st, int check_done, u64 *sp_sub, int *zero_cnt, u64 *prof_dev)
 {
     // sp_sub (incremental BUILD): SP[h] -= sp_sub[h] and sp_sub[h] = 0 on the way (every subset column is visited once);
     // zero_cnt: a counter the next kernel fills again
@@ -717,7 +715,13 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
     c = cand_reduce_block<BUILD>(c, sh);
     if (threadIdx.x == 0) {
         st->ticket = 0u;
-        if (zero_cnt) *zero_cnt = 0;
+        if (zero_cnt) {
+            if (prof_dev && sp_sub) { // rows the incremental pass of this step rescanned
+                atomicAdd((unsigned long long *)prof_dev, (unsigned long long)*zero_cnt * (unsigned long long)m);
+                atomicAdd((unsigned long long *)prof_dev + 1, (unsigned long long)*zero_cnt * (unsigned long long)ld);
+            }
+            *zero_cnt = 0;
+        }
         u64 td = acc[0];
         if (BUILD) {
             int h = subset[c.p];
@@ -1351,7 +1355,9 @@ static int launch_scan(rid_dmat *dm, PamWs *w, const int *rows, const u32 *capP,
     else
         LAUNCH(ctx, scan2, grid, SCAN_THREADS, 0, w->mat, w->ld, rows, capP, capQ, grp, nrows_ub, nrows_dev,
                rpc, SP, AQ, w->state, check_done);
-    rid_prof_end(ctx, pe, prof_kind, (double)nrows_ub * (double)w->m * 4.0, (double)nrows_ub * (double)w->ld * 4.0);
+    // a pass sized on the device (nrows_dev) is credited through ctx->prof_dev (k_select / k_prefix2)
+    rid_prof_end(ctx, pe, prof_kind, nrows_dev ? 0.0 : (double)nrows_ub * (double)w->m * 4.0,
+                 nrows_dev ? 0.0 : (double)nrows_ub * (double)w->ld * 4.0);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -1369,40 +1375,16 @@ static int zero_acc(rid_dmat *dm, PamWs *w, int ngroups, int check_done)
 // BUILD: k greedy picks.  Step 0 is one full pass (SP[h] = sum_j D[j][h]); every later step rescans only the rows whose
 // nearest-medoid distance just dropped (about N/(s+1) of them) and corrects SP in place: ~N*H_k row reads instead of
 // N*k, with bit-identical picks because all sums are exact integers.
-// profiling only: credit the incremental BUILD passes recorded in [bc_start, bc_end) with the rows they really rescanned
-static int pam_credit_build_passes(rid_ctx *ctx, PamWs *w)
-{
-    if (!((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) || w->bc_to <= 0 || w->bc_end <= w->bc_start) return RID_OK;
-    std::vector<int> hist(w->bc_to);
-    RID_CUDA(cudaMemcpyAsync(hist.data(), w->chg_hist, (size_t)w->bc_to * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    RID_CUDA(cudaStreamSynchronize(ctx->stream));
-    int s = w->bc_from;
-    for (size_t i = w->bc_start; i < w->bc_end && i < ctx->prof.size(); ++i) {
-        if (ctx->prof[i].kind != RID_PROF_SCAN_BUILD) continue;
-        if (s > 0 && s - 1 < w->bc_to) {
-            ctx->prof[i].work = (double)hist[s - 1] * (double)w->m * 4.0;
-            ctx->prof[i].traffic = (double)hist[s - 1] * (double)w->ld * 4.0;
-        }
-        ++s;
-    }
-    w->bc_end = w->bc_start = 0;
-    return RID_OK;
-}
-
-static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to, bool defer_credit = false)
+static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
 {
     rid_ctx *ctx = dm->ctx;
     u64 *SP = w->acc + 4, *AQ0 = SP + w->ld;
     auto sel_build = k_select<true>;
-    const size_t prof_start = ctx->prof.size();
-    bool step0_fused = false;
     for (int s = k_from; s < k_to; ++s) {
         if (s == 0) {
             if (!w->sp0_ready) {
                 RID_TRY(zero_acc(dm, w, 0, 0));
                 RID_TRY((launch_scan<0>(dm, w, w->rows, w->capP, nullptr, nullptr, w->nls, nullptr, 0, RID_PROF_SCAN_BUILD)));
-            } else {
-                step0_fused = true;
             }
             w->sp0_ready = false;
             RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + w->ld));
@@ -1415,17 +1397,13 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to, bool defer_cr
         }
         // picks the next medoid; for s > 0 it first applies SP -= AQ0 (and clears AQ0 and the changed-row counter)
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
-               w->is_med, w->blockbest, w->state, 0, s > 0 ? AQ0 : (u64 *)nullptr, w->chg_count);
+               w->is_med, w->blockbest, w->state, 0, s > 0 ? AQ0 : (u64 *)nullptr, w->chg_count,
+               ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr);
         if (w->nls)
             LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, w->mat, w->ld, w->rows, w->nls, w->capP,
                    w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
-        if ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1)
-            RID_CUDA(cudaMemcpyAsync(w->chg_hist + s, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         RID_CUDA(cudaGetLastError());
     }
-    w->bc_start = prof_start; w->bc_end = ctx->prof.size();
-    w->bc_from = k_from + (step0_fused ? 1 : 0); w->bc_to = k_to;
-    if (!defer_credit) RID_TRY(pam_credit_build_passes(ctx, w));
     return RID_OK;
 }
 
@@ -1486,7 +1464,8 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
     if (w->nls) {
         LAUNCH(ctx, k_diff_count, nblk(w->nls, 256), 256, 0, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ, w->o_grp,
                w->nls, k, w->hist2, w->state);
-        LAUNCH(ctx, k_prefix2, 1, 32, 0, w->hist2, k * k, w->chg_count, w->state);
+        LAUNCH(ctx, k_prefix2, 1, 32, 0, w->hist2, k * k, w->chg_count, w->state,
+               ((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) ? ctx->prof_dev : (u64 *)nullptr, w->m, w->ld);
         LAUNCH(ctx, k_diff_scatter, nblk(w->nls, 256), 256, 0, w->rows, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ,
                w->o_grp, w->nls, k, w->hist2, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn, w->state);
         int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
@@ -1506,8 +1485,6 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
             LAUNCH(ctx, d2, grid, SCAN_THREADS, 0, w->mat, w->ld, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn,
                    w->chg_count, rpc, k, SP2, AQ2, w->state);
         rid_prof_end(ctx, pe, RID_PROF_SCAN_DELTA, 0.0, 0.0);
-        if (((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) && *n_delta < CNT_HIST)
-            RID_CUDA(cudaMemcpyAsync(w->cnt_hist + *n_delta, w->chg_count, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
         if ((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) ++*n_delta;
     }
     RID_TRY(rid_allreduce_u64(ctx, w->acc2, nacc));
@@ -1518,7 +1495,7 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
     if (do_select) {
         auto sel_swap = k_select<false>;
         LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-               w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr);
+               w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
     }
     RID_CUDA(cudaGetLastError());
     return RID_OK;
@@ -1556,26 +1533,9 @@ static int pam_swap_enqueue(rid_dmat *dm, PamWs *w, int k, int ahead, int *n_del
     RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, 0, RID_PROF_SCAN_SWAP)));
     auto sel_swap = k_select<false>;
     LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr);
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
     RID_CUDA(cudaGetLastError());
     for (int i = 0; i < ahead; ++i) RID_TRY(pam_swap_delta_iteration(dm, w, k, n_delta));
-    return RID_OK;
-}
-
-static int pam_credit_delta_passes(rid_ctx *ctx, PamWs *w, size_t prof_start, int n_delta)
-{
-    if (!((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) || n_delta <= 0) return RID_OK;
-    // credit the delta passes with the rows they really rescanned
-    int cnt = std::min(n_delta, CNT_HIST);
-    std::vector<int> hist(cnt);
-    RID_CUDA(cudaMemcpy(hist.data(), w->cnt_hist, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
-    int j = 0;
-    for (size_t i = prof_start; i < ctx->prof.size() && j < cnt; ++i)
-        if (ctx->prof[i].kind == RID_PROF_SCAN_DELTA) {
-            ctx->prof[i].work = (double)hist[j] * (double)w->m * 4.0;
-            ctx->prof[i].traffic = (double)hist[j] * (double)w->ld * 4.0;
-            ++j;
-        }
     return RID_OK;
 }
 
@@ -1589,7 +1549,6 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resum
     const bool incremental = k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL");
     if (incremental) batch = std::max(batch, 2);
     int n_delta = 0;
-    const size_t prof_start = ctx->prof.size();
     for (;;) {
         for (int b = 0; b < batch; ++b) {
             if (incremental && !first) { RID_TRY(pam_swap_delta_iteration(dm, w, k, &n_delta)); continue; }
@@ -1613,7 +1572,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resum
                 RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
                 auto sel_swap = k_select<false>;
                 LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
-                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk, (u64 *)nullptr, (int *)nullptr);
+                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
                 RID_CUDA(cudaGetLastError());
             }
             // every later iteration only rescans the rows whose (nearest, second nearest) pair changed
@@ -1627,7 +1586,6 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resum
         }
         if (h_state->done) break;
     }
-    RID_TRY(pam_credit_delta_passes(ctx, w, prof_start, n_delta));
     return RID_OK;
 }
 
@@ -1869,7 +1827,6 @@ static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamSta
     const size_t nl = (size_t)std::max(w->nls, 1);
     const size_t nacc = 4 + (size_t)(1 + k) * w->ld;
     int n_delta = 0;
-    const size_t prof_start = ctx->prof.size();
     if (B.chain_k == 0) {
         RID_TRY(pam_swap_first_scan(dm, w, k));
     } else {
@@ -1890,9 +1847,8 @@ static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamSta
     B.chain_k = k;
     auto sel_swap = k_select<false>;
     LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr);
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
     RID_CUDA(cudaGetLastError());
-    RID_TRY(pam_credit_delta_passes(ctx, w, prof_start, n_delta));
     return pam_swap(dm, w, k, hs, true);
 }
 
@@ -2112,123 +2068,83 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             bootresult[(size_t)b * k + j] = best;
         }
     };
-    // Replicates are independent.  With the whole matrix on this GPU they run as a two-deep pipeline: a replicate is
-    // enqueued from start to finish (tables from page-locked memory, compaction, BUILD, the first SWAP scan plus a few
-    // incremental iterations that turn into no-ops at the optimum, labels, contingency table, result copies) without
-    // one host round trip, in its own workspace, while the host already prepares and enqueues the next one; results
-    // are picked up two replicates later.  A host hiccup shorter than a replicate no longer idles the GPU.
+    // Replicates are independent and all of a replicate's decisions are taken on the device, so with the whole matrix
+    // on this GPU the host only ENQUEUES: tables from page-locked memory, compaction, BUILD, the first SWAP scan plus a
+    // few incremental iterations that turn into no-ops at the optimum, labels, contingency table, result copies into the
+    // replicate's own page-locked slot -- no host round trip until the end of a wave of replicates.  The launch queue
+    // keeps the GPU several replicates ahead of the host, so host hiccups (a descheduled thread, a slow driver call) no
+    // longer idle it; stream order alone makes one device workspace enough.
     const int ahead = getenv("RID_BOOT_AHEAD") ? std::max(0, atoi(getenv("RID_BOOT_AHEAD"))) : 6;
     bool pipelined = rc == RID_OK && work->ctx->world == 1 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") &&
                      !getenv("RID_BOOT_SYNC") && !mine.empty();
-    struct Slot {
-        rid_dmat view;
-        rid_dmat *dm = nullptr;
-        cudaEvent_t ev = nullptr;
-        int *pin = nullptr, *h_tab = nullptr, *d_tab = nullptr;
-        PamState *h_state = nullptr;
-        int b = -1, m = 0, n_delta = 0;
-        size_t prof_start = 0;
-    } slot[2];
-    int depth = 2;
     // slot layout (ints): subset tables [8 N] | PamState [64, 8-byte aligned] | contingency table [k k]
     const size_t tab_off = (((size_t)8 * N + 1) & ~(size_t)1) + 64;
     const size_t slot_ints = (tab_off + (size_t)k * k + 1) & ~(size_t)1;
+    size_t wave = 1;
+    int *pin = nullptr, *d_tabs = nullptr;
     if (pipelined) {
-        int *pin = (int *)rid_pinned(ctx, 2 * slot_ints * sizeof(int));
-        int *dt = nullptr;
-        if (!pin || cudaMalloc(&dt, 2 * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
-        for (int s2 = 0; s2 < 2 && pipelined; ++s2) {
-            Slot &S = slot[s2];
-            S.pin = pin + s2 * slot_ints;
-            S.h_tab = S.pin + tab_off;
-            S.h_state = (PamState *)(S.pin + tab_off - 64);
-            S.d_tab = dt + (size_t)s2 * k * k;
-            if (cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
-            if (s2 == 0) S.dm = work;
-            else { S.view = *work; S.view.ws = nullptr; S.dm = &S.view; }
-        }
-        if (!pipelined && dt) cudaFree(dt);
+        const size_t budget = (size_t)768 << 20; // page-locked bytes per wave
+        wave = std::max<size_t>(2, std::min<size_t>(mine.size(), budget / (slot_ints * sizeof(int))));
+        pin = (int *)rid_pinned(ctx, wave * slot_ints * sizeof(int));
+        if (!pin || cudaMalloc(&d_tabs, wave * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
     }
-    auto tabulate = [&](Slot &S, PamWs *w) { // device labels by position -> contingency table -> page-locked slot
-        cudaMemsetAsync(w->lab_pos, 0, (size_t)w->m * sizeof(int), ctx->stream);
-        if (w->nls) LAUNCH(ctx, k_labels_to_pos, nblk(w->nls, 256), 256, 0, w->rows_pos, w->grp, w->nls, w->lab_pos);
-        cudaMemsetAsync(S.d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
-        LAUNCH(ctx, k_contingency, nblk(S.m, 256), 256, 0, w->subset_cells, w->lab_pos, S.m, d_part, k, S.d_tab);
-        cudaMemcpyAsync(S.h_state, w->state, sizeof(PamState), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(S.h_tab, S.d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-        return cudaEventRecord(S.ev, ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess ? RID_OK : RID_ERR_CUDA;
+    auto run_sync = [&](int b, HostSubset *H) -> int { // one replicate, start to finish, results on the host
+        const int m = sample_len[b];
+        blab.resize(m);
+        RID_TRY(pam_run(work, ptr[b], m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr, H));
+        PamWs *w = work->ws;
+        // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
+        RID_CUDA(cudaMemsetAsync(d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset_cells, w->lab_pos, m, d_part, k, d_tab);
+        RID_CUDA(cudaMemcpyAsync(tab.data(), d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
+        jaccard_row(tab.data(), b);
+        return RID_OK;
     };
-    auto finish = [&](Slot &S) -> int { // wait for the slot's replicate and turn its table into Jaccard similarities
-        if (S.b < 0) return RID_OK;
-        PamWs *w = S.dm->ws;
-        if (cudaEventSynchronize(S.ev) != cudaSuccess) { rid_set_error("rid_clusterboot: %s", cudaGetErrorString(cudaGetLastError())); return RID_ERR_CUDA; }
-        if (!S.h_state->done) { // more swaps than were enqueued ahead: finish this replicate the synchronous way
-            PamState hs;
-            RID_TRY(pam_swap(S.dm, w, k, &hs, true));
-            RID_TRY(tabulate(S, w));
-            RID_CUDA(cudaEventSynchronize(S.ev));
-        }
-        RID_TRY(pam_credit_build_passes(ctx, w));
-        RID_TRY(pam_credit_delta_passes(ctx, w, S.prof_start, S.n_delta));
-        jaccard_row(S.h_tab, S.b);
-        S.b = -1;
+    auto enqueue = [&](int b, HostSubset &H, int *slot, int *dt) -> int { // nothing here waits for the GPU
+        const int m = sample_len[b];
+        if (k >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); return RID_ERR_ARG; }
+        RID_TRY(pam_check_na(work, ptr[b], m));
+        PamWs *w = nullptr;
+        RID_TRY(ws_get(work, k, &w));
+        int n_delta = 0;
+        RID_TRY(pam_install_subset(work, w, H, slot));
+        RID_TRY(pam_begin(work, w));
+        RID_TRY(pam_build(work, w, 0, k));
+        RID_TRY(pam_swap_enqueue(work, w, k, ahead, &n_delta));
+        RID_CUDA(cudaMemsetAsync(w->lab_pos, 0, (size_t)w->m * sizeof(int), ctx->stream));
+        if (w->nls) LAUNCH(ctx, k_labels_to_pos, nblk(w->nls, 256), 256, 0, w->rows_pos, w->grp, w->nls, w->lab_pos);
+        RID_CUDA(cudaMemsetAsync(dt, 0, (size_t)k * k * sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset_cells, w->lab_pos, m, d_part, k, dt);
+        RID_CUDA(cudaMemcpyAsync(slot + tab_off - 64, w->state, sizeof(PamState), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(slot + tab_off, dt, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaGetLastError());
         return RID_OK;
     };
     if (!mine.empty() && rc == RID_OK) launch_prep(0);
-    for (size_t i = 0; i < mine.size() && rc == RID_OK; ++i) {
-        const int b = mine[i], m = sample_len[b];
-        const int *sp = ptr[b];
-        fut.get();
-        if (i + 1 < mine.size()) launch_prep(i + 1);
-        if (pipelined) {
-            Slot &S = slot[depth == 2 ? (i & 1) : 0];
-            if ((rc = finish(S)) != RID_OK) break; // the replicate that used this slot two rounds ago
-            HostSubset &H = prep[i & 1];
-            if (k >= m) { rid_set_error("Number of clusters 'k' must be in {1,2, .., n-1}"); rc = RID_ERR_ARG; break; }
-            if ((rc = pam_check_na(work, sp, m)) != RID_OK) break;
-            PamWs *w = nullptr;
-            if ((rc = ws_get(S.dm, k, &w)) != RID_OK) {
-                if (S.dm == work) break;
-                depth = 1; rc = RID_OK; // no room for a second workspace: one replicate at a time
-                Slot &S0 = slot[0];
-                if ((rc = finish(S0)) != RID_OK || (rc = ws_get(S0.dm, k, &w)) != RID_OK) break;
-            }
-            Slot &T = depth == 2 ? S : slot[0];
-            T.b = b; T.m = m; T.n_delta = 0; T.prof_start = ctx->prof.size();
-            if ((rc = pam_install_subset(T.dm, w, H, T.pin)) != RID_OK) break;
-            if (H.want_compact && !w->compact && depth == 2) depth = 1; // memory is short: stop double-buffering after this one
-            if ((rc = pam_begin(T.dm, w)) != RID_OK || (rc = pam_build(T.dm, w, 0, k, true)) != RID_OK ||
-                (rc = pam_swap_enqueue(T.dm, w, k, ahead, &T.n_delta)) != RID_OK || (rc = tabulate(T, w)) != RID_OK) break;
-            if (depth == 1 && &T != &slot[0]) { // drain the second slot and give its buffers back
-                if ((rc = finish(T)) != RID_OK) break;
-                rid_pam_ws_free(T.view.ws, ctx); T.view.ws = nullptr;
-            }
-            continue;
+    for (size_t i0 = 0; i0 < mine.size() && rc == RID_OK; i0 += wave) {
+        const size_t i1 = std::min(mine.size(), i0 + wave);
+        for (size_t i = i0; i < i1 && rc == RID_OK; ++i) {
+            fut.get();
+            if (i + 1 < mine.size()) launch_prep(i + 1);
+            if (pipelined) rc = enqueue(mine[i], prep[i & 1], pin + (i - i0) * slot_ints, d_tabs + (i - i0) * (size_t)k * k);
+            else rc = run_sync(mine[i], &prep[i & 1]);
         }
-        blab.resize(m);
-        rc = pam_run(work, sp, m, k, bmed.data(), blab.data(), nullptr, nullptr, nullptr, &prep[i & 1]);
-        if (rc != RID_OK) break;
-        PamWs *w = work->ws;
-        // Jaccard needs cluster NUMBERS only up to a permutation (max over k'), so the slot ids in lab_pos do.
-        cudaMemsetAsync(d_tab, 0, (size_t)k * k * sizeof(int), ctx->stream);
-        LAUNCH(ctx, k_contingency, nblk(m, 256), 256, 0, w->subset_cells, w->lab_pos, m, d_part, k, d_tab);
-        if (cudaMemcpyAsync(tab.data(), d_tab, (size_t)k * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-            rid_set_error("rid_clusterboot: contingency table copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (!pipelined || rc != RID_OK) continue;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rid_set_error("rid_clusterboot: %s", cudaGetErrorString(cudaGetLastError()));
             rc = RID_ERR_CUDA;
             break;
         }
-        jaccard_row(tab.data(), b);
-    }
-    if (pipelined) {
-        for (int s2 = 0; s2 < 2; ++s2) {
-            if (rc == RID_OK) rc = finish(slot[s2]);
-            if (slot[s2].ev) cudaEventDestroy(slot[s2].ev);
+        if (fut.valid()) fut.wait(); // run_sync below prepares its own tables in work->ws->hs; keep the helper thread out
+        for (size_t i = i0; i < i1 && rc == RID_OK; ++i) {
+            const int *slot = pin + (i - i0) * slot_ints;
+            const PamState *st = (const PamState *)(slot + tab_off - 64);
+            if (st->done) jaccard_row(slot + tab_off, mine[i]);
+            else rc = run_sync(mine[i], nullptr); // more swaps than were enqueued ahead (rare): redo this one the plain way
         }
-        cudaStreamSynchronize(ctx->stream);
-        if (slot[1].view.ws) { rid_pam_ws_free(slot[1].view.ws, ctx); slot[1].view.ws = nullptr; }
-        cudaFree(slot[0].d_tab);
     }
+    if (d_tabs) cudaFree(d_tabs);
     if (fut.valid()) fut.wait();
     cudaFree(d_part);
     cudaFree(d_tab);
