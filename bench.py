@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--clustnr", type=int, default=30)
     ap.add_argument("--bootnr", type=int, default=50)
     ap.add_argument("--seed", type=int, default=1004)
-    ap.add_argument("--cpu-cells", type=int, default=1200, help="cells in the CPU sample")
+    ap.add_argument("--cpu-cells", type=int, default=0,
+                    help="cells in the CPU sample (0: 2500 for the 1-thread leg, ~10 s; 6000 for the all-threads reference arm)")
     ap.add_argument("--cpu-bootnr", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -76,7 +77,7 @@ def cpu_sample(a, omp: bool):
 
     L = orc.lib(omp)
     cores = L.orc_num_threads()
-    ns = min(a.cpu_cells, a.cells)
+    ns = min(a.cpu_cells or (6000 if omp else 2500), a.cells)
     x, _ = synth_features_numpy(ns, a.genes, a.cln, a.seed)
     xt = np.ascontiguousarray(x.T)
     t0 = time.perf_counter()
