@@ -120,6 +120,12 @@ int rid_refresh(rid_dmat *dm, const int *medoid_idx, int k, int *labels);
  * contiguous, 0-based, ties to the lower index like order()); dist (nullable): the matching distances. */
 int rid_knn(rid_dmat *dm, int K, int *idx, double *dist);
 
+/* ---- cluster::silhouette(part, dist) as plotsilhouette calls it (R/RaceID.R:1283-1284; "next" row of SURVEY §8f) --- */
+/* labels[N]: positive cluster numbers, 0 = cell not in the partition.  neighbor[N]: the other cluster with the smallest
+ * mean distance (first one in sorted cluster-id order on ties; 0 for unlabelled cells); width[N]: (b - a) / max(a, b),
+ * 0 for singleton clusters, NaN for unlabelled cells.  Needs 2 <= #clusters <= #cells - 1. */
+int rid_silhouette(rid_dmat *dm, const int *labels, int N, int *neighbor, double *width);
+
 /* ---- W.k (R/RaceID_utils.R:39-53) for a given partition; used by tests and by callers of clusGapExt ---- */
 int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W);
 

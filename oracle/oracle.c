@@ -588,6 +588,50 @@ int orc_medoids(const double *dmat, int n, const int *labels, int *medoid_idx, i
     return nc;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * cluster::silhouette(x = part, dist), as plotsilhouette calls it (RaceID.R:1283-1284).
+ * upstream: cluster/R/silhouette.R silhouette.default() -> src/sildist.c: for cell i in cluster A,
+ * a(i) = mean distance to the other members of A, b(i) = min over clusters C != A of the mean
+ * distance to C (first minimum in increasing cluster number), neighbor = that C,
+ * s(i) = (b - a) / max(a, b); a cell alone in its cluster gets s = 0.
+ * labels: positive ints (0 = cell not in the partition -> neighbor 0, width NaN).
+ * Returns the number of clusters, or -1 if the 2 <= k <= n-1 precondition fails.
+ * ------------------------------------------------------------------------------------------- */
+int orc_silhouette(const double *dmat, int n, const int *labels, int *neighbor, double *width)
+{
+    size_t ld = (size_t)n;
+    int maxl = 0, m = 0, k = 0;
+    for (int i = 0; i < n; ++i) { if (labels[i] > maxl) maxl = labels[i]; m += labels[i] > 0; }
+    int *cnt = (int *)calloc((size_t)maxl + 1, sizeof(int));
+    double *sum = (double *)malloc(((size_t)maxl + 1) * sizeof(double));
+    for (int i = 0; i < n; ++i) if (labels[i] > 0) cnt[labels[i]]++;
+    for (int c = 1; c <= maxl; ++c) k += cnt[c] > 0;
+    if (k < 2 || k > m - 1) { free(cnt); free(sum); return -1; }
+    for (int i = 0; i < n; ++i) {
+        neighbor[i] = 0;
+        width[i] = NAN;
+        if (labels[i] <= 0) continue;
+        for (int c = 1; c <= maxl; ++c) sum[c] = 0.;
+        for (int j = 0; j < n; ++j)
+            if (labels[j] > 0 && j != i) sum[labels[j]] += dmat[(size_t)i * ld + j];
+        const int A = labels[i];
+        double b = INFINITY;
+        int nb = 0;
+        for (int c = 1; c <= maxl; ++c)
+            if (c != A && cnt[c] > 0) {
+                double v = sum[c] / cnt[c];
+                if (v < b) { b = v; nb = c; } /* first minimum */
+            }
+        neighbor[i] = nb;
+        if (cnt[A] == 1) { width[i] = 0.; continue; }
+        double a = sum[A] / (cnt[A] - 1);
+        double mx = a > b ? a : b;
+        width[i] = mx > 0. ? (b - a) / mx : 0.;
+    }
+    free(cnt); free(sum);
+    return k;
+}
+
 /* final partition refresh (RaceID.R:1049-1054): every cell -> nearest medoid column, first minimum
  * (order(x)[1] is stable), then compact empty cluster numbers. labels_out 1-based. */
 void orc_refresh(const double *dmat, int n, const int *medoid_idx, int k, int *labels_out)

@@ -46,6 +46,8 @@ def lib(omp: bool = False) -> C.CDLL:
         L.orc_medoids.argtypes = [_dp, C.c_int, _ip, _ip, _ip]
         L.orc_refresh.restype = None
         L.orc_refresh.argtypes = [_dp, C.c_int, _ip, C.c_int, _ip]
+        L.orc_silhouette.argtypes = [_dp, C.c_int, _ip, _ip, _dp]
+        L.orc_silhouette.restype = C.c_int
         L.orc_swap_deltas_colform.restype = None
         L.orc_swap_deltas_colform.argtypes = [_dp, C.c_int, C.c_void_p, C.c_int, _ip, C.c_int, _dp]
         _LIBS[omp] = L
@@ -147,6 +149,18 @@ def medoids(D, labels):
     ids = np.zeros(n, dtype=np.int32)
     nc = lib().orc_medoids(Dc, n, lab, out, ids)
     return out[:nc].copy(), ids[:nc].copy()
+
+
+def silhouette(D, labels):
+    """cluster::silhouette(part, dist): (neighbor, sil_width) per cell; labels 0 = not in the partition."""
+    Dc = _colmajor(D)
+    n = Dc.shape[0]
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    nb = np.zeros(n, dtype=np.int32)
+    sw = np.zeros(n)
+    if lib().orc_silhouette(Dc, n, lab, nb, sw) < 0:
+        raise ValueError("silhouette needs 2 <= number of clusters <= n - 1")
+    return nb, sw
 
 
 def refresh(D, medoid_idx):

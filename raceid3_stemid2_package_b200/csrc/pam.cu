@@ -835,6 +835,35 @@ __global__ void k_silhouette(const int *__restrict__ subset, const int *__restri
     }
 }
 
+// cluster::silhouette(part, dist) per cell: a = mean distance to the other members of the own cluster, b = smallest mean
+// distance to another cluster (the FIRST such cluster in sorted cluster-id order on ties, like which.min), neighbour = that
+// cluster, s = (b - a) / max(a, b); singleton clusters get s = 0.  Sums are exact integers; the ratios are FP64.
+__global__ void k_silhouette_full(const int *__restrict__ subset, const int *__restrict__ lab_pos, int m, int k,
+                                  const u64 *__restrict__ AQ, size_t ld, const int *__restrict__ grp_cnt, double *sil,
+                                  int *neighbor)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        const int h = subset[p], cj = lab_pos[p];
+        const int nj = grp_cnt[cj];
+        double b = INFINITY;
+        int nb = -1;
+        for (int c = 0; c < k; ++c)
+            if (c != cj && grp_cnt[c] > 0) {
+                double v = (double)AQ[(size_t)c * ld + h] / (double)grp_cnt[c];
+                if (v < b) { b = v; nb = c; }
+            }
+        double sw = 0.0;
+        if (nj > 1) {
+            const double a = (double)AQ[(size_t)cj * ld + h] / (double)(nj - 1);
+            const double mx = a > b ? a : b;
+            sw = mx > 0.0 ? (b - a) / mx : 0.0;
+        }
+        sil[p] = sw;
+        neighbor[p] = nb;
+    }
+}
+
 // ---- W.k for several partitions in ONE pass (the sweep) ---------------------------------------------------------------
 // S_q[h] = sum over rows j in h's cluster (under partition q) of D[j][h], for WB partitions at once: the matrix is read
 // once for WB values of k instead of once per k.  Labels are bytes; a thread keeps the labels of its 4 columns for the
@@ -2203,6 +2232,62 @@ extern "C" int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_i
     for (int c = 0; c < k; ++c) {
         medoid_idx[c] = sub[arg[c]];
         if (cluster_ids) cluster_ids[c] = ids[c];
+    }
+    return RID_OK;
+}
+
+// cluster::silhouette(x = part, dist) as plotsilhouette calls it (reference R/RaceID.R:1283-1284): per cell the neighbour
+// cluster and the silhouette width.  labels[N]: positive cluster numbers, 0 = cell not in the partition (gets NaN / 0).
+extern "C" int rid_silhouette(rid_dmat *dm, const int *labels, int N, int *neighbor, double *width)
+{
+    if (!dm || !labels || !neighbor || !width || N != dm->N) { rid_set_error("rid_silhouette: bad arguments"); return RID_ERR_ARG; }
+    rid_ctx *ctx = dm->ctx;
+    std::vector<int> ids;
+    for (int i = 0; i < N; ++i) if (labels[i] > 0) ids.push_back(labels[i]);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    const int k = (int)ids.size();
+    std::vector<int> sub, g;
+    for (int i = 0; i < N; ++i)
+        if (labels[i] > 0) {
+            sub.push_back(i);
+            g.push_back((int)(std::lower_bound(ids.begin(), ids.end(), labels[i]) - ids.begin()));
+        }
+    const int m = (int)sub.size();
+    if (k < 2 || k > m - 1) { // silhouette.default: "need 2 <= k <= n-1"
+        rid_set_error("silhouette needs 2 <= number of clusters <= n - 1 (got %d clusters for %d cells)", k, m);
+        return RID_ERR_ARG;
+    }
+    RID_TRY(pam_check_na(dm, sub.data(), m));
+    PamWs *w;
+    RID_TRY(ws_get(dm, k, &w));
+    RID_TRY(pam_set_subset(dm, w, sub.data(), m, false));
+    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    int *d_nb = nullptr;
+    RID_CUDA(cudaMalloc(&d_nb, (size_t)m * sizeof(int)));
+    int rc = rid_time_begin(ctx);
+    if (rc == RID_OK) rc = grouped_colsums(dm, w, k);
+    std::vector<int> h_nb(m);
+    std::vector<double> h_sw(m);
+    if (rc == RID_OK) {
+        cudaMemsetAsync(w->grp_sum, 0, (size_t)k * sizeof(u64), ctx->stream);
+        cudaMemsetAsync(w->grp_cnt, 0, (size_t)k * sizeof(int), ctx->stream);
+        LAUNCH(ctx, k_wdisp, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, w->acc + 4 + w->ld, w->ld, w->grp_sum, w->grp_cnt);
+        LAUNCH(ctx, k_silhouette_full, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, k, w->acc + 4 + w->ld, w->ld, w->grp_cnt,
+               w->sil, d_nb);
+        if (cudaMemcpyAsync(h_nb.data(), d_nb, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(h_sw.data(), w->sil, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+            rid_set_error("rid_silhouette: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = RID_ERR_CUDA;
+        }
+    }
+    if (rc == RID_OK) rc = rid_time_end(ctx);
+    cudaFree(d_nb);
+    if (rc != RID_OK) return rc;
+    for (int i = 0; i < N; ++i) { neighbor[i] = 0; width[i] = NAN; }
+    for (int p = 0; p < m; ++p) {
+        neighbor[sub[p]] = h_nb[p] >= 0 ? ids[h_nb[p]] : 0;
+        width[sub[p]] = h_sw[p];
     }
     return RID_OK;
 }

@@ -20,7 +20,7 @@ SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dist_csc", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
     "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
-    "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn",
+    "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn", "rid_silhouette",
 ]
 
 
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     L.rid_medoids.argtypes = [vp, ip, C.c_int, ip, ip, ip]
     L.rid_refresh.argtypes = [vp, ip, C.c_int, ip]
     L.rid_within_disp.argtypes = [vp, ip, C.c_int, ip, C.c_int, dp]
+    L.rid_silhouette.argtypes = [vp, ip, C.c_int, ip, dp]
     L.rid_knn.argtypes = [vp, C.c_int, ip, dp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what include/raceid_b200.h declares
@@ -315,6 +316,16 @@ class DistMatrix:
         dist = np.zeros((self.N, K)) if with_dist else None
         _check(load().rid_knn(self._h, K, _p(idx), _p(dist)))
         return (idx, dist) if with_dist else idx
+
+    def silhouette(self, labels):
+        """cluster::silhouette(part, dist) (R/RaceID.R:1283-1284): neighbour cluster and silhouette width per cell."""
+        lab = _i32(labels)
+        if len(lab) != self.N:
+            raise ValueError("labels must have one entry per cell")
+        nb = np.zeros(self.N, dtype=np.int32)
+        sw = np.zeros(self.N)
+        _check(load().rid_silhouette(self._h, _p(lab), self.N, _p(nb), _p(sw)))
+        return nb, sw
 
     def within_disp(self, labels, k: int, subset=None) -> float:
         s = _i32(subset)

@@ -135,3 +135,17 @@ SEXP rid_dist_csc_call(SEXP ctx, IntegerVector i, IntegerVector p, NumericVector
     if (nzero) Rcpp::warning("the standard deviation is zero");
     return DmatPtr(dm, true);
 }
+
+// silhouette(kpart, as.dist(object@distances)) of plotsilhouette (R/RaceID.R:1283-1284): an n x 3 matrix with the
+// columns cluster::silhouette returns (cluster, neighbor, sil_width)
+// [[Rcpp::export]]
+NumericMatrix rid_silhouette_call(SEXP dm, IntegerVector part) {
+    const int N = part.size();
+    IntegerVector nb(N);
+    NumericVector sw(N);
+    rid_check(rid_silhouette(DmatPtr(dm), part.begin(), N, nb.begin(), sw.begin()));
+    NumericMatrix out(N, 3);
+    for (int i = 0; i < N; ++i) { out(i, 0) = part[i]; out(i, 1) = nb[i]; out(i, 2) = sw[i]; }
+    colnames(out) = CharacterVector::create("cluster", "neighbor", "sil_width");
+    return out;
+}

@@ -364,6 +364,21 @@ def compmedoids(object: SCseq, part) -> list:
     return [names[i] for i in idx]
 
 
+def silhouette(object: SCseq, final: bool = False) -> np.ndarray:
+    """The data behind plotsilhouette (R/RaceID.R:1270-1285): `silhouette(kpart, as.dist(object@distances))`, an n x 3
+    matrix with columns cluster, neighbor, sil_width (cells in `ndata` order).  final=TRUE uses `cpart`."""
+    if object.distances is None:
+        raise ValueError("run compdist before plotsilhouette")
+    part = object.cpart if final else (object.cluster or {}).get("kpart")
+    if part is None or len(part) == 0:
+        raise ValueError("run findoutliers before plotsilhouette" if final else "run clustexp before plotsilhouette")
+    part = np.asarray(part, dtype=np.int32)
+    if part.max() < 2:
+        raise ValueError("only a single cluster: no silhouette plot")
+    nb, sw = _as_dmat(object.distances).silhouette(part)
+    return np.column_stack([part.astype(np.float64), nb.astype(np.float64), sw])
+
+
 def refresh_partition(object: SCseq, cpart):
     """The final-cluster block of findoutliers (R/RaceID.R:1034-1060): per-cluster medoid by mean within-cluster
     distance, every cell to its nearest medoid (first minimum), empty clusters compacted, medoids recomputed."""

@@ -366,6 +366,34 @@ def test_dist_from_csc_equals_dense_getfdata_path(ctx):
         b.free()
 
 
+def test_silhouette_matches_oracle(ctx, oracle):
+    """rid_silhouette = cluster::silhouette(part, dist) of plotsilhouette (R/RaceID.R:1283-1284): neighbours identical,
+    widths to 1e-12 (exact integer sums on the device, FP64 ratios), arbitrary cluster numbers, unlabelled cells,
+    singleton clusters, exact ties (duplicated cells), both fixed-point grids."""
+    for metric, G, N in (("pearson", 150, 700), ("euclidean", 40, 500)):
+        x, truth = _features(seed=44, G=G, N=N, C=5)
+        x[:, 9] = x[:, 2]
+        dm = ctx.dist(x, metric)
+        Dg = dm.as_matrix()
+        lab = (np.asarray(truth) % 5 * 3 + 2).astype(np.int32)  # cluster numbers 2, 5, 8, 11, 14
+        lab[5] = 40    # singleton
+        lab[6] = 0     # not in the partition
+        nb, sw = dm.silhouette(lab)
+        nbo, swo = oracle.silhouette(Dg, lab)
+        assert np.array_equal(nb, nbo)
+        assert np.isnan(sw[6]) and nb[6] == 0 and sw[5] == 0.0
+        ok = ~np.isnan(swo)
+        assert np.max(np.abs(sw[ok] - swo[ok])) < 1e-12
+        r = dm.pam(4, want_sil=True)
+        _, swp = dm.silhouette(r["clustering"])
+        assert abs(float(np.mean(swp)) - r["avg_sil"]) < 1e-12  # pam's silinfo$avg.width is the mean of the same widths
+        import raceid3_stemid2_package_b200 as rid
+
+        with pytest.raises(rid.RaceIDError):
+            dm.silhouette(np.ones(N, dtype=np.int32))
+        dm.free()
+
+
 def test_knn_matches_stable_order(ctx):
     """rid_knn == apply(D, 1, function(x) head(order(x), K)) (R/RaceID.R:774): stable order, ties to the lower index."""
     x, _ = _features(seed=12, G=80, N=700, C=4)
@@ -501,6 +529,10 @@ def test_api_compdist_clustexp_end_to_end(ctx, oracle):
     med = rid.compmedoids(sc, sc.cluster["kpart"])
     medo, _ = oracle.medoids(Dg, cb["partition"])
     assert med == [sc.cell_names[i] for i in medo]
+    si = rid.silhouette(sc)  # the matrix behind plotsilhouette: cluster, neighbor, sil_width
+    nbo, swo = oracle.silhouette(Dg, cb["partition"])
+    assert si.shape == (N, 3) and np.array_equal(si[:, 0], cb["partition"]) and np.array_equal(si[:, 1], nbo)
+    assert np.max(np.abs(si[:, 2] - swo)) < 1e-12
     sc2 = rid.clustexp(sc, sat=False, cln=7, bootnr=1, verbose=False)
     assert int(sc2.cluster["kpart"].max()) == 7
     with pytest.raises(ValueError):

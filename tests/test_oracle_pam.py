@@ -225,3 +225,37 @@ def test_golden_pam_and_boot(oracle, name):
     lw = oracle.gap_sweep(D, len(g["logW"]))
     assert np.array_equal(lw, g["logW"])
     assert oracle.saturation(lw) == int(g["cln_sat"])
+
+
+def test_silhouette_matches_sklearn_and_tie_rules(oracle):
+    """orc_silhouette restates cluster::silhouette(part, dist) (plotsilhouette, reference R/RaceID.R:1283-1284).  The
+    widths are pinned by scikit-learn's independent implementation; the neighbour rule (first minimum in increasing
+    cluster number) and the singleton rule (s = 0) by construction."""
+    from sklearn.metrics import silhouette_samples
+
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.normal(c, 0.7, (40, 3)) for c in ((0, 0, 0), (4, 0, 0), (0, 5, 0), (3, 3, 3))])
+    D = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1))
+    lab = np.repeat([2, 5, 7, 9], 40).astype(np.int32)  # arbitrary positive cluster numbers
+    lab[[3, 50, 90]] = [5, 9, 2]                          # a few misassigned cells -> negative widths
+    nb, sw = oracle.silhouette(D, lab)
+    assert np.allclose(sw, silhouette_samples(D, lab, metric="precomputed"), atol=1e-12)
+    means = np.stack([D[:, lab == c].mean(1) for c in (2, 5, 7, 9)], 1)
+    for i in range(len(lab)):
+        other = [c for c in (2, 5, 7, 9) if c != lab[i]]
+        assert nb[i] == other[int(np.argmin([means[i, (2, 5, 7, 9).index(c)] for c in other]))]
+    # singleton cluster -> width 0; unlabelled cell -> NaN / neighbour 0 and it is ignored by everybody else
+    lab2 = lab.copy()
+    lab2[0] = 11
+    lab2[1] = 0
+    nb2, sw2 = oracle.silhouette(D, lab2)
+    assert sw2[0] == 0.0 and nb2[0] in (2, 5, 7, 9) and np.isnan(sw2[1]) and nb2[1] == 0
+    keep = lab2 > 0
+    ref = silhouette_samples(D[np.ix_(keep, keep)], lab2[keep], metric="precomputed")
+    assert np.allclose(sw2[keep], ref, atol=1e-12)
+    # exact tie between two neighbour clusters: the lower cluster number wins
+    Dt = np.array([[0, 1, 2, 2], [1, 0, 2, 2], [2, 2, 0, 9], [2, 2, 9, 0]], dtype=np.float64)
+    nbt, _ = oracle.silhouette(Dt, np.array([1, 1, 3, 2], dtype=np.int32))
+    assert nbt[0] == 2 and nbt[1] == 2
+    with pytest.raises(ValueError):
+        oracle.silhouette(D, np.ones(len(lab), dtype=np.int32))
