@@ -126,6 +126,14 @@ int rid_knn(rid_dmat *dm, int K, int *idx, double *dist);
  * 0 for singleton clusters, NaN for unlabelled cells.  Needs 2 <= #clusters <= #cells - 1. */
 int rid_silhouette(rid_dmat *dm, const int *labels, int N, int *neighbor, double *width);
 
+/* ---- stats::cmdscale(d, k): classical MDS, the t-SNE start configuration of comptsne (R/RaceID.R:1093; "next" row of
+ * SURVEY §8f).  points: N x k column-major = E_k diag(sqrt(lambda_k)) of B = -1/2 J D^2 J for the k algebraically largest
+ * eigenvalues; eig[k]: those eigenvalues (a non-positive one gives a NaN column, cmdscale warns and drops it).  The sign
+ * of every axis is fixed so that its largest-magnitude coordinate is positive (LAPACK's is arbitrary).  tol: relative
+ * residual |B v - lambda v| / |lambda| of the k pairs (<= 0: 1e-9); max_iter (<= 0: 1000); iters (nullable): used.
+ * k <= 4 on this path (block of 8 vectors); NA in the matrix is an error like in cmdscale. */
+int rid_cmdscale(rid_dmat *dm, int k, double tol, int max_iter, double *points, double *eig, int *iters);
+
 /* ---- W.k (R/RaceID_utils.R:39-53) for a given partition; used by tests and by callers of clusGapExt ---- */
 int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W);
 

@@ -151,6 +151,20 @@ def medoids(D, labels):
     return out[:nc].copy(), ids[:nc].copy()
 
 
+def cmdscale(D, k: int = 2):
+    """stats::cmdscale(d, k) restated with numpy (upstream: R src/library/stats/R/cmdscale.R + C_DoubleCentre): x = D^2,
+    double centring, e = eigen(-x/2, symmetric = TRUE), points = e$vectors[, 1:k] * sqrt(e$values[1:k]).  Returns
+    (points n x k, eigenvalues k).  Eigenvector signs are LAPACK's: compare up to a sign per axis."""
+    D = np.asarray(D, dtype=np.float64)
+    x = D * D
+    x = x - x.mean(axis=0, keepdims=True)
+    x = x - x.mean(axis=1, keepdims=True)
+    w, v = np.linalg.eigh(-x / 2.0)
+    idx = np.argsort(-w)[:k]
+    ev = w[idx]
+    return v[:, idx] * np.sqrt(np.where(ev > 0, ev, np.nan)), ev
+
+
 def silhouette(D, labels):
     """cluster::silhouette(part, dist): (neighbor, sil_width) per cell; labels 0 = not in the partition."""
     Dc = _colmajor(D)

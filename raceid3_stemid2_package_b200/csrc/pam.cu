@@ -1302,11 +1302,8 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
                 const bool sym = w->nls == m && dm->row0 == 0 && dm->row1 == N && !getenv("RID_COMPACT_FULL");
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 if (sym) {
-                    static bool attr_set = false;
-                    if (!attr_set) {
-                        RID_CUDA(cudaFuncSetAttribute(k_compact_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
-                        attr_set = true;
-                    }
+                    // (per device and cheap: set on every call rather than once per process)
+                    RID_CUDA(cudaFuncSetAttribute(k_compact_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
                     const unsigned nb = (unsigned)((m + CS_S - 1) / CS_S);
                     LAUNCH(ctx, k_compact_sym, dim3(nb, nb), CS_THREADS, CS_SMEM, dm->D, dm->ld, w->colmap, w->cbuf, ldc, m,
                            w->acc + 4);

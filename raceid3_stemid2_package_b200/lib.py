@@ -20,7 +20,7 @@ SYMBOLS = [
     "rid_last_error", "rid_version", "rid_nccl_unique_id", "rid_ctx_create", "rid_ctx_destroy", "rid_ctx_sync",
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dist_csc", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
     "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
-    "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn", "rid_silhouette",
+    "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn", "rid_silhouette", "rid_cmdscale",
 ]
 
 
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.rid_refresh.argtypes = [vp, ip, C.c_int, ip]
     L.rid_within_disp.argtypes = [vp, ip, C.c_int, ip, C.c_int, dp]
     L.rid_silhouette.argtypes = [vp, ip, C.c_int, ip, dp]
+    L.rid_cmdscale.argtypes = [vp, C.c_int, C.c_double, C.c_int, dp, dp, ip]
     L.rid_knn.argtypes = [vp, C.c_int, ip, dp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what include/raceid_b200.h declares
@@ -316,6 +317,15 @@ class DistMatrix:
         dist = np.zeros((self.N, K)) if with_dist else None
         _check(load().rid_knn(self._h, K, _p(idx), _p(dist)))
         return (idx, dist) if with_dist else idx
+
+    def cmdscale(self, k: int = 2, tol: float = 1e-9, max_iter: int = 1000, with_eig: bool = False):
+        """stats::cmdscale(d, k) (R/RaceID.R:1093): N x k coordinates (axis signs: largest coordinate positive)."""
+        pts = np.zeros((k, self.N))  # column-major N x k
+        ev = np.zeros(k)
+        it = np.zeros(1, dtype=np.int32)
+        _check(load().rid_cmdscale(self._h, k, float(tol), int(max_iter), _p(pts), _p(ev), _p(it)))
+        out = np.ascontiguousarray(pts.T)
+        return (out, ev, int(it[0])) if with_eig else out
 
     def silhouette(self, labels):
         """cluster::silhouette(part, dist) (R/RaceID.R:1283-1284): neighbour cluster and silhouette width per cell."""

@@ -149,3 +149,15 @@ NumericMatrix rid_silhouette_call(SEXP dm, IntegerVector part) {
     colnames(out) = CharacterVector::create("cluster", "neighbor", "sil_width");
     return out;
 }
+
+// cmdscale(di, k = 2) of comptsne (R/RaceID.R:1093): the t-SNE start configuration, an n x k matrix
+// [[Rcpp::export]]
+NumericMatrix rid_cmdscale_call(SEXP dm, int k) {
+    int N = 0; rid_check(rid_dmat_info(DmatPtr(dm), &N, nullptr, nullptr, nullptr, nullptr));
+    NumericMatrix pts(N, k);                         // column-major, like cmdscale's result
+    NumericVector ev(k);
+    rid_check(rid_cmdscale(DmatPtr(dm), k, 1e-9, 1000, pts.begin(), ev.begin(), nullptr));
+    int pos = 0; for (int t = 0; t < k; ++t) pos += ev[t] > 0;
+    if (pos < k) Rcpp::warning("only %d of the first %d eigenvalues are > 0", pos, k);
+    return pts;
+}

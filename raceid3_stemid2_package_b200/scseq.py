@@ -379,6 +379,14 @@ def silhouette(object: SCseq, final: bool = False) -> np.ndarray:
     return np.column_stack([part.astype(np.float64), nb.astype(np.float64), sw])
 
 
+def tsne_initial_config(object: SCseq, k: int = 2) -> np.ndarray:
+    """`cmdscale(as.dist(object@distances), k = 2)`, the `initial_config` comptsne hands to Rtsne when
+    `initial_cmd = TRUE` (R/RaceID.R:1086-1093).  Rtsne itself is outside this package's scope."""
+    if object.distances is None:
+        raise ValueError("run compdist before comptsne (the dimRed arm of comptsne does not use a distance matrix)")
+    return _as_dmat(object.distances).cmdscale(k)
+
+
 def refresh_partition(object: SCseq, cpart):
     """The final-cluster block of findoutliers (R/RaceID.R:1034-1060): per-cluster medoid by mean within-cluster
     distance, every cell to its nearest medoid (first minimum), empty clusters compacted, medoids recomputed."""

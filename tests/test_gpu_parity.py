@@ -394,6 +394,32 @@ def test_silhouette_matches_oracle(ctx, oracle):
         dm.free()
 
 
+@pytest.mark.parametrize("metric,G,N,C", [("pearson", 200, 900, 5), ("euclidean", 30, 500, 4), ("spearman", 120, 700, 12)])
+def test_cmdscale_matches_dense_eigensolver(ctx, oracle, metric, G, N, C):
+    """rid_cmdscale = stats::cmdscale(d, k = 2) of comptsne (R/RaceID.R:1093): block subspace iteration on the implicit
+    B = -1/2 J D^2 J against the dense eigensolver on the exported matrix.  Tolerance: eigenvalues 1e-8 relative,
+    coordinates 1e-6 of the axis scale, up to the sign of an axis (LAPACK's is arbitrary; ours: largest coordinate > 0)."""
+    x, _ = _features(seed=52, G=G, N=N, C=C)
+    dm = ctx.dist(x, metric)
+    Dg = dm.as_matrix()
+    pts, ev, iters = dm.cmdscale(2, with_eig=True)
+    Po, evo = oracle.cmdscale(Dg, 2)
+    assert pts.shape == (N, 2) and 1 <= iters <= 1000
+    assert np.max(np.abs(ev - evo) / evo) < 1e-8
+    for a in range(2):
+        scale = np.sqrt(evo[a])
+        err = min(np.max(np.abs(pts[:, a] - Po[:, a])), np.max(np.abs(pts[:, a] + Po[:, a])))
+        assert err < 1e-6 * scale, (a, err, scale, iters)
+        assert pts[np.argmax(np.abs(pts[:, a])), a] > 0
+    p3, _, _ = dm.cmdscale(3, with_eig=True)
+    assert np.max(np.abs(np.abs(p3[:, :2]) - np.abs(pts))) < 1e-6 * np.sqrt(evo[0])
+    import raceid3_stemid2_package_b200 as rid
+
+    with pytest.raises(rid.RaceIDError):
+        dm.cmdscale(7)
+    dm.free()
+
+
 def test_knn_matches_stable_order(ctx):
     """rid_knn == apply(D, 1, function(x) head(order(x), K)) (R/RaceID.R:774): stable order, ties to the lower index."""
     x, _ = _features(seed=12, G=80, N=700, C=4)
@@ -533,6 +559,9 @@ def test_api_compdist_clustexp_end_to_end(ctx, oracle):
     nbo, swo = oracle.silhouette(Dg, cb["partition"])
     assert si.shape == (N, 3) and np.array_equal(si[:, 0], cb["partition"]) and np.array_equal(si[:, 1], nbo)
     assert np.max(np.abs(si[:, 2] - swo)) < 1e-12
+    ic = rid.tsne_initial_config(sc)  # cmdscale(di, k = 2), comptsne's start configuration
+    Po, evo = oracle.cmdscale(Dg, 2)
+    assert ic.shape == (N, 2) and np.max(np.abs(np.abs(ic) - np.abs(Po))) < 1e-6 * np.sqrt(evo[0])
     sc2 = rid.clustexp(sc, sat=False, cln=7, bootnr=1, verbose=False)
     assert int(sc2.cluster["kpart"].max()) == 7
     with pytest.raises(ValueError):

@@ -80,3 +80,23 @@ def test_golden_distances(oracle, name):
     ref = 1.0 - np.corrcoef(x.T)
     np.fill_diagonal(ref, 0.0)
     assert np.max(np.abs(g["D_pearson"] - ref)) < 1e-12
+
+
+def test_cmdscale_recovers_euclidean_configurations(oracle):
+    """oracle.cmdscale restates stats::cmdscale (reference R/RaceID.R:1093).  Classical MDS of Euclidean distances
+    recovers the configuration up to a rigid motion: with k = d the pairwise distances of the returned points equal
+    the input, and the eigenvalues are those of the centred Gram matrix."""
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(60, 3)) * np.array([5.0, 2.0, 0.5])
+    D = np.sqrt(((X[:, None, :] - X[None, :, :]) ** 2).sum(-1))
+    P, ev = oracle.cmdscale(D, 3)
+    D2 = np.sqrt(((P[:, None, :] - P[None, :, :]) ** 2).sum(-1))
+    assert np.max(np.abs(D2 - D)) < 1e-10
+    Xc = X - X.mean(0)
+    assert np.allclose(ev, np.sort(np.linalg.eigvalsh(Xc @ Xc.T))[::-1][:3], rtol=1e-10)
+    assert np.allclose(P.mean(0), 0.0, atol=1e-12)  # double centring: coordinates are centred
+    # a non-Euclidean "distance" (1 - correlation) still gives the k largest eigenvalues, in decreasing order
+    Z = rng.normal(size=(40, 25))
+    Dc = 1.0 - np.corrcoef(Z)
+    _, ev2 = oracle.cmdscale(Dc, 2)
+    assert ev2[0] >= ev2[1] > 0
