@@ -771,13 +771,6 @@ __global__ void k_build_update(const u32 *__restrict__ D, size_t ld, const int *
     }
 }
 
-// SP[h] -= delta[h]   (delta = AQ group 0 of the incremental BUILD pass, already all-reduced)
-__global__ void k_sp_sub(u64 *SP, const u64 *__restrict__ delta, size_t n)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) SP[i] -= delta[i];
-}
-
 __global__ void k_capture_td_build(PamState *st, const u64 *acc) { st->td_build = acc[0]; }
 
 __global__ void k_labels_to_pos(const int *__restrict__ rows_pos, const int *__restrict__ grp, int nls, int *lab_pos)
