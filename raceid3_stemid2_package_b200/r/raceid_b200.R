@@ -69,3 +69,28 @@ compmedoids <- function(object, part) {
   full <- integer(length(d@names)); full[match(names(part), d@names)] <- as.integer(part)
   d@names[rid_compmedoids(d@ptr, full)]
 }
+
+## plotsilhouette (R/RaceID.R:1270-1285): the silhouette object is built from rid_silhouette()'s n x 3 matrix instead
+## of cluster::silhouette(kpart, as.dist(object@distances)) on an n x n host matrix; plot.silhouette() is unchanged.
+plotsilhouette <- function(object, final = FALSE) {
+  if (length(object@cluster$kpart) == 0) stop("run clustexp before plotsilhouette")
+  if (length(unique(object@cluster$kpart)) < 2) stop("only a single cluster: no silhouette plot")
+  kpart <- if (final) object@cpart else object@cluster$kpart
+  if (is(object@distances, "RidDist")) {
+    si <- rid_silhouette_call(object@distances@ptr, as.integer(kpart))
+    rownames(si) <- names(kpart)
+    attr(si, "Ordered") <- FALSE
+    attr(si, "call") <- quote(silhouette(x = kpart, dist = distances))
+    class(si) <- "silhouette"
+  } else {
+    si <- cluster::silhouette(kpart, as.dist(object@distances))
+  }
+  plot(si)
+}
+
+## comptsne (R/RaceID.R:1086-1098): only the start configuration changes; Rtsne still receives a dist object, which
+## as.dist.RidDist materialises on demand (Rtsne's own O(n^2) input is outside this library's scope).
+rid_tsne_initial_config <- function(object, k = 2L) {
+  if (is(object@distances, "RidDist")) rid_cmdscale_call(object@distances@ptr, as.integer(k))
+  else stats::cmdscale(as.dist(object@distances), k = k)
+}
