@@ -10,12 +10,15 @@
 // two lowest diagonals (s+t <= 1) are below 2^-54 * 257 * G * 64^2 and are covered by an a-posteriori bound computed
 // from the actual digit norms (the host falls back to the FP64 DMMA kernel if the bound exceeds 8e-7).
 //
-// Kernel shape: one 128 x 96 output tile per CTA (5 accumulators x 96 columns = 480 of the 512 TMEM columns),
-// K blocks of 128 bytes, two 112 KB shared-memory stages filled by TMA (SWIZZLE_128B, K-major), one elected thread
-// issuing 13 x 4 tcgen05.mma per stage, tcgen05.commit -> mbarrier to recycle stages and to hand the accumulators to
-// the four epilogue warps, which read TMEM with tcgen05.ld, rebuild the 64-bit integer dot product, turn it into the
-// fixed-point distance and store the tile and its mirror image (D is symmetric; only tiles touching the upper
-// triangle are computed).
+// Kernel shape: 128 x 96 output tiles (5 accumulators x 96 columns = 480 of the 512 TMEM columns), K blocks of 128
+// bytes, two 112 KB shared-memory stages filled by TMA (SWIZZLE_128B, K-major), one elected thread issuing the
+// tcgen05.mma stream (7 instructions per K = 32 step: products (s,t),(s,t+1) share one N = 192 instruction),
+// tcgen05.commit -> mbarrier to recycle stages and to hand the accumulators to the epilogue warps, which read TMEM with
+// tcgen05.ld, rebuild the 64-bit integer dot product, turn it into the fixed-point distance and store the tile and its
+// mirror image (D is symmetric; only tiles touching the upper triangle are computed).
+// Kernels in this file: k_gram_i8_persist (the default: persistent CTAs over a tile list, prefetch across tiles, integer
+// epilogue), k_gram_i8<1> (one tile per CTA, FP64 epilogue), k_gram_i8<2> (2 x 2 cluster, TMA multicast),
+// k_gram_i8_2sm (CTA pair, tcgen05.mma.cta_group::2) -- all bit-identical (tests/test_gpu_parity.py).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
