@@ -94,6 +94,18 @@ def test_api_validation_matches_reference_messages():
                     (dict(FUNcluster="dbscan"), "FUNcluster needs to be one of")]:
         with pytest.raises(ValueError, match=msg):
             rid.clustexp(sc, **kw)
+    # the consumers of the matrix after clustexp: plotsilhouette (R/RaceID.R:1276-1277) and comptsne's start configuration
+    sc2 = rid.SCseq(np.ones((3, 3)))
+    with pytest.raises(ValueError, match="run compdist before plotsilhouette"):
+        rid.silhouette(sc2)
+    with pytest.raises(ValueError, match="run compdist before comptsne"):
+        rid.tsne_initial_config(sc2)
+    sc2.distances = np.zeros((3, 3))
+    with pytest.raises(ValueError, match="run clustexp before plotsilhouette"):
+        rid.silhouette(sc2)
+    sc2.cluster["kpart"] = np.ones(3, dtype=np.int32)
+    with pytest.raises(ValueError, match="only a single cluster: no silhouette plot"):
+        rid.silhouette(sc2)
     with pytest.raises(ValueError, match="more than one row"):
         rid.SCseq(np.ones((1, 5)))
     with pytest.raises(ValueError, match="negative values"):
