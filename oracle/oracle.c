@@ -20,6 +20,8 @@
  *   fpc::clusterboot call   R/RaceID_utils.R:132-133   -> orc_clusterboot()
  *   compmedoids             R/RaceID.R:1298-1316       -> orc_medoids()
  *   final partition refresh R/RaceID.R:1034-1060       -> orc_refresh()
+ *   plotsilhouette          R/RaceID.R:1283-1284       -> orc_silhouette()   (cluster::silhouette; pinned by scikit-learn)
+ *   comptsne start config   R/RaceID.R:1093            -> oracle.py cmdscale() (stats::cmdscale, numpy eigh)
  *
  * All matrices are column-major like R.  Indices crossing the API are 0-based; labels are 1-based
  * like R's cluster numbers.
