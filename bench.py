@@ -1,25 +1,36 @@
 #!/usr/bin/env python
 """bench.py — compdist + clustexp(kmedoids) wall seconds on synthetic UMI matrices (BASELINE.json's metric).
 
-A "step" is one pass of the hot path over one synthetic matrix: compdist(metric) -> clustexp(sat, cln, bootnr) through
-the reference-facing API (raceid3_stemid2_package_b200.compdist / clustexp -> C ABI -> CUDA kernels).
+A "step" is one pass of the hot path over one synthetic matrix: compdist(metric) -> clustexp(sat, cln, clustnr, bootnr).
+The default workload is BASELINE.json configs[3]: 100 000 cells x 3 000 genes, pearson, `clustexp(sc, cln=30)` — i.e.
+R's defaults sat=TRUE (the 30-k clusGapExt sweep runs although cln is given, R/RaceID.R:894,904), clustnr=30, bootnr=50.
 
-  value : seconds per step with the feature matrix already resident in HBM (CUDA events on the library's stream,
-          barrier + synchronize on both sides, max over ranks)
-  e2e   : seconds per step starting from a HOST (pinned) feature matrix: H2D copy inside the timed region, partition
-          / jaccard / medoids read back to the host
-  roofline : the dominant kernel (k_scan, the PAM streaming pass of BUILD and SWAP, HBM-bound): algorithmic bytes /
-          CUDA-event duration of its launches inside the timed region, against MEASURED_PEAKS.json's hbm_gbs;
+  value : seconds per step with the feature matrix already resident in HBM, through the C ABI (rid_dist ->
+          rid_gap_sweep -> rid_clusterboot); CUDA events on the library's stream, barrier + synchronize on both sides,
+          max over ranks
+  e2e   : seconds per step through the reference-facing API, `rid.compdist(sc)` -> `rid.clustexp(sc, ...)` on an SCseq
+          object that holds the count matrix the way the R package does (dgCMatrix = CSC, here in page-locked host
+          memory): H2D copy of the CSC triplet inside the timed region (getfdata is fused on the device, rid_dist_csc),
+          R-compatible bootstrap index vectors drawn inside it, partition / jaccard / medoids / logW read back
+  roofline : the dominant kernel family (k_scan, the PAM streaming pass of BUILD and SWAP, HBM-bound): algorithmic
+          bytes / CUDA-event duration of its launches inside the timed region, against MEASURED_PEAKS.json's hbm_gbs;
           detail.roofline_all holds the same object for the compaction, incremental-SWAP and distance kernels
+  parity_spot / result_digest : checked OUTSIDE the timed region at the benchmarked size — sampled rows of D against
+          FP64 numpy, a subset PAM and a bootstrap replicate against the CPU oracle; sha1 of the step's results
+          (identical for every GPU count) and the number of accepted swaps
+  detail.sat_false / swap_heavy / cfg5 / cooperative : the lighter sat=FALSE variant, a ring-structured synthetic on
+          which SWAP really iterates, BASELINE configs[4] (250k cells, logpearson, needs >= 2 GPUs) and the all-reduce
+          schedule (RID_NO_REPLICA=1) of the headline workload
   cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's R/C path; R itself is not installed
           in this image) on a bounded sample of the same workload, extrapolated ~ N^2
 
 One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE); the distance matrix is row-block sharded and the
-library runs its own NCCL all-reduces.  Rank 0 prints ONE JSON line.
+library runs its own NCCL collectives and NVLink peer copies.  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -45,23 +56,28 @@ def parse():
     ap.add_argument("--genes", type=int, default=3000)
     ap.add_argument("--metric", default="pearson")
     ap.add_argument("--cln", type=int, default=30)
-    ap.add_argument("--sat", type=int, default=0)
+    ap.add_argument("--sat", type=int, default=1, help="1: clustexp's default sat=TRUE (the k sweep runs); 0: sat=FALSE")
     ap.add_argument("--clustnr", type=int, default=30)
     ap.add_argument("--bootnr", type=int, default=50)
     ap.add_argument("--seed", type=int, default=1004)
+    ap.add_argument("--structure", default="clusters", choices=["clusters", "ring"])
     ap.add_argument("--cpu-cells", type=int, default=0,
                     help="cells in the CPU sample (0: 2500 for the 1-thread leg, ~10 s; 6000 for the all-threads reference arm)")
     ap.add_argument("--cpu-bootnr", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--timed-kinds", default="gram,gram_i8,scan_swap,scan_build,scan_delta,compact",
+    ap.add_argument("--no-extra", action="store_true", help="skip the detail legs (sat_false, swap_heavy, cfg5, cooperative)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--timed-kinds", default="gram,gram_i8,scan_swap,scan_build,scan_delta,scan_group,compact",
                     help="kernel kinds bracketed with CUDA events inside the timed region")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"synthetic {a.cells} cells x {a.genes} genes, metric={a.metric}, clustexp(sat={bool(a.sat)}, cln={a.cln}, "
-            f"clustnr={a.clustnr}, bootnr={a.bootnr}, FUNcluster=kmedoids)")
+def workload_name(a, cells=None, metric=None, sat=None, bootnr=None, structure=None):
+    return (f"synthetic {cells or a.cells} cells x {a.genes} genes ({structure or a.structure}), metric={metric or a.metric}, "
+            f"clustexp(sat={bool(a.sat if sat is None else sat)}, cln={a.cln}, clustnr={a.clustnr}, "
+            f"bootnr={a.bootnr if bootnr is None else bootnr}, FUNcluster=kmedoids)")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -76,9 +92,13 @@ def cpu_sample(a, omp: bool):
     from raceid3_stemid2_package_b200.synth import synth_features_numpy
 
     L = orc.lib(omp)
+    if omp:
+        # launchers (torchrun) export OMP_NUM_THREADS=1: this arm is "the reference's CPU path with all the host threads
+        # it can use", so ask for every core explicitly
+        L.orc_set_threads(os.cpu_count() or 1)
     cores = L.orc_num_threads()
     ns = min(a.cpu_cells or (6000 if omp else 2500), a.cells)
-    x, _ = synth_features_numpy(ns, a.genes, a.cln, a.seed)
+    x, _ = synth_features_numpy(ns, a.genes, a.cln, a.seed, a.structure)
     xt = np.ascontiguousarray(x.T)
     t0 = time.perf_counter()
     D, _ = orc.dist(xt, a.metric, omp=omp)
@@ -86,10 +106,12 @@ def cpu_sample(a, omp: bool):
     Dc = np.ascontiguousarray(D.T)
     k = min(a.cln, ns - 1)
     t_sweep = 0.0
+    nsw = min(ns, 3000 if omp else 1000)  # the 30 PAM runs of the sweep get a smaller sample of their own
     if a.sat:
+        sub = np.ascontiguousarray(np.arange(nsw), dtype=np.int32)
         t0 = time.perf_counter()
-        out = np.zeros(min(a.clustnr, ns - 1))
-        L.orc_gap_sweep(Dc, ns, None, ns, len(out), out)
+        out = np.zeros(min(a.clustnr, nsw - 1))
+        L.orc_gap_sweep(Dc, ns, sub.ctypes.data, nsw, len(out), out)
         t_sweep = time.perf_counter() - t0
     bs = min(a.cpu_bootnr, a.bootnr)
     samples = bootstrap_samples(ns, bs, 17000)
@@ -106,9 +128,11 @@ def cpu_sample(a, omp: bool):
     L.orc_clusterboot(Dc, ns, k, cat, lens, bs, part, med, br, bm)
     t_boot = max(time.perf_counter() - t0 - t_c1, 0.0)
     s2 = (a.cells / ns) ** 2
-    full = (t_dist + t_sweep + t_c1) * s2 + t_boot * s2 * (a.bootnr / max(bs, 1))
+    s2w = (a.cells / nsw) ** 2
+    full = (t_dist + t_c1) * s2 + t_sweep * s2w + t_boot * s2 * (a.bootnr / max(bs, 1))
     sample = (f"oracle port ({'OpenMP ' + str(cores) + ' threads' if omp else '1 thread'}) on {ns} cells x {a.genes} genes, "
-              f"k={k}, {bs} of {a.bootnr} bootstrap replicates: dist {t_dist:.2f}s, sweep {t_sweep:.2f}s, pam(c1) {t_c1:.2f}s, "
+              f"k={k}, {bs} of {a.bootnr} bootstrap replicates: dist {t_dist:.2f}s, sweep {t_sweep:.2f}s"
+              f"{' (on the first ' + str(nsw) + ' cells, x' + format(s2w, '.0f') + ')' if a.sat else ''}, pam(c1) {t_c1:.2f}s, "
               f"boot {t_boot:.2f}s; extrapolated x(N/n)^2={s2:.0f} (distance ~N^2 G, PAM ~k N^2 per iteration with the "
               f"sample's iteration counts) and linearly in bootnr")
     return {"value": full, "unit": "s", "cores": cores, "kind": "port", "sample": sample,
@@ -116,20 +140,20 @@ def cpu_sample(a, omp: bool):
 
 
 def run_reference(a):
+    """The reference's CPU path (oracle port, all host threads) on a bounded sample.  The sample is deterministic, so
+    it is timed once (twice if it is short: the faster run counts) instead of warmup+steps times; rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    info = None
-    for i in range(a.warmup + a.steps):
-        info = cpu_sample(a, omp=True)
-        if i >= a.warmup:
-            vals.append(info["value"])
-        if i == 0 and info["sample_seconds"] * (a.warmup + a.steps) > 240:
-            # keep the whole run within a few minutes: one warm-up only
-            a.warmup = min(a.warmup, 1)
-    v = statistics.mean(vals)
-    info["value"] = v
+    info = cpu_sample(a, omp=True)
+    runs = 1
+    if info["sample_seconds"] < 30.0:
+        again = cpu_sample(a, omp=True)
+        runs = 2
+        if again["value"] < info["value"]:
+            info = again
+    v = info["value"]
+    info["sample"] += f"; sample timed {runs}x (deterministic input), best run reported"
     line = {"metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference", "config": {"workload": workload_name(a)},
@@ -142,7 +166,7 @@ def run_reference(a):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region.  In-process NVML polling (one cheap call per 250 ms); a
+    """SM clock / throttle reasons DURING the timed region.  In-process NVML polling (one cheap call per 500 ms); a
     polling `nvidia-smi -lms` process proved intrusive (it stretched driver calls of the timed step on some boxes) and is
     only the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -225,6 +249,87 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# results of one step -> digest (identical for every GPU count: all sums are exact integers)
+# ---------------------------------------------------------------------------------------------------------------
+def digest_of(out) -> str:
+    import numpy as np
+
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(out["partition"], dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(out["id_med"], dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(out["bootresult"], dtype=np.float64).tobytes())
+    if out.get("logW") is not None:
+        h.update(np.ascontiguousarray(out["logW"], dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
+def transform_rows_fp64(x_ng, metric):
+    """FP64 numpy restatement of what cor()/dist() see for each cell (rows of x): centred unit rows for the correlation
+    metrics (average-tie ranks for spearman, log2 for logpearson), raw rows for euclidean."""
+    import numpy as np
+
+    x = np.asarray(x_ng, dtype=np.float64)
+    if metric == "euclidean":
+        return x
+    if metric == "logpearson":
+        x = np.log2(x)
+    elif metric == "spearman":
+        from scipy.stats import rankdata
+
+        x = rankdata(x, method="average", axis=1)
+    x = x - x.mean(axis=1, keepdims=True)
+    x = x - x.mean(axis=1, keepdims=True)  # second pass like cov.c
+    n = np.sqrt((x * x).sum(axis=1, keepdims=True))
+    return x / n
+
+
+def parity_spot(ctx, dm, x_host, a, metric, rank, rows=64, sub_cells=4000):
+    """Value-level checks at the benchmarked size (VERDICT r1 #1a), outside any timed region.  Collective: every rank
+    calls the library; rank 0 compares."""
+    import numpy as np
+
+    from oracle import oracle as orc
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+
+    N = dm.N
+    rng = np.random.default_rng(12345)
+    ridx = np.sort(rng.choice(N, size=min(rows, N), replace=False)).astype(np.int32)
+    got = dm.sub(ridx, None)  # rows x N
+    out = {"rows": int(len(ridx))}
+    t0 = time.perf_counter()
+    if rank == 0:
+        Z = transform_rows_fp64(x_host, metric)
+        if metric == "euclidean":
+            ref = np.stack([np.sqrt(((Z - Z[r]) ** 2).sum(1)) for r in ridx])
+        else:
+            ref = 1.0 - np.clip(Z[ridx] @ Z.T, -1.0, 1.0)
+            ref[np.arange(len(ridx)), ridx] = 0.0
+        out["max_abs_D"] = float(np.max(np.abs(got - ref)))
+        out["tolerance"] = 1e-6
+        del Z
+    # a PAM run on a subset of the resident matrix, and c1 + one bootstrap replicate on that sub-matrix, against the oracle
+    S = rng.permutation(N)[:min(sub_cells, N)].astype(np.int32)  # order significant (positions drive the tie rules)
+    k = min(a.cln, len(S) - 1)
+    r = dm.pam(k, subset=S)
+    Dsub = dm.sub(S, S)
+    dm2 = ctx.from_matrix(Dsub)
+    smp = bootstrap_samples(len(S), 1, 17000)
+    rb = dm2.clusterboot(k, smp)
+    dm2.free()
+    if rank == 0:
+        ro = orc.pam(Dsub, k)
+        out["pam_identical"] = bool(np.array_equal(r["id_med"], ro["id_med"]) and np.array_equal(r["clustering"], ro["clustering"])
+                                    and r["n_swaps"] == ro["n_swaps"])
+        out["pam_subset_cells"] = int(len(S))
+        out["pam_swaps"] = int(ro["n_swaps"])
+        bo = orc.clusterboot(Dsub, k, smp)
+        out["boot_identical"] = bool(np.array_equal(rb["partition"], bo["partition"]) and
+                                     np.array_equal(rb["bootresult"], np.asarray(bo["bootresult"])))
+        out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     a = parse()
     if a.impl == "reference":
@@ -260,99 +365,163 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def allsum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
     N, G = a.cells, a.genes
     dev = torch.device("cuda", local)
-    x_dev, _ = synth_features_torch(N, G, a.cln, a.seed, dev)  # N x G, cell-major; identical on every rank
-    torch.cuda.synchronize()
-    x_host = None
-    if not a.no_e2e:
-        x_host = torch.empty((N, G), dtype=torch.float64, pin_memory=True)
-        x_host.copy_(x_dev)
-        torch.cuda.synchronize()
-    h2d = N * G * 8
+    KINDS = ("gram", "gram_i8", "scan_swap", "scan_delta", "scan_build", "scan_group", "prep", "compact")
 
-    samples = rid.bootstrap_samples(N, a.bootnr, 17000)  # R-compatible index vectors; drawn once, outside the timing
     # ceilings measured on this GPU right now (outside the timed region)
     dmma_peak = ctx.measure_dmma_peak()
     read_peak = ctx.measure_read_peak(8.0)
+    i8_peak = ctx.measure_i8_peak()
 
-    state = {}
+    class Workload:
+        """One synthetic matrix resident in HBM (identical on every rank) + the step over it through the C ABI."""
 
-    def step(resident: bool):
-        if resident:
-            dm = ctx.dist((x_dev.data_ptr(), G, N), a.metric)
-        else:
-            dm = ctx.dist_cellmajor(x_host.numpy(), a.metric)
-        t_dist = ctx.last_ms
-        out = {}
-        if a.sat:
-            out["logW"] = dm.gap_sweep(min(a.clustnr, N - 1))
-            out["t_sweep"] = ctx.last_ms
-        r = dm.clusterboot(a.cln, samples)
-        out["t_boot"] = ctx.last_ms
-        out["t_dist"] = t_dist
-        out["partition"] = r["partition"]
-        out["bootmean"] = r["bootmean"]
-        out["d2h"] = r["partition"].nbytes + r["bootresult"].nbytes + r["id_med"].nbytes
-        dm.free()
-        state.update(out)
+        def __init__(self, cells, metric, sat, bootnr, seed, structure, clusters=None):
+            self.N, self.metric, self.sat, self.bootnr = cells, metric, sat, bootnr
+            self.x_dev, _ = synth_features_torch(cells, G, clusters or a.cln, seed, dev, structure)
+            torch.cuda.synchronize()
+            # R-compatible index vectors; for the C-ABI leg they are an input of rid_clusterboot, drawn once
+            self.samples = rid.bootstrap_samples(cells, bootnr, 17000, packed=True)
+            self.state = {}
 
-    # ---- resident leg: W warm-up + K timed steps -------------------------------------------------------------
+        def step(self, keep=False):
+            dm = ctx.dist((self.x_dev.data_ptr(), G, self.N), self.metric)
+            out = {"t_dist": ctx.last_ms}
+            if self.sat:
+                out["logW"] = dm.gap_sweep(min(a.clustnr, self.N - 1))
+                out["t_sweep"] = ctx.last_ms
+            r = dm.clusterboot(a.cln, self.samples)
+            out["t_boot"] = ctx.last_ms
+            out.update(partition=r["partition"], bootmean=r["bootmean"], bootresult=r["bootresult"], id_med=r["id_med"])
+            self.state = out
+            if keep:
+                return dm
+            dm.free()
+            return None
+
+        def timed(self, steps, warmup, kinds=None):
+            for _ in range(warmup):
+                self.step()
+            barrier()
+            if kinds is not None:
+                ctx.profile(kinds)
+            l0, s0 = ctx.launches, ctx.swaps
+            barrier()
+            ctx.event_record(0)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.step()
+            ctx.event_record(1)
+            barrier()
+            wall = time.perf_counter() - t0
+            dev_ms = ctx.event_elapsed_ms(0, 1)
+            prof = {k: ctx.profile_get(k) for k in KINDS} if kinds is not None else None
+            if kinds is not None:
+                ctx.profile(False)
+            ms, wl = allmax([dev_ms, wall * 1e3])
+            swaps = allsum([ctx.swaps - s0])[0]
+            return {"ms_per_step": ms / steps, "wall_ms_per_step": wl / steps, "launches": ctx.launches - l0,
+                    "n_swaps_per_step": swaps / steps, "prof": prof}
+
+    # ---- headline: resident leg, W warm-up + K timed steps ---------------------------------------------------
+    W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure)
     for _ in range(a.warmup):
-        step(True)
+        W.step()
     barrier()
     clocks = ClockSampler(local)
-    if rank == 0:  # one sampler per job: eight concurrent nvidia-smi pollers slow every rank's driver calls down
+    if rank == 0:  # one sampler per job: eight concurrent pollers slow every rank's driver calls down
         clocks.start()
-    # inside the timed region the kernels of the roofline objects are bracketed with CUDA events (~1800 pairs per step at
-    # the defaults, pre-created); the per-kind breakdown of everything comes from one extra, untimed step below
-    ctx.profile([k for k in a.timed_kinds.split(",") if k])
-    l0 = ctx.launches
-    barrier()
-    ctx.event_record(0)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step(True)
-    ctx.event_record(1)
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = ctx.event_elapsed_ms(0, 1)
-    launches = ctx.launches - l0
-    KINDS = ("gram", "gram_i8", "scan_swap", "scan_delta", "scan_build", "scan_group", "prep", "compact")
-    prof = {k: ctx.profile_get(k) for k in KINDS}
-    ctx.profile(False)
+    # inside the timed region the kernels of the roofline objects are bracketed with CUDA events (pre-created); the
+    # per-kind breakdown of everything comes from one extra, untimed step below
+    res = W.timed(a.steps, 0, [k for k in a.timed_kinds.split(",") if k])
     clk = clocks.stop()
-    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t[0]) / a.steps
-    wall_ms_per_step = float(t[1]) / a.steps
-
-    # ---- e2e leg: host input, host outputs -------------------------------------------------------------------
-    e2e = None
-    if not a.no_e2e:
-        step(False)  # warm-up of the host path
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            step(False)
-        barrier()
-        e = torch.tensor([(time.perf_counter() - t0) / a.steps], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(e, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(e[0]), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(state["d2h"])}
+    ms_per_step, wall_ms_per_step, launches, prof = res["ms_per_step"], res["wall_ms_per_step"], res["launches"], res["prof"]
+    state = W.state
+    digest = digest_of(state)
+    d2h = sum(int(np.asarray(state[k]).nbytes) for k in ("partition", "bootresult", "id_med")) + \
+        (int(state["logW"].nbytes) if state.get("logW") is not None else 0)
 
     # ---- untimed breakdown step: every kernel kind bracketed (its events slow the step down a little; shares only) ----
     ctx.profile(True)
     ctx.event_record(2)
-    step(True)
+    W.step()
     ctx.event_record(3)
     barrier()
     breakdown_ms = ctx.event_elapsed_ms(2, 3)
     prof_all = {k: ctx.profile_get(k) for k in KINDS}
     ctx.profile(False)
 
-    # ---- rooflines: the two hot kernels; `roofline` is the one with the larger share of the step --------------------
+    # ---- parity at the benchmarked size (outside the timed regions) -------------------------------------------
+    spot = None
+    x_host_dense = None
+    if not a.no_parity:
+        x_host_dense = W.x_dev.cpu().numpy() if rank == 0 else None
+        dm = W.step(keep=True)
+        spot = parity_spot(ctx, dm, x_host_dense, a, a.metric, rank)
+        dm.free()
+        x_host_dense = None
+
+    # ---- e2e leg: the reference-facing API on an SCseq object with the count matrix in CSC, host outputs ---------------
+    e2e = None
+    e2e_detail = None
+    if not a.no_e2e:
+        from scipy.sparse import csc_matrix
+
+        from raceid3_stemid2_package_b200.synth import synth_features_torch as _gen
+
+        cnt, _ = _gen(N, G, a.cln, a.seed, dev, a.structure, want_counts=True)  # N x G counts; CSR of it == CSC of genes x cells
+        sp = cnt.to_sparse_csr()
+        del cnt
+
+        def pinned(t, dtype):
+            h = torch.empty(t.shape, dtype=dtype, pin_memory=True)
+            h.copy_(t.to(dtype))
+            return h.numpy()
+
+        indptr, indices, data = pinned(sp.crow_indices(), torch.int32), pinned(sp.col_indices(), torch.int32), pinned(sp.values(), torch.float64)
+        del sp
+        torch.cuda.synchronize()
+        counts_csc = csc_matrix((data, indices, indptr), shape=(G, N), copy=False)
+        sc = rid.SCseq.from_filtered_counts(counts_csc)
+        h2d = int(data.nbytes + indices.nbytes + indptr.nbytes + N * 8 + G * 4)
+
+        def api_step():
+            rid.compdist(sc, metric=a.metric)
+            rid.clustexp(sc, sat=bool(a.sat), cln=a.cln, clustnr=a.clustnr, bootnr=a.bootnr, rseed=17000, verbose=False)
+            return sc
+
+        api_step()  # warm-up of the host path
+        barrier()
+        nst = max(1, min(a.steps, a.e2e_steps))
+        t0 = time.perf_counter()
+        for _ in range(nst):
+            api_step()
+        barrier()
+        e = allmax([(time.perf_counter() - t0) / nst])[0]
+        clb = sc.cluster["clb"]
+        api_out = {"partition": sc.cluster["kpart"], "id_med": clb["result"]["result"]["pamobject"]["id.med"] - 1,
+                   "bootresult": clb["bootresult"], "logW": sc.cluster["gap"]["Tab"][:, 0] if sc.cluster.get("gap") else None}
+        e2e = {"value": e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        e2e_detail = {"steps": nst, "api": "rid.compdist(sc) -> rid.clustexp(sc) on SCseq.from_filtered_counts(CSC, page-locked)",
+                      "digest": digest_of(api_out), "digest_equals_c_abi_leg": digest_of(api_out) == digest,
+                      "csc_nnz": int(len(data))}
+        sc.distances.free()
+        del sc, counts_csc, data, indices, indptr
+
+    # ---- rooflines -------------------------------------------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -361,9 +530,6 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = ("measured copy bandwidth, MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks
                else "fallback 6650 GB/s (B200_PROFILING.md)")
-    step_ms_total = ms_per_step * a.steps
-    roofs = []
-    # DRAM bytes per algorithmic byte of the captured launches (ncu --set full; profiles/ncu_traffic_ratios.json)
     try:
         ratios = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_ratios.json")))
     except Exception:
@@ -373,82 +539,85 @@ def main():
         r = ratios.get(kernel, {}).get("dram_per_algorithmic")
         return alg_bytes_per_launch * r if r else None
 
-    sw = prof["scan_swap"]
-    # k_scan<MODE>: one streaming body, three instantiations (0: BUILD step 0, 1: SWAP / grouped sums, 2: incremental BUILD)
-    sc = {f: sum(prof[k][f] for k in ("scan_swap", "scan_build", "scan_group")) for f in ("launches", "ms", "work", "traffic")}
-    if sc["launches"]:
-        ach = sc["work"] / (sc["ms"] * 1e-3) / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k_scan<MODE> (PAM streaming pass: BUILD steps, SWAP scan, grouped column sums)",
-                      "achieved": ach, "peak": hbm_peak,
-                      "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic_of("k_scan", sc["work"] / sc["launches"]),
-                      "peak_source": hbm_src,
-                      "read_only_stream_gbs_measured_here": read_peak, "launches": sc["launches"],
-                      "avg_launch_ms": sc["ms"] / sc["launches"],
-                      "algorithmic_bytes_per_launch": sc["work"] / sc["launches"],
-                      "requested_bytes_per_launch": sc["traffic"] / sc["launches"],
-                      "by_mode": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"],
-                                      "gbs": prof[k]["work"] / (prof[k]["ms"] * 1e-3) / 1e9 if prof[k]["ms"] else None}
-                                  for k in ("scan_swap", "scan_build", "scan_group")},
-                      "note": "bytes = rows scanned x subset size x 4, every distance read once per pass; the kernel only "
-                              "reads, so the measured copy bandwidth (read + write) understates its ceiling: "
-                              "read_only_stream_gbs_measured_here is the read-only streaming figure of this run; traffic = "
-                              "algorithmic bytes x the DRAM/algorithmic ratio of the ncu capture",
-                      "share_of_step": sc["ms"] / step_ms_total})
-    sd = prof["scan_delta"]
-    if sd["launches"] and sd["ms"] > 0:
-        ach = sd["work"] / (sd["ms"] * 1e-3) / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k_scan_delta (incremental SWAP: rows whose nearest / second medoid changed)",
-                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                      "peak_source": hbm_src, "launches": sd["launches"], "avg_launch_ms": sd["ms"] / sd["launches"],
-                      "algorithmic_bytes_per_launch": sd["work"] / sd["launches"],
-                      "requested_bytes_per_launch": sd["traffic"] / sd["launches"],
-                      "note": "launches enqueued ahead of the local optimum are no-ops and count with ~2 us each",
-                      "share_of_step": sd["ms"] / step_ms_total})
-    cp = prof["compact"]
-    if cp["launches"]:
-        ach = cp["work"] / (cp["ms"] * 1e-3) / 1e9
-        roofs.append({"bound": "hbm", "kernel": "k_compact_sym (D[bsamp,bsamp] copy of a bootstrap replicate, fused with BUILD step 0)",
-                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                      "traffic": traffic_of("k_compact_sym", cp["work"] / cp["launches"]),
-                      "peak_source": hbm_src, "launches": cp["launches"], "avg_launch_ms": cp["ms"] / cp["launches"],
-                      "algorithmic_bytes_per_launch": cp["work"] / cp["launches"],
-                      "requested_bytes_per_launch": cp["traffic"] / cp["launches"],
-                      "note": "one GPU / full replica: algorithmic bytes = upper triangle of D[bsamp,bsamp] gathered once + the "
-                              "square written (1.5 m^2 x 4); requested = the 32-byte sectors those gathers touch (x N/m) + "
-                              "the square.  Row shards use k_compact (whole rows read: rows x (N + m) x 4)",
-                      "share_of_step": cp["ms"] / step_ms_total})
-    gm = prof["gram"]
-    if gm["launches"]:
-        ach = gm["work"] / (gm["ms"] * 1e-3) / 1e12
-        roofs.append({"bound": "tensor", "kernel": "k_gram_dmma (FP64 DMMA distance contraction)", "achieved": ach,
-                      "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if dmma_peak else None,
-                      "traffic": None,
-                      "peak_source": "FP64 DMMA issue-rate ceiling measured in this run (rid_measure_dmma_peak); "
-                                     "MEASURED_PEAKS.json holds no FP64 figure (nominal B200 FP64 tensor: 40 TFLOP/s)",
-                      "launches": gm["launches"], "avg_launch_ms": gm["ms"] / gm["launches"],
-                      "issued_flops_per_launch": gm["work"] / gm["launches"],
-                      "algorithmic_flops_per_launch": 2.0 * N * N * G / world,
-                      "note": "work = flops actually issued (upper-triangle tiles only; the mirror tile is a store)",
-                      "share_of_step": gm["ms"] / step_ms_total})
-    g8 = prof["gram_i8"]
-    if g8["launches"]:
-        ach = g8["work"] / (g8["ms"] * 1e-3) / 1e12
-        bf16 = float(peaks.get("bf16_tflops", 1590.0))
-        i8_peak = 2.0 * bf16  # int8 tcgen05 issues at twice the bf16 rate; the bf16 figure is the measured cuBLAS burst
-        roofs.append({"bound": "tensor", "kernel": "k_gram_i8_persist (tcgen05.mma kind::i8, exact Ozaki-split distance contraction)",
-                      "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak,
-                      "traffic": (ratios.get("k_gram_i8_persist", {}).get("dram_bytes_per_launch_cfg4")
-                                  if (N, G, world) == (100000, 3000, 1) else None),
-                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (measured cuBLAS bf16 burst; int8 dense is 2x bf16 "
-                                     "on sm_100: nominal 4500 TOP/s)" if "bf16_tflops" in peaks else
-                                     "2 x fallback 1590 TFLOP/s bf16 (B200_PROFILING.md)",
-                      "launches": g8["launches"], "avg_launch_ms": g8["ms"] / g8["launches"],
-                      "issued_int8_ops_per_launch": g8["work"] / g8["launches"],
-                      "fp64_equivalent_tflops_2N2G": 2.0 * N * N * G * g8["launches"] / (g8["ms"] * 1e-3) / 1e12,
-                      "note": "work = 13 digit products x 2*128*96*Kp per computed tile (tiles touching the upper triangle)",
-                      "share_of_step": g8["ms"] / step_ms_total})
-    roofs.sort(key=lambda r: -r["share_of_step"])
+    def rooflines(prof, step_ms_total, Nw, worldw):
+        roofs = []
+        # k_scan<MODE>: one streaming body, three instantiations (0: BUILD step 0, 1: SWAP / grouped sums, 2: incremental BUILD)
+        sc_ = {f: sum(prof[k][f] for k in ("scan_swap", "scan_build", "scan_group")) for f in ("launches", "ms", "work", "traffic")}
+        if sc_["launches"] and sc_["ms"] > 0:
+            ach = sc_["work"] / (sc_["ms"] * 1e-3) / 1e9
+            roofs.append({"bound": "hbm", "kernel": "k_scan<MODE> / k_wk_batch (PAM streaming pass: BUILD steps, SWAP scan, grouped column sums)",
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                          "traffic": traffic_of("k_scan", sc_["work"] / sc_["launches"]), "peak_source": hbm_src,
+                          "read_only_stream_gbs_measured_here": read_peak, "launches": sc_["launches"],
+                          "avg_launch_ms": sc_["ms"] / sc_["launches"],
+                          "algorithmic_bytes_per_launch": sc_["work"] / sc_["launches"],
+                          "requested_bytes_per_launch": sc_["traffic"] / sc_["launches"],
+                          "by_mode": {k: {"launches": prof[k]["launches"], "ms": prof[k]["ms"],
+                                          "gbs": prof[k]["work"] / (prof[k]["ms"] * 1e-3) / 1e9 if prof[k]["ms"] else None}
+                                      for k in ("scan_swap", "scan_build", "scan_group")},
+                          "note": "bytes = rows scanned x subset size x 4, every distance read once per pass; the kernel only "
+                                  "reads, so the measured copy bandwidth (read + write) understates its ceiling: "
+                                  "read_only_stream_gbs_measured_here is the read-only streaming figure of this run; traffic = "
+                                  "algorithmic bytes x the DRAM/algorithmic ratio of the ncu capture",
+                          "share_of_step": sc_["ms"] / step_ms_total})
+        sd = prof["scan_delta"]
+        if sd["launches"] and sd["ms"] > 0:
+            ach = sd["work"] / (sd["ms"] * 1e-3) / 1e9
+            roofs.append({"bound": "hbm", "kernel": "k_scan_delta (incremental SWAP: rows whose nearest / second medoid changed)",
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                          "peak_source": hbm_src, "launches": sd["launches"], "avg_launch_ms": sd["ms"] / sd["launches"],
+                          "algorithmic_bytes_per_launch": sd["work"] / sd["launches"],
+                          "requested_bytes_per_launch": sd["traffic"] / sd["launches"],
+                          "note": "launches enqueued ahead of the local optimum are no-ops and count with ~2 us each",
+                          "share_of_step": sd["ms"] / step_ms_total})
+        cp = prof["compact"]
+        if cp["launches"] and cp["ms"] > 0:
+            ach = cp["work"] / (cp["ms"] * 1e-3) / 1e9
+            roofs.append({"bound": "hbm", "kernel": "k_compact_sym (D[bsamp,bsamp] copy of a bootstrap replicate, fused with BUILD step 0)",
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                          "traffic": traffic_of("k_compact_sym", cp["work"] / cp["launches"]),
+                          "peak_source": hbm_src, "launches": cp["launches"], "avg_launch_ms": cp["ms"] / cp["launches"],
+                          "algorithmic_bytes_per_launch": cp["work"] / cp["launches"],
+                          "requested_bytes_per_launch": cp["traffic"] / cp["launches"],
+                          "note": "one GPU / full replica: algorithmic bytes = upper triangle of D[bsamp,bsamp] gathered once + the "
+                                  "square written (1.5 m^2 x 4); requested = the 32-byte sectors those gathers touch (x N/m) + "
+                                  "the square.  Row shards use k_compact (whole rows read: rows x (N + m) x 4)",
+                          "share_of_step": cp["ms"] / step_ms_total})
+        gm = prof["gram"]
+        if gm["launches"] and gm["ms"] > 0:
+            ach = gm["work"] / (gm["ms"] * 1e-3) / 1e12
+            roofs.append({"bound": "tensor", "kernel": "k_gram_dmma (FP64 DMMA distance contraction)", "achieved": ach,
+                          "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak if dmma_peak else None,
+                          "traffic": None,
+                          "peak_source": "FP64 DMMA issue-rate ceiling measured in this run (rid_measure_dmma_peak); "
+                                         "MEASURED_PEAKS.json holds no FP64 figure (nominal B200 FP64 tensor: 40 TFLOP/s)",
+                          "launches": gm["launches"], "avg_launch_ms": gm["ms"] / gm["launches"],
+                          "issued_flops_per_launch": gm["work"] / gm["launches"],
+                          "algorithmic_flops_per_launch": 2.0 * Nw * Nw * G / worldw,
+                          "note": "work = flops actually issued (upper-triangle tiles only; the mirror tile is a store)",
+                          "share_of_step": gm["ms"] / step_ms_total})
+        g8 = prof["gram_i8"]
+        if g8["launches"] and g8["ms"] > 0:
+            ach = g8["work"] / (g8["ms"] * 1e-3) / 1e12
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            roofs.append({"bound": "tensor", "kernel": "k_gram_i8_persist (tcgen05.mma kind::i8, exact Ozaki-split distance contraction)",
+                          "achieved": ach, "peak": i8_peak, "unit": "TOP/s", "frac": ach / i8_peak if i8_peak else None,
+                          "traffic": (ratios.get("k_gram_i8_persist", {}).get("dram_bytes_per_launch_cfg4")
+                                      if (Nw, G, worldw) == (100000, 3000, 1) else None),
+                          "peak_source": "int8 tcgen05 issue-rate ceiling measured in this run (rid_measure_i8_peak: M=128 N=192 "
+                                         "K=32 kind::i8 from shared memory, one CTA per SM, no loads)",
+                          "frac_of_2x_measured_bf16_burst": ach / (2.0 * bf16),
+                          "launches": g8["launches"], "avg_launch_ms": g8["ms"] / g8["launches"],
+                          "issued_int8_ops_per_launch": g8["work"] / g8["launches"],
+                          "fp64_equivalent_tflops_2N2G": 2.0 * Nw * Nw * G * g8["launches"] / (g8["ms"] * 1e-3) / 1e12,
+                          "note": "work = digit products issued x 2*128*96*Kp per computed tile (tiles touching the upper triangle)",
+                          "share_of_step": g8["ms"] / step_ms_total})
+        roofs.sort(key=lambda r: -r["share_of_step"])
+        return roofs
+
+    roofs = rooflines(prof, ms_per_step * a.steps, N, world)
     roof = roofs[0] if roofs else None
+    sw = prof["scan_swap"]
     detail = {"breakdown_step_ms": breakdown_ms}
     for k, v in prof_all.items():
         if not v["launches"]:
@@ -459,11 +628,11 @@ def main():
             d["int8_tops_issued"] = v["work"] / (v["ms"] * 1e-3) / 1e12
             d["tflops_algorithmic_2N2G"] = 2.0 * N * N * G / world * v["launches"] / (v["ms"] * 1e-3) / 1e12
             d["tflops_algorithmic_2N2G_timed"] = (2.0 * N * N * G / world * prof[k]["launches"] / (prof[k]["ms"] * 1e-3) / 1e12
-                                                  if prof[k]["launches"] else None)
+                                                  if prof[k]["launches"] and prof[k]["ms"] > 0 else None)
         elif k == "gram":
             d["tflops_issued"] = v["work"] / (v["ms"] * 1e-3) / 1e12
             d["tflops_algorithmic_2N2G"] = 2.0 * N * N * G / world * v["launches"] / (v["ms"] * 1e-3) / 1e12
-        else:
+        elif v["ms"] > 0:
             d["algorithmic_gbs"] = v["work"] / (v["ms"] * 1e-3) / 1e9
             d["requested_gbs"] = v["traffic"] / (v["ms"] * 1e-3) / 1e9
         detail[k] = d
@@ -472,6 +641,66 @@ def main():
     detail["clusters_found"] = int(state["partition"].max())
     detail["bootmean_min"] = float(np.min(state["bootmean"]))
     detail["roofline_all"] = roofs
+    detail["ceilings_measured_here"] = {"int8_tops": i8_peak, "fp64_dmma_tflops": dmma_peak, "read_only_stream_gbs": read_peak}
+    if e2e_detail:
+        detail["e2e"] = e2e_detail
+    del W
+    ctx.trim()
+    torch.cuda.empty_cache()
+
+    # ---- detail legs -------------------------------------------------------------------------------------------------
+    def leg(cells, metric, sat, bootnr, seed, structure, steps=2, warmup=1, clusters=None, env=None, want_spot=False):
+        old = {}
+        for k_, v_ in (env or {}).items():
+            old[k_] = os.environ.get(k_)
+            os.environ[k_] = v_
+        try:
+            Wl = Workload(cells, metric, sat, bootnr, seed, structure, clusters)
+            r = Wl.timed(steps, warmup, ["gram", "gram_i8", "scan_swap", "scan_build", "scan_delta", "scan_group", "compact"])
+            out = {"workload": workload_name(a, cells, metric, sat, bootnr, structure), "value": r["ms_per_step"] / 1e3, "unit": "s",
+                   "steps": steps, "warmup": warmup, "result_digest": digest_of(Wl.state), "n_swaps_per_step": r["n_swaps_per_step"],
+                   "gpu_launches_per_step": r["launches"] / steps, "bootmean_min": float(np.min(Wl.state["bootmean"])),
+                   "phase_ms_last_step": {k: Wl.state.get(k) for k in ("t_dist", "t_sweep", "t_boot") if k in Wl.state}}
+            rf = rooflines(r["prof"], r["ms_per_step"] * steps, cells, world)
+            out["roofline"] = rf[0] if rf else None
+            out["kernels"] = {x["kernel"].split(" ")[0]: {"achieved": x["achieved"], "unit": x["unit"], "frac": x["frac"],
+                                                         "share_of_step": x["share_of_step"], "launches": x["launches"]} for x in rf}
+            if want_spot:
+                xh = Wl.x_dev.cpu().numpy() if rank == 0 else None
+                dmk = Wl.step(keep=True)
+                out["parity_spot"] = parity_spot(ctx, dmk, xh, a, metric, rank, rows=32, sub_cells=3000)
+                dmk.free()
+            del Wl
+            return out
+        finally:
+            for k_, v_ in old.items():
+                if v_ is None:
+                    os.environ.pop(k_, None)
+                else:
+                    os.environ[k_] = v_
+            ctx.trim()
+            torch.cuda.empty_cache()
+
+    if not a.no_extra:
+        if a.sat:
+            detail["sat_false"] = leg(N, a.metric, False, a.bootnr, a.seed, a.structure, steps=3, warmup=1)
+        # ring-structured data (10 profiles mixed along a closed trajectory): BUILD is not the optimum, SWAP iterates
+        detail["swap_heavy"] = leg(N, a.metric, False, min(a.bootnr, 10), a.seed + 100, "ring", steps=2, warmup=1, clusters=10)
+        if world > 1:
+            # the north_star's all-reduce schedule on the headline workload: every PAM pass row-sharded, SP / AQ combined
+            # by ncclAllReduce, no replica
+            detail["cooperative"] = leg(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure, steps=2, warmup=1,
+                                        env={"RID_NO_REPLICA": "1"})
+            # BASELINE configs[4]: 250k cells x 3k genes, logpearson, row-sharded 250 GB matrix (cannot replicate)
+            torch.cuda.empty_cache()
+            free_b, _tot = torch.cuda.mem_get_info()
+            need = 250000.0 * 250112.0 * 4.0 / world + 40e9
+            fits_all = -allmax([-(1.0 if free_b > need else 0.0)])[0] > 0.5
+            if fits_all:
+                detail["cfg5"] = leg(250000, "logpearson", False, min(a.bootnr, 10), 1005, "clusters", steps=2, warmup=1,
+                                     want_spot=not a.no_parity)
+            else:
+                detail["cfg5"] = {"skipped": f"250k x 250k x 4 B / {world} GPUs does not fit next to the work buffers ({free_b / 1e9:.0f} GB free)"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -485,8 +714,9 @@ def main():
                 "config": {"workload": workload_name(a), "seed": a.seed, "parallelism": f"row-block shard x{world}",
                            "l2": "inputs (distance matrix %.1f GB) larger than L2" % (N * N * 4 / 1e9)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "result_digest": digest, "n_swaps": res["n_swaps_per_step"], "parity_spot": spot,
                 "dist_tflops": (detail.get("gram_i8") or detail.get("gram") or {}).get("tflops_algorithmic_2N2G"),
-                "pam_swap_gbs": (sw["work"] / (sw["ms"] * 1e-3) / 1e9) if sw["launches"] else None, "detail": detail}
+                "pam_swap_gbs": (sw["work"] / (sw["ms"] * 1e-3) / 1e9) if sw["launches"] and sw["ms"] > 0 else None, "detail": detail}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -36,7 +36,8 @@ enum {
     RID_ERR_CUDA = -2,    /* CUDA / NCCL runtime failure, or no usable sm_100 device                    */
     RID_ERR_NA = -3,      /* NAs in the dissimilarity matrix (pam() refuses them upstream)               */
     RID_ERR_NOMEM = -4,
-    RID_ERR_UNSUPPORTED = -5
+    RID_ERR_UNSUPPORTED = -5,
+    RID_ERR_INTERRUPTED = -6 /* the caller asked for cancellation (rid_ctx_request_abort / the poll callback)   */
 };
 
 const char *rid_last_error(void);
@@ -50,10 +51,24 @@ int rid_nccl_unique_id(void *uid128);
 int rid_ctx_create(int device, int rank, int world, const void *nccl_uid, rid_ctx **out);
 int rid_ctx_destroy(rid_ctx *ctx);
 int rid_ctx_sync(rid_ctx *ctx);
+/* Cancellation (upstream cluster::pam polls R_CheckUserInterrupt once per candidate row).
+ * rid_ctx_request_abort may be called from any thread or from a signal handler while a compute call is running on
+ * `ctx`; rid_ctx_set_interrupt_poll installs a callback the library runs ON THE CALLING THREAD between enqueued waves
+ * of GPU work (per k of the sweep, per SWAP batch, per wave of bootstrap replicates) — the R stub passes a function
+ * that wraps R_CheckUserInterrupt in R_ToplevelExec and returns non-zero when the user pressed Ctrl-C.  Either way the
+ * running call drains the GPU, releases its work buffers and returns RID_ERR_INTERRUPTED; the context and the
+ * distance matrix stay usable.  Multi-rank jobs agree on the answer (one small all-reduce per poll point). */
+int rid_ctx_request_abort(rid_ctx *ctx);
+int rid_ctx_clear_abort(rid_ctx *ctx);
+int rid_ctx_set_interrupt_poll(rid_ctx *ctx, int (*poll)(void *), void *arg);
 /* Milliseconds the GPU spent in the last compute call of this ctx, from CUDA events on its stream. */
 double rid_ctx_last_ms(const rid_ctx *ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 long long rid_ctx_launches(const rid_ctx *ctx);
+/* Accepted SWAP exchanges summed over every PAM run this ctx has finished (c1, sweep, bootstrap replicates). */
+long long rid_ctx_swaps(const rid_ctx *ctx);
+/* Give the cached device buffers back to the driver (collective when world > 1: call it on every rank). */
+int rid_ctx_trim(rid_ctx *ctx);
 
 /* The row block [row0,row1) of an N x N matrix that rank `rank` of `world` owns (pure host function). */
 int rid_shard_rows(int N, int rank, int world, int *row0, int *row1);
@@ -67,6 +82,8 @@ int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, double *ms,
  * 128-bit streaming loop over `gib` GiB of HBM, GB/s (MEASURED_PEAKS.json holds a copy figure and a bf16 figure only). */
 int rid_measure_dmma_peak(rid_ctx *ctx, double *tflops);
 int rid_measure_read_peak(rid_ctx *ctx, double gib, double *gbs);
+/* Issue-rate ceiling of the int8 tensor pipe (tcgen05.mma kind::i8, M=128 N=192 K=32 from shared memory), TOP/s. */
+int rid_measure_i8_peak(rid_ctx *ctx, double *tops);
 /* user events on the library's stream, slots 0..7 */
 int rid_ctx_event_record(rid_ctx *ctx, int slot);
 int rid_ctx_event_elapsed_ms(rid_ctx *ctx, int slot_a, int slot_b, double *ms);
@@ -91,7 +108,10 @@ int rid_dmat_free(rid_dmat *dm);
  * see DESIGN.md), 1 if the matrix holds NAs. */
 int rid_dmat_info(const rid_dmat *dm, int *N, int *row0, int *row1, double *step, int *has_na);
 /* as.matrix() on demand: out is m x n column-major, rows ridx (NULL = 0..m-1), columns cidx (NULL = 0..n-1).
- * Collective when world>1 (every rank calls with the same arguments; every rank receives the block). */
+ * Collective when world>1 (every rank calls with the same arguments; every rank receives the block).
+ * Values are q * step (what the clustering kernels see), within step / 2 <= 1e-6 of R's doubles.  A euclidean matrix
+ * whose range makes step larger than 2e-6 (largest distance >= 4096) keeps its feature rows, and this call then
+ * returns sqrt(sum (x_i - x_j)^2) recomputed in FP64 like stats::dist, so the 1e-6 budget holds for any range. */
 int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cidx, int n, double *out);
 
 /* ---- cluster::pam(as.dist(x[subset,subset]), k) as called at R/RaceID_utils.R:113,221 ------------------ */
@@ -133,6 +153,13 @@ int rid_silhouette(rid_dmat *dm, const int *labels, int N, int *neighbor, double
  * residual |B v - lambda v| / |lambda| of the k pairs (<= 0: 1e-9); max_iter (<= 0: 1000); iters (nullable): used.
  * k <= 4 on this path (block of 8 vectors); NA in the matrix is an error like in cmdscale. */
 int rid_cmdscale(rid_dmat *dm, int k, double tol, int max_iter, double *points, double *eig, int *iters);
+
+/* ---- host-only helper: the resamples fpc::clusterboot draws after set.seed(seed) (R/RaceID_utils.R:132-133), from R's
+ * default generator (Mersenne-Twister, "Rejection" sample.kind).  subset_size <= 0: bootmethod "boot" — sample(n, n,
+ * replace=TRUE) then unique() in first-occurrence order; > 0: bootmethod "subset" — sample(n, min(n, subset_size)).
+ * out_cat holds up to B * n 0-based indices (the resamples concatenated), out_len[B] their lengths.  No GPU involved;
+ * an R host passes the vectors its own sample() drew instead. */
+int rid_r_bootstrap_samples(int n, int B, unsigned int seed, int subset_size, int *out_cat, int *out_len);
 
 /* ---- W.k (R/RaceID_utils.R:39-53) for a given partition; used by tests and by callers of clusGapExt ---- */
 int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int *labels, int k, double *W);

@@ -45,6 +45,16 @@ int orc_num_threads(void)
 #endif
 }
 
+/* bench.py --impl reference: launchers such as torchrun export OMP_NUM_THREADS=1; the arm asks for all cores itself */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---------------------------------------------------------------------------------------------
  * rank(x, ties.method="average")  — upstream: R rank(); used by cor(method="spearman") through
  * apply(X,2,rank) (RaceID_utils.R:10).  Ranks are over the G genes within one cell.

@@ -29,6 +29,8 @@ def lib(omp: bool = False) -> C.CDLL:
         build()
         L = C.CDLL(os.path.join(_HERE, "liboracle_omp.so" if omp else "liboracle.so"))
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = None
         L.orc_dist.restype = C.c_int
         L.orc_dist.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp]
         L.orc_pam.restype = C.c_int

@@ -39,9 +39,16 @@ struct rid_ctx {
     int rank = 0, world = 1;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // copy-engine work that overlaps kernels on `stream` (peer pulls of matrix shards)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // cooperative cancellation (long calls must be interruptible): a flag any thread / signal handler may
+    // set, and an optional poll callback run on the calling thread between enqueued waves of work
+    volatile int abort_flag = 0;
+    int (*poll_fn)(void *) = nullptr;
+    void *poll_arg = nullptr;
     double last_ms = 0.0;
     long long launches = 0;
+    long long swaps = 0; // accepted SWAP exchanges of every PAM run read back so far (bench.py's n_swaps)
     void *comm = nullptr; // ncclComm_t
     NcclApi *nccl = nullptr;
     // optional per-kernel profiling (rid_ctx_profile): CUDA-event pairs around the hot kernels, on `stream`
@@ -60,6 +67,9 @@ struct rid_ctx {
     // peer distance-matrix shards mapped through CUDA IPC (multi-rank symmetric Gram kernel)
     struct IpcMap { unsigned char handle[64]; void *ptr; };
     std::vector<IpcMap> ipc;
+    // allocations of this rank whose IPC handle went out to the peers: a peer may hold them mapped, so they are never
+    // given back to the driver (pool eviction / trim) before rid_ipc_release_all has closed the mappings everywhere
+    std::vector<void *> exported;
     void *scratch = nullptr; // small device scratch (barriers, handle exchange)
     // tile list of the persistent distance kernel (device), cached per problem shape
     void *i8_tiles = nullptr;
@@ -69,14 +79,27 @@ struct rid_ctx {
     // page-locked host staging (grow-only), e.g. the subset tables and result slots of the bootstrap pipeline
     void *pin = nullptr;
     size_t pin_bytes = 0;
+    int live_sharded = 0; // multi-rank matrices alive (their peers' mappings must stay open)
 };
 
 // page-locked host memory owned by the context (contents are not preserved when it grows)
 void *rid_pinned(rid_ctx *ctx, size_t bytes);
 
 // Collect the device pointers of every rank's buffer (peers mapped with CUDA IPC).  peers[rank] = mine.
-// Returns RID_OK with *all_ok = 1 only if every rank could map every peer.
+// `mine` may point inside a larger allocation: the offset from the allocation base travels with the handle.
+// Returns RID_OK with *all_ok = 1 only if every rank could map every peer.  Collective.
 int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok);
+// Collective: every rank closes its mappings of the peers' buffers, then (after a barrier) forgets which of its own
+// buffers were exported, so that they may be freed again.
+int rid_ipc_release_all(rid_ctx *ctx);
+// Collective: *all_ok = 1 iff every rank passed ok != 0.
+int rid_agree_all(rid_ctx *ctx, int ok, int *all_ok);
+// dist.cu: start / finish pulling the other ranks' row blocks into dm->full (no-ops without a replica buffer)
+int rid_replica_start(rid_dmat *dm);
+int rid_replica_complete(rid_dmat *dm);
+// RID_ERR_INTERRUPTED if the caller asked for cancellation (flag or poll callback); clears the request.  With
+// collective = true the answer is agreed over all ranks (an all-reduce: call it at the same point on every rank).
+int rid_check_abort(rid_ctx *ctx, bool collective);
 int rid_barrier(rid_ctx *ctx);
 int rid_allgather(rid_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 
@@ -111,6 +134,27 @@ struct rid_dmat {
     int has_na = 0;
     std::vector<unsigned char> na_cell; // host copy: 1 if the cell's row/col is NA
     PamWs *ws = nullptr;
+    // ---- multi-rank replica ----
+    // When N x ld words fit next to the work buffers, every rank allocates the WHOLE matrix; `D` then points at the
+    // rank's own row block inside `full`.  The other ranks' blocks are pulled over NVLink by the copy engines
+    // (cudaMemcpy2DAsync from the peers' IPC-mapped buffers on ctx->copy_stream), overlapping the kernels of the first
+    // clustering phase.  replica_state: 0 nothing pulled, 1 columns >= replica_lo[s] of every peer block s (all the
+    // symmetric compaction of a bootstrap replicate reads), 2 complete.
+    u32 *full = nullptr;
+    size_t full_bytes = 0;
+    u32 *peer_full[16] = {nullptr};
+    u32 *peer_shard[16] = {nullptr}; // every rank's row block (CUDA IPC); valid when peers_ok
+    int peers_ok = 0;
+    rid_dmat *parent = nullptr;      // set in a replica view: the sharded matrix it was made from
+    int replica_state = 0;
+    int replica_lo[16] = {0};
+    cudaEvent_t replica_ev = nullptr;
+    rid_dmat *replica_view = nullptr; // the "one GPU owns every row" view of `full` the bootstrap PAM runs use
+    // euclidean only: the raw feature matrix (N x Gx doubles, one row per cell) kept so that exported distances are
+    // recomputed in FP64 difference form when the fixed-point step alone would exceed the 1e-6 budget
+    double *xraw = nullptr;
+    size_t xraw_bytes = 0;
+    int xraw_G = 0, xraw_ld = 0;
 };
 
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

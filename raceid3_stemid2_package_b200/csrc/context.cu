@@ -110,6 +110,7 @@ extern "C" int rid_ctx_create(int device, int rank, int world, const void *nccl_
     ctx->world = world;
     ctx->sm_count = prop.multiProcessorCount;
     RID_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RID_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     RID_CUDA(cudaEventCreate(&ctx->ev0));
     RID_CUDA(cudaEventCreate(&ctx->ev1));
     if (world > 1) {
@@ -140,8 +141,12 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     if (!ctx) return RID_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    // peers may hold this rank's exported buffers mapped: everybody closes first, then everybody frees
+    if (ctx->world > 1 && ctx->comm && (!ctx->ipc.empty() || !ctx->exported.empty())) rid_ipc_release_all(ctx);
     for (auto &m : ctx->ipc) cudaIpcCloseMemHandle(m.ptr);
     ctx->ipc.clear();
+    ctx->exported.clear();
     rid_pool_trim(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -151,6 +156,7 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return RID_OK;
 }
@@ -165,6 +171,18 @@ extern "C" int rid_ctx_sync(rid_ctx *ctx)
 
 extern "C" double rid_ctx_last_ms(const rid_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
 extern "C" long long rid_ctx_launches(const rid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long rid_ctx_swaps(const rid_ctx *ctx) { return ctx ? ctx->swaps : 0; }
+
+// Collective when world > 1: closes the peers' mappings, then gives every cached device buffer back to the driver.
+extern "C" int rid_ctx_trim(rid_ctx *ctx)
+{
+    if (!ctx) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->world > 1 && ctx->live_sharded == 0) RID_TRY(rid_ipc_release_all(ctx));
+    rid_pool_trim(ctx);
+    return RID_OK;
+}
 
 int rid_time_begin(rid_ctx *ctx)
 {
@@ -198,6 +216,13 @@ static double now_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+static bool is_exported(const rid_ctx *ctx, const void *p)
+{
+    for (void *q : ctx->exported)
+        if (q == p) return true;
+    return false;
+}
+
 cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes)
 {
     for (size_t i = 0; i < ctx->pool.size(); ++i)
@@ -227,9 +252,13 @@ void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
         return;
     }
     if (ctx->pool.size() >= 16) { // full: drop the buffer that has waited longest, the steady-state sizes stay cached
-        cudaFree(ctx->pool.front().p);
-        if (rid_tracing()) fprintf(stderr, "[rid] pool full: cudaFree %.1f MB took %.2f ms\n", ctx->pool.front().bytes / 1e6, now_ms() - t0);
-        ctx->pool.erase(ctx->pool.begin());
+        for (size_t i = 0; i < ctx->pool.size(); ++i) {
+            if (is_exported(ctx, ctx->pool[i].p)) continue; // a peer may have it mapped (CUDA IPC)
+            cudaFree(ctx->pool[i].p);
+            if (rid_tracing()) fprintf(stderr, "[rid] pool full: cudaFree %.1f MB took %.2f ms\n", ctx->pool[i].bytes / 1e6, now_ms() - t0);
+            ctx->pool.erase(ctx->pool.begin() + i);
+            break;
+        }
     }
     ctx->pool.push_back({p, bytes});
 }
@@ -246,8 +275,13 @@ void *rid_pinned(rid_ctx *ctx, size_t bytes)
 
 void rid_pool_trim(rid_ctx *ctx)
 {
-    for (auto &b : ctx->pool) cudaFree(b.p);
-    ctx->pool.clear();
+    // buffers whose IPC handle went out stay (freeing memory a peer still has mapped is undefined behaviour)
+    std::vector<rid_ctx::PoolBuf> keep;
+    for (auto &b : ctx->pool) {
+        if (is_exported(ctx, b.p)) keep.push_back(b);
+        else cudaFree(b.p);
+    }
+    ctx->pool.swap(keep);
 }
 
 // ---- per-kernel profiling -------------------------------------------------------------------------------
@@ -326,7 +360,8 @@ extern "C" int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, 
     if (ctx->prof_dev && (kind == RID_PROF_SCAN_BUILD || kind == RID_PROF_SCAN_DELTA)) {
         // passes sized on the device: their work was counted there (cells -> bytes)
         u64 h[4];
-        RID_CUDA(cudaMemcpy(h, ctx->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        RID_CUDA(cudaMemcpyAsync(h, ctx->prof_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
         const int o = kind == RID_PROF_SCAN_BUILD ? 0 : 2;
         w += 4.0 * (double)h[o];
         tr += 4.0 * (double)h[o + 1];
@@ -399,6 +434,29 @@ int rid_barrier(rid_ctx *ctx)
     return rid_allreduce_i32(ctx, (int *)ctx->scratch + 512, 1);
 }
 
+// base of the allocation a device pointer lies in (cuMemGetAddressRange through the runtime's driver entry points)
+static void *alloc_base(void *p)
+{
+    typedef int (*PFN_range)(unsigned long long *, size_t *, unsigned long long);
+    static PFN_range fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_range)f;
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return p;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return p;
+    return (void *)(uintptr_t)base;
+}
+
 int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok)
 {
     *all_ok = 0;
@@ -408,34 +466,44 @@ int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok)
     if (ctx->world > 16 || !ctx->nccl->AllGather) return RID_OK;
     RID_TRY(ensure_scratch(ctx));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    // record: 64-byte handle of the ALLOCATION + 8-byte offset of `mine` inside it (cudaIpcOpenMemHandle returns the base)
+    const size_t REC = 72;
+    unsigned char rec[72];
+    void *base = alloc_base(mine);
     cudaIpcMemHandle_t h;
-    int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+    int ok = cudaIpcGetMemHandle(&h, base) == cudaSuccess ? 1 : 0;
     if (!ok) { cudaGetLastError(); memset(&h, 0, sizeof(h)); }
-    unsigned char *dev = (unsigned char *)ctx->scratch; // world * 64 bytes <= 1024
-    RID_CUDA(cudaMemcpyAsync(dev + 64 * ctx->rank, &h, 64, cudaMemcpyHostToDevice, ctx->stream));
-    RID_NCCL(ctx->nccl, ctx->nccl->AllGather(dev + 64 * ctx->rank, dev, 64, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
-    unsigned char all[16 * 64];
-    RID_CUDA(cudaMemcpyAsync(all, dev, 64 * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    const unsigned long long off = (unsigned long long)((char *)mine - (char *)base);
+    memcpy(rec, &h, 64);
+    memcpy(rec + 64, &off, 8);
+    if (ok && !is_exported(ctx, base)) ctx->exported.push_back(base);
+    unsigned char *dev = (unsigned char *)ctx->scratch; // world * 72 bytes <= 1152 (the barrier / flag words sit at 2048+)
+    RID_CUDA(cudaMemcpyAsync(dev + REC * ctx->rank, rec, REC, cudaMemcpyHostToDevice, ctx->stream));
+    RID_NCCL(ctx->nccl, ctx->nccl->AllGather(dev + REC * ctx->rank, dev, REC, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    unsigned char all[16 * 72];
+    RID_CUDA(cudaMemcpyAsync(all, dev, REC * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < ctx->world && ok; ++r) {
         if (r == ctx->rank) continue;
         void *ptr = nullptr;
         for (auto &m : ctx->ipc)
-            if (memcmp(m.handle, all + 64 * r, 64) == 0) { ptr = m.ptr; break; }
+            if (memcmp(m.handle, all + REC * r, 64) == 0) { ptr = m.ptr; break; }
         if (!ptr) {
             cudaIpcMemHandle_t ph;
-            memcpy(&ph, all + 64 * r, 64);
+            memcpy(&ph, all + REC * r, 64);
             if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
                 break;
             }
             rid_ctx::IpcMap m;
-            memcpy(m.handle, all + 64 * r, 64);
+            memcpy(m.handle, all + REC * r, 64);
             m.ptr = ptr;
             ctx->ipc.push_back(m);
         }
-        peers[r] = ptr;
+        unsigned long long poff = 0;
+        memcpy(&poff, all + REC * r + 64, 8);
+        peers[r] = (char *)ptr + poff;
     }
     // every rank must take the same path
     int *flag = (int *)ctx->scratch + 600;
@@ -446,4 +514,73 @@ int rid_peer_pointers(rid_ctx *ctx, void *mine, void **peers, int *all_ok)
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     *all_ok = sum == ctx->world ? 1 : 0;
     return RID_OK;
+}
+
+int rid_agree_all(rid_ctx *ctx, int ok, int *all_ok)
+{
+    *all_ok = ok ? 1 : 0;
+    if (ctx->world == 1) return RID_OK;
+    RID_TRY(ensure_scratch(ctx));
+    int *flag = (int *)ctx->scratch + 680;
+    int v = ok ? 1 : 0;
+    RID_CUDA(cudaMemcpyAsync(flag, &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_TRY(rid_allreduce_i32(ctx, flag, 1));
+    RID_CUDA(cudaMemcpyAsync(&v, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    *all_ok = v == ctx->world ? 1 : 0;
+    return RID_OK;
+}
+
+int rid_ipc_release_all(rid_ctx *ctx)
+{
+    if (ctx->world == 1) return RID_OK;
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) RID_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    for (auto &m : ctx->ipc) cudaIpcCloseMemHandle(m.ptr);
+    ctx->ipc.clear();
+    RID_TRY(rid_barrier(ctx)); // nobody holds a mapping of anybody's buffer any more
+    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->exported.clear();
+    return RID_OK;
+}
+
+// ---- cancellation ---------------------------------------------------------------------------------------------
+extern "C" int rid_ctx_request_abort(rid_ctx *ctx)
+{
+    if (!ctx) return RID_ERR_ARG;
+    ctx->abort_flag = 1;
+    return RID_OK;
+}
+extern "C" int rid_ctx_clear_abort(rid_ctx *ctx)
+{
+    if (!ctx) return RID_ERR_ARG;
+    ctx->abort_flag = 0;
+    return RID_OK;
+}
+extern "C" int rid_ctx_set_interrupt_poll(rid_ctx *ctx, int (*poll)(void *), void *arg)
+{
+    if (!ctx) return RID_ERR_ARG;
+    ctx->poll_fn = poll;
+    ctx->poll_arg = arg;
+    return RID_OK;
+}
+
+int rid_check_abort(rid_ctx *ctx, bool collective)
+{
+    int want = ctx->abort_flag ? 1 : 0;
+    if (!want && ctx->poll_fn && ctx->poll_fn(ctx->poll_arg)) want = 1;
+    if (ctx->world > 1) {
+        if (!collective) return RID_OK; // a rank must never leave a collective sequence on its own
+        RID_TRY(ensure_scratch(ctx));
+        int *flag = (int *)ctx->scratch + 640;
+        RID_CUDA(cudaMemcpyAsync(flag, &want, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        RID_TRY(rid_allreduce_i32(ctx, flag, 1));
+        RID_CUDA(cudaMemcpyAsync(&want, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (!want) return RID_OK;
+    ctx->abort_flag = 0;
+    cudaStreamSynchronize(ctx->stream);
+    rid_set_error("interrupted: the caller asked for cancellation");
+    return RID_ERR_INTERRUPTED;
 }

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
                             d2 += dv * dv;
                         }
                     }
-                    v = (u32)__double2ull_rn(sqrt(fmax(d2, 0.0)) * P.inv_step);
+                    v = (u32)min(__double2ull_rn(sqrt(fmax(d2, 0.0)) * P.inv_step), 0x7FFFFFFFull); // q < 2^31: two rows add up in 32 bits
                 }
                 q[e] = v;
             }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gram_dmma(GramParams P)
 // ----------------------------------------------------------------------------------------------------------
 // src: N x N column-major doubles (device).  Lower triangle is authoritative (as.dist): D(a,b) = src[max,min].
 __global__ void k_import(const double *__restrict__ src, int N, int row0, int nloc, u32 *__restrict__ D, size_t ld,
-                         double inv_step, int *has_na)
+                         double inv_step, u32 qmax, int *has_na)
 {
     size_t col = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
     int lrow = blockIdx.x;
@@ -354,7 +354,7 @@ __global__ void k_import(const double *__restrict__ src, int N, int row0, int nl
         int hi = max(r, (int)col), lo = min(r, (int)col);
         double d = src[(size_t)lo * N + hi];
         if (isnan(d)) { v = RID_Q_NA; *has_na = 1; }
-        else v = (u32)__double2ull_rn(d * inv_step);
+        else v = (u32)min(__double2ull_rn(d * inv_step), (unsigned long long)qmax);
     }
     D[(size_t)lrow * ld + col] = v;
 }
@@ -370,6 +370,26 @@ __global__ void k_export(const u32 *__restrict__ D, size_t ld, int row0, int row
     if (r < row0 || r >= row1) return;
     u32 q = D[(size_t)(r - row0) * ld + c];
     out[(size_t)b * m + a] = q == RID_Q_NA ? __longlong_as_double(0x7ff8000000000000LL) : (double)q * step;
+}
+
+// euclidean matrices whose range makes the 31-bit grid coarser than the 1e-6 budget: exported distances are recomputed
+// from the retained feature rows in FP64 difference form, like stats::dist (sum of squared differences, then sqrt)
+__global__ void k_export_exact(const double *__restrict__ x, int ldx, int G, int row0, int row1,
+                               const int *__restrict__ ridx, int m, const int *__restrict__ cidx, int c_first, int n,
+                               double *__restrict__ out)
+{
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (a >= m || b >= n) return;
+    int r = ridx ? ridx[a] : a, c = cidx ? cidx[b] : c_first + b;
+    if (r < row0 || r >= row1) return;
+    const double *xa = x + (size_t)r * ldx, *xb = x + (size_t)c * ldx;
+    double d2 = 0.0;
+    for (int k = 0; k < G; ++k) {
+        const double dv = xa[k] - xb[k];
+        d2 += dv * dv;
+    }
+    out[(size_t)b * m + a] = sqrt(d2);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -396,6 +416,9 @@ extern "C" int rid_shard_rows(int N, int rank, int world, int *row0, int *row1)
     return RID_OK;
 }
 
+// Multi-rank: when the whole matrix fits next to the work buffers on EVERY rank, each rank allocates all N rows and
+// its shard is the row block [row0, row1) inside that buffer; the other blocks are pulled over NVLink later
+// (rid_replica_start).  Otherwise only the shard is allocated and every clustering phase runs cooperatively.
 static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
 {
     rid_dmat *dm = new rid_dmat();
@@ -404,14 +427,46 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
     shard_rows(N, ctx->rank, ctx->world, &dm->row0, &dm->row1);
     dm->ld = round_up((size_t)N, 128);
     size_t nloc = (size_t)(dm->row1 - dm->row0);
-    if (ctx->world > 1) { // every shard is allocated at the size of rank 0's (equal counts for ncclAllGather)
+    if (ctx->world > 1) { // every shard is allocated at the size of rank 0's
         int r0, r1;
         shard_rows(N, 0, ctx->world, &r0, &r1);
         dm->alloc_rows = (size_t)std::max(r1 - r0, 1);
     } else {
         dm->alloc_rows = std::max<size_t>(nloc, 1);
     }
-    cudaError_t e = rid_pool_alloc(ctx, (void **)&dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
+    const size_t shard_bytes = dm->alloc_rows * dm->ld * sizeof(u32);
+    cudaError_t e = cudaSuccess;
+    if (ctx->world > 1) {
+        // mappings of buffers nobody uses any more pile up when shapes change: drop them while no sharded matrix lives
+        if (ctx->live_sharded == 0 && ctx->exported.size() > 4) {
+            int rc = rid_ipc_release_all(ctx);
+            if (rc != RID_OK) { delete dm; return rc; }
+        }
+        const size_t full_bytes = (size_t)ctx->world * shard_bytes;
+        int want = getenv("RID_NO_REPLICA") ? 0 : 1;
+        void *buf = nullptr;
+        if (want) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            for (auto &b : ctx->pool) free_b += b.bytes; // cached buffers are given back on demand
+            // replica + a compact bootstrap copy (~0.45 N^2 words) + operands / accumulators + slack
+            const size_t need = full_bytes + (size_t)(0.45 * (double)N * (double)dm->ld * 4.0) + ((size_t)6 << 30);
+            if (free_b < need || rid_pool_alloc(ctx, &buf, full_bytes) != cudaSuccess) { cudaGetLastError(); buf = nullptr; want = 0; }
+        }
+        int all = 0;
+        int rc = rid_agree_all(ctx, want, &all);
+        if (rc != RID_OK) { if (buf) rid_pool_free(ctx, buf, full_bytes); delete dm; return rc; }
+        if (all) {
+            dm->full = (u32 *)buf;
+            dm->full_bytes = full_bytes;
+            dm->D = dm->full + (size_t)ctx->rank * dm->alloc_rows * dm->ld;
+        } else {
+            if (buf) rid_pool_free(ctx, buf, full_bytes); // some rank cannot hold the replica: everybody shards
+            e = rid_pool_alloc(ctx, (void **)&dm->D, shard_bytes);
+        }
+    } else {
+        e = rid_pool_alloc(ctx, (void **)&dm->D, shard_bytes);
+    }
     if (e == cudaSuccess && dm->alloc_rows > nloc) // rows nobody owns (last rank): keep them defined
         cudaMemsetAsync(dm->D + nloc * dm->ld, 0, (dm->alloc_rows - nloc) * dm->ld * sizeof(u32), ctx->stream);
     if (e != cudaSuccess) {
@@ -420,17 +475,98 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
         delete dm;
         return RID_ERR_NOMEM;
     }
+    if (ctx->world > 1) {
+        // every rank's row block, mapped once per matrix (CUDA IPC; cached per allocation): the distance kernels store
+        // mirror tiles through these pointers, the replica pulls read through them
+        void *peers[16];
+        int ok = 0;
+        int rc = rid_peer_pointers(ctx, dm->D, peers, &ok);
+        if (rc != RID_OK) { rid_pool_free(ctx, dm->full ? (void *)dm->full : (void *)dm->D, dm->full ? dm->full_bytes : shard_bytes); delete dm; return rc; }
+        dm->peers_ok = ok;
+        for (int r = 0; r < ctx->world; ++r) {
+            dm->peer_shard[r] = ok ? (u32 *)peers[r] : nullptr;
+            dm->peer_full[r] = (ok && dm->full) ? (u32 *)peers[r] - (size_t)r * dm->alloc_rows * dm->ld : nullptr;
+        }
+        ctx->live_sharded++;
+    }
     *out = dm;
     return RID_OK;
 }
 
+// Pull the other ranks' row blocks into dm->full with the copy engines.  Call after the barrier that ends the distance
+// kernels (every shard complete everywhere).  Only columns >= replica_lo[s] of block s are fetched at first: the
+// symmetric compaction of a bootstrap replicate reads nothing else (plus a margin for its diagonal super-tiles);
+// rid_replica_complete fetches the rest on demand.  One-sided: no rank waits for another here.
+#define RID_REPLICA_MARGIN 4096
+int rid_replica_start(rid_dmat *dm)
+{
+    rid_ctx *ctx = dm->ctx;
+    if (ctx->world == 1 || !dm->full || !dm->peers_ok || dm->replica_state != 0) return RID_OK;
+    if (!dm->replica_ev) RID_CUDA(cudaEventCreateWithFlags(&dm->replica_ev, cudaEventDisableTiming));
+    RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->stream));
+    RID_CUDA(cudaStreamWaitEvent(ctx->copy_stream, dm->replica_ev, 0));
+    const bool whole = getenv("RID_REPLICA_FULL") != nullptr;
+    const int margin = getenv("RID_REPLICA_MARGIN") ? std::max(0, atoi(getenv("RID_REPLICA_MARGIN"))) : RID_REPLICA_MARGIN;
+    bool all_whole = true;
+    for (int i = 1; i < ctx->world; ++i) {
+        const int s = (ctx->rank + i) % ctx->world; // staggered: in round i every source serves one destination
+        int r0, r1;
+        shard_rows(dm->N, s, ctx->world, &r0, &r1);
+        if (r1 <= r0) continue;
+        size_t lo = whole ? 0 : (size_t)std::max(0, r0 - margin) & ~(size_t)31;
+        dm->replica_lo[s] = (int)lo;
+        if (lo) all_whole = false;
+        const size_t off = (size_t)s * dm->alloc_rows * dm->ld + lo;
+        RID_CUDA(cudaMemcpy2DAsync(dm->full + off, dm->ld * sizeof(u32), dm->peer_full[s] + off, dm->ld * sizeof(u32),
+                                   (dm->ld - lo) * sizeof(u32), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    }
+    dm->replica_lo[ctx->rank] = 0;
+    RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->copy_stream));
+    dm->replica_state = all_whole ? 2 : 1;
+    return RID_OK;
+}
+
+int rid_replica_complete(rid_dmat *dm)
+{
+    rid_ctx *ctx = dm->ctx;
+    if (ctx->world == 1 || !dm->full) return RID_OK;
+    if (dm->replica_state == 0) RID_TRY(rid_replica_start(dm));
+    if (dm->replica_state == 2) return RID_OK;
+    for (int i = 1; i < ctx->world; ++i) {
+        const int s = (ctx->rank + i) % ctx->world;
+        int r0, r1;
+        shard_rows(dm->N, s, ctx->world, &r0, &r1);
+        const size_t lo = (size_t)dm->replica_lo[s];
+        if (r1 <= r0 || lo == 0) continue;
+        const size_t off = (size_t)s * dm->alloc_rows * dm->ld;
+        RID_CUDA(cudaMemcpy2DAsync(dm->full + off, dm->ld * sizeof(u32), dm->peer_full[s] + off, dm->ld * sizeof(u32),
+                                   lo * sizeof(u32), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        dm->replica_lo[s] = 0;
+    }
+    RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->copy_stream));
+    dm->replica_state = 2;
+    return RID_OK;
+}
+
+// Multi-rank: every rank must free a sharded matrix before the next rid_dist / rid_dmat_from_host call reuses its
+// buffer (the peers' pulls read it); the local synchronisation below is all that is needed then.
 extern "C" int rid_dmat_free(rid_dmat *dm)
 {
     if (!dm) return RID_OK;
-    cudaSetDevice(dm->ctx->device);
-    cudaStreamSynchronize(dm->ctx->stream);
-    rid_pam_ws_free(dm->ws, dm->ctx);
-    rid_pool_free(dm->ctx, dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
+    rid_ctx *ctx = dm->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (dm->replica_view) {
+        rid_pam_ws_free(dm->replica_view->ws, ctx);
+        delete dm->replica_view;
+    }
+    rid_pam_ws_free(dm->ws, ctx);
+    if (dm->replica_ev) cudaEventDestroy(dm->replica_ev);
+    if (dm->xraw) rid_pool_free(ctx, dm->xraw, dm->xraw_bytes);
+    if (dm->full) rid_pool_free(ctx, dm->full, dm->full_bytes);
+    else rid_pool_free(ctx, dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
+    if (ctx->world > 1 && ctx->live_sharded > 0) ctx->live_sharded--;
     delete dm;
     return RID_OK;
 }
@@ -567,14 +703,9 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
             P.tiles_per_rank = std::max(1, (int)(round_up((size_t)std::max(r1 - r0, 1), GM_BM) / GM_BM));
         }
         for (int r = 0; r < 16; ++r) P.peer[r] = nullptr;
-        if (ctx->world > 1) {
-            void *peers[16];
-            int all_ok = 0;
-            if ((rc = rid_peer_pointers(ctx, dm->D, peers, &all_ok)) != RID_OK) return fail(rc);
-            if (all_ok) {
-                P.psym = 1;
-                for (int r = 0; r < ctx->world; ++r) P.peer[r] = (u32 *)peers[r];
-            }
+        if (ctx->world > 1 && dm->peers_ok) {
+            P.psym = 1;
+            for (int r = 0; r < ctx->world; ++r) P.peer[r] = dm->peer_shard[r];
         }
         double tiles_done = 0.0;
         {
@@ -606,6 +737,12 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         // peers have written mirror tiles into this rank's shard: nobody may go on before every kernel is done
         if (P.psym && (rc = rid_barrier(ctx)) != RID_OK) return fail(rc);
     }
+    // every shard is complete on every rank (both tensor paths end with a barrier): the copy engines start pulling the
+    // other ranks' row blocks into the replica while the first clustering phase runs on the shard
+    if (ctx->world > 1 && dm->full) {
+        // (the pulls need the peers' pointers, and with those both paths have just passed their closing barrier)
+        if ((rc = rid_replica_start(dm)) != RID_OK) return fail(rc);
+    }
     // zero-variance cells (cor(): NA + warning "the standard deviation is zero")
     dm->na_cell.assign(N, 0);
     DCHK(cudaMemcpyAsync(dm->na_cell.data(), zv, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -614,7 +751,13 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     for (int i = 0; i < N; ++i) nz += dm->na_cell[i];
     dm->has_na = nz > 0;
     if (n_zero_var) *n_zero_var = nz;
-    rid_pool_free(ctx, Z, z_bytes); rid_pool_free(ctx, aux, aux_bytes);
+    if (metric == RID_EUCLIDEAN && dm->step > 2e-6) {
+        // the grid alone would miss the 1e-6 budget (error up to step / 2): keep the raw rows for exact exports
+        dm->xraw = Z; dm->xraw_bytes = z_bytes; dm->xraw_G = G; dm->xraw_ld = Gp;
+    } else {
+        rid_pool_free(ctx, Z, z_bytes);
+    }
+    rid_pool_free(ctx, aux, aux_bytes);
     if (!x_on_device) rid_pool_free(ctx, xd, x_bytes);
     *out = dm;
     return RID_OK;
@@ -637,12 +780,14 @@ extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat
     if (neg) { rid_set_error("negative dissimilarities are not supported"); return RID_ERR_ARG; }
     rid_dmat *dm = nullptr;
     RID_TRY(dmat_alloc(ctx, N, &dm));
-    if (mx <= 2.0) {
+    if (mx > 1.0 && mx <= 2.0) {
         dm->bits = 28;
         dm->step = ldexp(1.0, -27);
     } else {
+        // (also for small ranges: a fixed 2^-27 step would turn a matrix with maximum 1e-4 into a few thousand levels
+        // and create ties the real values do not have)
         int e = 0;
-        frexp(mx, &e); // mx < 2^e (or == 2^(e-1))
+        frexp(mx > 0.0 ? mx : 1.0, &e); // mx < 2^e (or == 2^(e-1))
         dm->bits = 31;
         dm->step = ldexp(1.0, e - 31);
     }
@@ -659,7 +804,8 @@ extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat
     int nloc = dm->row1 - dm->row0;
     if (nloc > 0) {
         dim3 grid((unsigned)nloc, (unsigned)((dm->ld + 255) / 256));
-        LAUNCH(ctx, k_import, grid, 256, 0, src, N, dm->row0, nloc, dm->D, dm->ld, 1.0 / dm->step, flag);
+        LAUNCH(ctx, k_import, grid, 256, 0, src, N, dm->row0, nloc, dm->D, dm->ld, 1.0 / dm->step,
+               dm->bits <= 28 ? (u32)(1u << 28) : 0x7FFFFFFFu, flag);
     }
     int h = 0;
     cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
@@ -676,6 +822,10 @@ extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat
         for (int r = c + 1; r < N; ++r)
             if (D[(size_t)c * N + r] != D[(size_t)c * N + r]) { h = 1; break; }
     dm->has_na = h;
+    if (ctx->world > 1 && dm->full && dm->peers_ok) {
+        // every rank has imported its own rows: let the copy engines fetch the others
+        if ((rc = rid_barrier(ctx)) != RID_OK || (rc = rid_replica_start(dm)) != RID_OK) { rid_dmat_free(dm); return rc; }
+    }
     *out = dm;
     return RID_OK;
 }
@@ -693,15 +843,19 @@ extern "C" int rid_dmat_sub(rid_dmat *dm, const int *ridx, int m, const int *cid
     // export in column panels to bound the staging buffer
     const int panel = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)n, 65535), ((size_t)256 << 20) / ((size_t)m * 8)));
     RID_CUDA(cudaMalloc(&d_out, (size_t)m * panel * sizeof(double)));
-    if (ridx) { RID_CUDA(cudaMalloc(&d_r, (size_t)m * sizeof(int))); RID_CUDA(cudaMemcpy(d_r, ridx, (size_t)m * sizeof(int), cudaMemcpyHostToDevice)); }
-    if (cidx) { RID_CUDA(cudaMalloc(&d_c, (size_t)n * sizeof(int))); RID_CUDA(cudaMemcpy(d_c, cidx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice)); }
+    // (uploads on the library's own stream: it is non-blocking, i.e. not ordered against the legacy default stream)
+    if (ridx) { RID_CUDA(cudaMalloc(&d_r, (size_t)m * sizeof(int))); RID_CUDA(cudaMemcpyAsync(d_r, ridx, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
+    if (cidx) { RID_CUDA(cudaMalloc(&d_c, (size_t)n * sizeof(int))); RID_CUDA(cudaMemcpyAsync(d_c, cidx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); }
     int rc = RID_OK;
     for (int c0 = 0; c0 < n && rc == RID_OK; c0 += panel) {
         int nc = std::min(panel, n - c0);
         cudaMemsetAsync(d_out, 0, (size_t)m * nc * sizeof(double), ctx->stream);
         dim3 grid((unsigned)((m + 127) / 128), (unsigned)nc);
         // without a column list the panel's columns are c0.. ; shift through a pointer offset on the matrix
-        if (d_c)
+        if (dm->xraw)
+            LAUNCH(ctx, k_export_exact, grid, 128, 0, dm->xraw, dm->xraw_ld, dm->xraw_G, dm->row0, dm->row1, d_r, m,
+                   d_c ? d_c + c0 : (const int *)nullptr, c0, nc, d_out);
+        else if (d_c)
             LAUNCH(ctx, k_export, grid, 128, 0, dm->D, dm->ld, dm->row0, dm->row1, d_r, m, d_c + c0, nc, dm->step, d_out);
         else
             LAUNCH(ctx, k_export, grid, 128, 0, dm->D + c0, dm->ld, dm->row0, dm->row1, d_r, m, (const int *)nullptr, nc, dm->step, d_out);
@@ -838,22 +992,28 @@ extern "C" int rid_dist_csc(rid_ctx *ctx, const int *row_idx, const int *col_ptr
     }
     double mincount = counts[0];
     for (int c = 1; c < N; ++c) mincount = std::min(mincount, counts[c]);
+    // one pooled staging buffer (exact-size reuse: a repeated compdist() on the same object allocates nothing)
     int *d_i = nullptr, *d_p = nullptr, *d_f = nullptr;
     double *d_v = nullptr, *d_c = nullptr, *d_x = nullptr;
     const size_t x_bytes = (size_t)G * N * sizeof(double);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_v = 0, o_c = o_v + al(std::max<size_t>(nnz, 1) * sizeof(double)), o_i = o_c + al((size_t)N * sizeof(double)),
+                 o_p = o_i + al(std::max<size_t>(nnz, 1) * sizeof(int)), o_f = o_p + al(((size_t)N + 1) * sizeof(int)),
+                 st_bytes = std::max<size_t>(o_f + al((size_t)n_rows_all * sizeof(int)), (size_t)256 << 10);
+    char *stage = nullptr;
     int rc = RID_OK;
     auto done = [&](int code) {
-        cudaFree(d_i); cudaFree(d_p); cudaFree(d_f); cudaFree(d_v); cudaFree(d_c);
+        rid_pool_free(ctx, stage, st_bytes);
         rid_pool_free(ctx, d_x, x_bytes);
         return code;
     };
-    if (cudaMalloc(&d_i, std::max<size_t>(nnz, 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&d_p, ((size_t)N + 1) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&d_f, (size_t)n_rows_all * sizeof(int)) != cudaSuccess || cudaMalloc(&d_v, std::max<size_t>(nnz, 1) * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&d_c, (size_t)N * sizeof(double)) != cudaSuccess || rid_pool_alloc(ctx, (void **)&d_x, x_bytes) != cudaSuccess) {
+    if (rid_pool_alloc(ctx, (void **)&stage, st_bytes) != cudaSuccess || rid_pool_alloc(ctx, (void **)&d_x, x_bytes) != cudaSuccess) {
         rid_set_error("rid_dist_csc: out of device memory");
         cudaGetLastError();
         return done(RID_ERR_NOMEM);
     }
+    d_v = (double *)(stage + o_v); d_c = (double *)(stage + o_c); d_i = (int *)(stage + o_i); d_p = (int *)(stage + o_p);
+    d_f = (int *)(stage + o_f);
     cudaMemcpyAsync(d_i, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_p, col_ptr, ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_f, feat.data(), (size_t)n_rows_all * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);

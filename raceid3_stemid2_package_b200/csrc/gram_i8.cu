@@ -876,9 +876,8 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
     for (int r = 0; r < 16; ++r) peers[r] = nullptr;
     peers[0] = dm->D;
     if (ctx->world > 1) {
-        int all_ok = 0;
-        RID_TRY(rid_peer_pointers(ctx, dm->D, peers, &all_ok));
-        if (!all_ok) return RID_OK;
+        if (!dm->peers_ok) return RID_OK; // (mapped once per matrix by dmat_alloc; the same answer on every rank)
+        for (int r = 0; r < ctx->world; ++r) peers[r] = dm->peer_shard[r];
     }
     PFN_encodeTiled encode = get_encode();
     if (!encode) return RID_OK;
@@ -981,8 +980,9 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
                     if (cudaMalloc(&ctx->i8_tiles, bytes) != cudaSuccess) { cudaGetLastError(); cleanup(); return RID_OK; }
                     ctx->i8_tiles_bytes = bytes;
                 }
-                // (synchronous copy: `list` is a local)
-                if (cudaMemcpy(ctx->i8_tiles, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
+                // (`list` is a local: copy on the library's stream and wait for it)
+                if (cudaMemcpyAsync(ctx->i8_tiles, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
                     cudaGetLastError(); cleanup(); return RID_OK;
                 }
                 memcpy(ctx->i8_tiles_key, key, sizeof(key));
@@ -1054,5 +1054,79 @@ int rid_gram_i8(rid_ctx *ctx, const double *Z, int Gp_src, int G, int N, const u
         return RID_ERR_CUDA;
     }
     *used = 1;
+    return RID_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Ceiling of the int8 tensor pipe, measured on the spot (MEASURED_PEAKS.json holds a bf16 figure only): one CTA per SM
+// issues a long stream of the same tcgen05.mma.kind::i8 instructions the distance kernel uses (M = 128, N = 192, K = 32,
+// operands in SWIZZLE_128B shared memory, two TMEM accumulators) with no loads and no epilogue.
+// ----------------------------------------------------------------------------------------------------------
+#define I8PK_SMEM (I8_A_PLANE + 2 * I8_B_PLANE + 1024)
+__global__ void __launch_bounds__(128, 1) k_i8_peak(int iters)
+{
+    extern __shared__ uint8_t pk_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)pk_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t done_bar;
+    __shared__ uint32_t tmem_slot;
+    for (int i = threadIdx.x; i < (I8_A_PLANE + 2 * I8_B_PLANE) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0x01010101u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 1 && lane == 0) {
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(I8_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 1 && lane == 0) {
+        const uint32_t sa = smem_u32(smem), sb = sa + I8_A_PLANE;
+        const uint64_t A = umma_desc_sw128(sa), B = umma_desc_sw128(sb);
+        constexpr uint32_t ID192 = I8_IDESC_N(2 * I8_BN);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                umma_i8(tmem_base, A + 2 * kk, B + 2 * kk, (it | kk) ? 1u : 0u, ID192);
+                umma_i8(tmem_base + 2 * I8_BN, A + 2 * kk, B + 2 * kk, (it | kk) ? 1u : 0u, ID192);
+            }
+        }
+        umma_commit(&done_bar);
+    }
+    // (bounded wait, 2^26 polls: far beyond the ~ms this loop takes)
+    mbar_wait(&done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+}
+
+extern "C" int rid_measure_i8_peak(rid_ctx *ctx, double *tops)
+{
+    if (!ctx || !tops) return RID_ERR_ARG;
+    RID_CUDA(cudaSetDevice(ctx->device));
+    RID_CUDA(cudaFuncSetAttribute(k_i8_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, I8PK_SMEM));
+    const int iters = 4000, blocks = ctx->sm_count;
+    k_i8_peak<<<blocks, 128, I8PK_SMEM, ctx->stream>>>(200); // warm-up
+    cudaEvent_t a, b;
+    RID_CUDA(cudaEventCreate(&a));
+    RID_CUDA(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        RID_CUDA(cudaEventRecord(a, ctx->stream));
+        k_i8_peak<<<blocks, 128, I8PK_SMEM, ctx->stream>>>(iters);
+        RID_CUDA(cudaEventRecord(b, ctx->stream));
+        RID_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        RID_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best) best = ms;
+    }
+    RID_CUDA(cudaGetLastError());
+    // 8 instructions per iteration, each 2 * 128 * 192 * 32 int8 operations
+    *tops = (double)blocks * iters * 8.0 * 2.0 * I8_BM * (2.0 * I8_BN) * 32.0 / (best * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b);
     return RID_OK;
 }

@@ -1250,6 +1250,16 @@ static inline const int *stage_table(int *&pin, const std::vector<int> &v)
     return dst;
 }
 
+static bool replica_upper_suffices(const rid_dmat *parent, const std::vector<int> &ccells);
+// a replica view whose parent has pulled only part of the peers' row blocks: fetch the rest and wait for it
+static int replica_need_whole(rid_dmat *dm)
+{
+    if (!dm->parent || dm->parent->replica_state == 2) return RID_OK;
+    RID_TRY(rid_replica_complete(dm->parent));
+    RID_CUDA(cudaStreamWaitEvent(dm->ctx->stream, dm->parent->replica_ev, 0));
+    return RID_OK;
+}
+
 static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = nullptr)
 {
     rid_ctx *ctx = dm->ctx;
@@ -1293,6 +1303,8 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
                 RID_CUDA(cudaMemcpyAsync(w->src_rows, stage_table(pin, H.src), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 // complete view (rows == columns == the sorted subset): gather the upper triangle only and mirror it
                 const bool sym = w->nls == m && dm->row0 == 0 && dm->row1 == N && !getenv("RID_COMPACT_FULL");
+                // (a replica that holds only the upper part of the peers' blocks serves the symmetric gather, nothing else)
+                if (dm->parent && !(sym && replica_upper_suffices(dm->parent, H.ccells))) RID_TRY(replica_need_whole(dm));
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 if (sym) {
                     // (per device and cheap: set on every call rather than once per process)
@@ -1323,6 +1335,7 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
         }
     }
     // view mode: rows of the resident shard through a row list, columns masked by the candidate list
+    RID_TRY(replica_need_whole(dm)); // (whole rows are read)
     w->compact = false;
     w->sp0_ready = false;
     w->mat = dm->D;
@@ -1603,7 +1616,8 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resum
             h_state->td = h_state->td_build;
             break;
         }
-        if (h_state->done) break;
+        if (h_state->done) { if (ctx->rank == 0) ctx->swaps += h_state->nswaps; break; } // (cooperating ranks count once)
+        RID_TRY(rid_check_abort(ctx, false));
     }
     return RID_OK;
 }
@@ -1695,7 +1709,8 @@ static int pam_run(rid_dmat *dm, const int *subset, int m, int k, int *medoids, 
     std::vector<int> slot;
     RID_TRY(pam_collect_labels(dm, w, slot));
     std::vector<int> h_medpos(k);
-    RID_CUDA(cudaMemcpy(h_medpos.data(), w->medpos, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost));
+    RID_CUDA(cudaMemcpyAsync(h_medpos.data(), w->medpos, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, dm->ctx->stream));
+    RID_CUDA(cudaStreamSynchronize(dm->ctx->stream));
     number_clusters(slot, k, h_medpos, labels, medoids);
     if (objective) {
         objective[0] = (double)hs.td_build * dm->step / (double)m;
@@ -1748,7 +1763,8 @@ extern "C" int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int
         if (labels[p] < 1 || labels[p] > k) { rid_set_error("label %d out of 1..%d", labels[p], k); return RID_ERR_ARG; }
         g[p] = labels[p] - 1;
     }
-    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    // (on the library's stream, which is not ordered against the legacy default stream; pageable source: staged on return)
+    RID_CUDA(cudaMemcpyAsync(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, dm->ctx->stream));
     RID_TRY(rid_time_begin(dm->ctx));
     RID_TRY(within_disp(dm, w, k, W, nullptr));
     return rid_time_end(dm->ctx);
@@ -1760,50 +1776,38 @@ extern "C" int rid_within_disp(rid_dmat *dm, const int *subset, int m, const int
 // the replica at single-GPU efficiency (no per-step all-reduce, no latency-bound 1/world-sized passes); otherwise all
 // ranks cooperate on every problem through the row shards.  Results are identical either way (exact integer sums).
 struct FullReplica {
-    rid_dmat full;
-    size_t bytes = 0;
+    rid_dmat *full = nullptr; // view of dm->full as a matrix one GPU owns completely (lives as long as dm does)
     int saved_world = 1, saved_rank = 0;
     bool active = false;
 };
 
+// The replica buffer was allocated with the matrix (dist.cu dmat_alloc) and the copy engines have been pulling the other
+// ranks' row blocks since the distance kernels ended; here the library's stream starts to depend on those copies.
 static int replica_begin(rid_dmat *dm, FullReplica *R)
 {
     rid_ctx *ctx = dm->ctx;
     R->active = false;
-    if (ctx->world == 1 || getenv("RID_NO_REPLICA")) return RID_OK;
-    const size_t bytes = (size_t)ctx->world * dm->alloc_rows * dm->ld * sizeof(u32);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    // replica + a compact bootstrap copy (~0.45 N^2 words) + accumulators + slack
-    const size_t need = bytes + (size_t)(0.45 * (double)dm->N * (double)dm->ld * 4.0) + ((size_t)4 << 30);
-    int miss = free_b >= need ? 0 : 1;
-    void *buf = nullptr;
-    if (!miss && rid_pool_alloc(ctx, &buf, bytes) != cudaSuccess) { cudaGetLastError(); miss = 1; buf = nullptr; }
-    PamWs *w;
-    RID_TRY(ws_get(dm, 1, &w));
-    int *flag = (int *)w->dscratch;
-    RID_CUDA(cudaMemcpyAsync(flag, &miss, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_TRY(rid_allreduce_i32(ctx, flag, 1));
-    RID_CUDA(cudaMemcpyAsync(&miss, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    RID_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (miss) { // some rank cannot hold the replica: everybody cooperates
-        if (buf) rid_pool_free(ctx, buf, bytes);
-        return RID_OK;
+    if (ctx->world == 1 || !dm->full || !dm->peers_ok || getenv("RID_NO_REPLICA")) return RID_OK;
+    RID_TRY(rid_replica_start(dm)); // (no-op when the pulls are already under way)
+    if (dm->replica_state == 0) return RID_OK;
+    RID_CUDA(cudaStreamWaitEvent(ctx->stream, dm->replica_ev, 0));
+    if (!dm->replica_view) {
+        rid_dmat *v = new rid_dmat();
+        v->ctx = ctx;
+        v->N = dm->N;
+        v->row0 = 0;
+        v->row1 = dm->N;
+        v->ld = dm->ld;
+        v->D = dm->full;
+        v->alloc_rows = (size_t)ctx->world * dm->alloc_rows;
+        v->bits = dm->bits;
+        v->step = dm->step;
+        v->parent = dm;
+        dm->replica_view = v;
     }
-    RID_TRY(rid_allgather(ctx, dm->D, buf, dm->alloc_rows * dm->ld * sizeof(u32)));
-    R->full = rid_dmat();
-    R->full.ctx = ctx;
-    R->full.N = dm->N;
-    R->full.row0 = 0;
-    R->full.row1 = dm->N;
-    R->full.ld = dm->ld;
-    R->full.D = (u32 *)buf;
-    R->full.alloc_rows = (size_t)ctx->world * dm->alloc_rows;
-    R->full.bits = dm->bits;
-    R->full.step = dm->step;
-    R->full.has_na = dm->has_na;
-    R->full.na_cell = dm->na_cell;
-    R->bytes = bytes;
+    dm->replica_view->has_na = dm->has_na;
+    dm->replica_view->na_cell = dm->na_cell;
+    R->full = dm->replica_view;
     R->saved_world = ctx->world;
     R->saved_rank = ctx->rank;
     R->active = true;
@@ -1813,7 +1817,7 @@ static int replica_begin(rid_dmat *dm, FullReplica *R)
 static void replica_local(FullReplica *R, bool on)
 {
     if (!R->active) return;
-    rid_ctx *ctx = R->full.ctx;
+    rid_ctx *ctx = R->full->ctx;
     ctx->world = on ? 1 : R->saved_world;
     ctx->rank = on ? 0 : R->saved_rank;
 }
@@ -1821,12 +1825,27 @@ static void replica_end(FullReplica *R)
 {
     if (!R->active) return;
     replica_local(R, false);
-    rid_ctx *ctx = R->full.ctx;
-    cudaStreamSynchronize(ctx->stream);
-    rid_pam_ws_free(R->full.ws, ctx);
-    R->full.ws = nullptr;
-    rid_pool_free(ctx, R->full.D, R->bytes);
     R->active = false;
+}
+
+// A view whose parent has only pulled the columns >= replica_lo[s] of every peer block s: true if the symmetric
+// compaction of this (sorted) subset reads nothing else.  A compact super-tile (bi, bj), bi <= bj, reads source rows
+// ccells[bi*512 ..] x source columns ccells[bj*512 ..]; the smallest column a row of block s ever meets is therefore the
+// first cell of the super-tile row that holds the block's first subset cell.
+static bool replica_upper_suffices(const rid_dmat *parent, const std::vector<int> &ccells)
+{
+    const int world = parent->ctx->world > 1 ? parent->ctx->world : (int)(((size_t)parent->N + parent->alloc_rows - 1) / parent->alloc_rows);
+    const size_t per = parent->alloc_rows;
+    for (int s = 0; s < world && s < 16; ++s) {
+        const int lo = parent->replica_lo[s];
+        if (lo <= 0) continue;
+        const int r0 = (int)std::min<size_t>((size_t)s * per, (size_t)parent->N);
+        const size_t p = (size_t)(std::lower_bound(ccells.begin(), ccells.end(), r0) - ccells.begin());
+        if (p >= ccells.size()) continue; // no subset row in this block
+        const size_t I0 = p / 512 * 512;  // (CS_S)
+        if (ccells[I0] < lo) return false;
+    }
+    return true;
 }
 
 // State of the BUILD medoids of the last k a rank handled in the sweep: accumulators (hdr | SP | AQ[k]) and assignment.
@@ -1871,6 +1890,20 @@ static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamSta
     return pam_swap(dm, w, k, hs, true);
 }
 
+// after a phase in which every rank polled for cancellation on its own: one answer for all
+static int agree_interrupt(rid_ctx *ctx, int rc)
+{
+    if (ctx->world == 1) return rc;
+    int none = 0;
+    int r2 = rid_agree_all(ctx, rc != RID_ERR_INTERRUPTED, &none);
+    if (r2 != RID_OK) return r2;
+    if (!none && rc == RID_OK) {
+        rid_set_error("interrupted: the caller asked for cancellation");
+        return RID_ERR_INTERRUPTED;
+    }
+    return rc;
+}
+
 // clusGapExt's k loop.  BUILD is greedy and does not depend on k, so BUILD(k) is the first k picks of
 // BUILD(Kmax): run it once and start SWAP(k) from the k-prefix (identical results, Kmax instead of
 // Kmax(Kmax+1)/2 BUILD passes).
@@ -1887,7 +1920,7 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     int *d_order = nullptr;
     RID_CUDA(cudaMalloc(&d_order, (size_t)Kmax * sizeof(int)));
-    RID_CUDA(cudaMemcpy(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice));
+    RID_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int rc = RID_OK;
     // Labels of every k this rank owns are kept by column (bytes); W.k is then evaluated for WB values of k per pass
     // over the matrix instead of one pass per k.
@@ -1923,6 +1956,7 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
         logW[k - 1] = 0.0;
         if ((k - 1) % nshare != myshare) continue; // another rank's k
+        if ((rc = rid_check_abort(ctx, nshare == 1)) != RID_OK) break;
         double W = 0.0;
         if (k == 1) {
             rc = cudaMemsetAsync(w->lab_pos, 0, (size_t)m * sizeof(int), ctx->stream) == cudaSuccess ? RID_OK : RID_ERR_CUDA;
@@ -2001,13 +2035,20 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
     RID_TRY(pam_check_na(dm, subset, m));
     rid_ctx *ctx = dm->ctx;
     RID_TRY(rid_time_begin(ctx));
+    // Several ranks cooperate on the row shards: every pass reads 1/world of the bytes per rank and needs no replica
+    // (measured equal to splitting the k values over full replicas, which repeats the shared BUILD on every rank and
+    // needs the complete matrix everywhere first).  RID_SWEEP_REPLICA=1 selects the replica schedule: every rank repeats
+    // the shared BUILD and takes every world-th k.
     FullReplica R;
-    RID_TRY(replica_begin(dm, &R));
+    if (getenv("RID_SWEEP_REPLICA")) {
+        RID_TRY(replica_begin(dm, &R));
+        if (R.active) RID_TRY(replica_need_whole(R.full));
+    }
     replica_local(&R, true);
-    // on a replica every rank repeats the (cheap, shared) BUILD and takes every world-th k of the sweep
-    int rc = gap_sweep_on(R.active ? &R.full : dm, subset, m, Kmax, logW, R.active ? R.saved_world : 1,
+    int rc = gap_sweep_on(R.active ? R.full : dm, subset, m, Kmax, logW, R.active ? R.saved_world : 1,
                           R.active ? R.saved_rank : 0);
     replica_local(&R, false);
+    if (R.active) rc = agree_interrupt(ctx, rc);
     if (R.active && rc == RID_OK) {
         double *d_lw = nullptr;
         if (cudaMalloc(&d_lw, (size_t)Kmax * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
@@ -2034,11 +2075,12 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     RID_TRY(rid_time_begin(ctx));
     // c1 = PAM on all cells: every rank scans its own row shard (1/world of the bytes), before any replica exists
     std::vector<int> med_pos(k);
-    int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, nullptr);
+    int c1_swaps = 0;
+    int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
     if (rc != RID_OK) return rc;
     FullReplica R;
     RID_TRY(replica_begin(dm, &R));
-    rid_dmat *work = R.active ? &R.full : dm; // the matrix the bootstrap PAM runs read
+    rid_dmat *work = R.active ? R.full : dm; // the matrix the bootstrap PAM runs read
     const int nshare = R.active ? R.saved_world : 1, myshare = R.active ? R.saved_rank : 0;
     replica_local(&R, true);
     int *d_part = nullptr, *d_tab = nullptr;
@@ -2051,7 +2093,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         if (medoids) for (int c = 0; c < k; ++c) medoids[c] = med_pos[c]; // positions == cells for the full set
         std::vector<int> p0(N);
         for (int i = 0; i < N; ++i) p0[i] = partition[i] - 1; // c1 labels by cell (0-based) on the device
-        if (cudaMemcpy(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) rc = RID_ERR_CUDA;
+        if (cudaMemcpyAsync(d_part, p0.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
     }
     std::vector<int> tab((size_t)k * k), blab, bmed(k);
     // this rank's replicates; the host tables of the next one are prepared on a helper thread while the GPU works
@@ -2093,7 +2135,10 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     // replicate's own page-locked slot -- no host round trip until the end of a wave of replicates.  The launch queue
     // keeps the GPU several replicates ahead of the host, so host hiccups (a descheduled thread, a slow driver call) no
     // longer idle it; stream order alone makes one device workspace enough.
-    const int ahead = getenv("RID_BOOT_AHEAD") ? std::max(0, atoi(getenv("RID_BOOT_AHEAD"))) : 6;
+    // iterations enqueued ahead per replicate: c1 (the same data, all cells) shows how hard SWAP has to work; every
+    // unused iteration costs a handful of early-exit launches, a replicate that needs more is redone from scratch
+    const int ahead = getenv("RID_BOOT_AHEAD") ? std::max(0, atoi(getenv("RID_BOOT_AHEAD")))
+                                               : std::min(48, 6 + c1_swaps + c1_swaps / 2);
     bool pipelined = rc == RID_OK && work->ctx->world == 1 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") &&
                      !getenv("RID_BOOT_SYNC") && !mine.empty();
     // slot layout (ints): subset tables [8 N] | PamState [64, 8-byte aligned] | contingency table [k k]
@@ -2103,7 +2148,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     int *pin = nullptr, *d_tabs = nullptr;
     if (pipelined) {
         const size_t budget = (size_t)768 << 20; // page-locked bytes per wave
-        wave = std::max<size_t>(2, std::min<size_t>(mine.size(), budget / (slot_ints * sizeof(int))));
+        // (at most 16 replicates per wave: the cancellation poll runs between waves)
+        wave = std::max<size_t>(2, std::min<size_t>(std::min<size_t>(mine.size(), 16), budget / (slot_ints * sizeof(int))));
         pin = (int *)rid_pinned(ctx, wave * slot_ints * sizeof(int));
         if (!pin || cudaMalloc(&d_tabs, wave * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
     }
@@ -2145,6 +2191,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         const size_t i1 = std::min(mine.size(), i0 + wave);
         for (size_t i = i0; i < i1 && rc == RID_OK; ++i) {
             fut.get();
+            if (i == i0 || !pipelined) rc = rid_check_abort(ctx, !R.active);
+            if (rc != RID_OK) break;
             if (i + 1 < mine.size()) launch_prep(i + 1);
             if (pipelined) rc = enqueue(mine[i], prep[i & 1], pin + (i - i0) * slot_ints, d_tabs + (i - i0) * (size_t)k * k);
             else rc = run_sync(mine[i], &prep[i & 1]);
@@ -2159,7 +2207,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         for (size_t i = i0; i < i1 && rc == RID_OK; ++i) {
             const int *slot = pin + (i - i0) * slot_ints;
             const PamState *st = (const PamState *)(slot + tab_off - 64);
-            if (st->done) jaccard_row(slot + tab_off, mine[i]);
+            if (st->done) { ctx->swaps += st->nswaps; jaccard_row(slot + tab_off, mine[i]); }
             else rc = run_sync(mine[i], nullptr); // more swaps than were enqueued ahead (rare): redo this one the plain way
         }
     }
@@ -2168,6 +2216,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     cudaFree(d_part);
     cudaFree(d_tab);
     replica_local(&R, false);
+    if (R.active) rc = agree_interrupt(ctx, rc);
+    if (rc != RID_OK) cudaStreamSynchronize(ctx->stream);
     if (R.active && rc == RID_OK && B > 0) {
         // every rank holds the columns of its own replicates and zeros elsewhere: one sum makes them whole
         double *d_br = nullptr;
@@ -2207,7 +2257,8 @@ extern "C" int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_i
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
     RID_TRY(pam_set_subset(dm, w, sub.data(), m, false));
-    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    // (on the library's stream, which is not ordered against the legacy default stream; pageable source: staged on return)
+    RID_CUDA(cudaMemcpyAsync(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, dm->ctx->stream));
     RID_TRY(rid_time_begin(ctx));
     RID_TRY(grouped_colsums(dm, w, k));
     RID_CUDA(cudaMemsetAsync(w->grp_min, 0xFF, (size_t)k * sizeof(u64), ctx->stream));
@@ -2252,7 +2303,8 @@ extern "C" int rid_silhouette(rid_dmat *dm, const int *labels, int N, int *neigh
     PamWs *w;
     RID_TRY(ws_get(dm, k, &w));
     RID_TRY(pam_set_subset(dm, w, sub.data(), m, false));
-    RID_CUDA(cudaMemcpy(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    // (on the library's stream, which is not ordered against the legacy default stream; pageable source: staged on return)
+    RID_CUDA(cudaMemcpyAsync(w->lab_pos, g.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, dm->ctx->stream));
     int *d_nb = nullptr;
     RID_CUDA(cudaMalloc(&d_nb, (size_t)m * sizeof(int)));
     int rc = rid_time_begin(ctx);

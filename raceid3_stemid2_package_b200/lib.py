@@ -21,7 +21,11 @@ SYMBOLS = [
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dist_csc", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
     "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn", "rid_silhouette", "rid_cmdscale",
+    "rid_ctx_request_abort", "rid_ctx_clear_abort", "rid_ctx_set_interrupt_poll", "rid_measure_i8_peak", "rid_r_bootstrap_samples", "rid_ctx_swaps", "rid_ctx_trim",
 ]
+
+INTERRUPTED = -6  # RID_ERR_INTERRUPTED
+POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
 class RaceIDError(RuntimeError):
@@ -50,6 +54,13 @@ def load() -> C.CDLL:
     L.rid_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.rid_ctx_destroy.argtypes = [vp]
     L.rid_ctx_sync.argtypes = [vp]
+    L.rid_ctx_swaps.argtypes = [vp]
+    L.rid_ctx_swaps.restype = C.c_longlong
+    L.rid_ctx_trim.argtypes = [vp]
+    L.rid_ctx_request_abort.argtypes = [vp]
+    L.rid_ctx_clear_abort.argtypes = [vp]
+    L.rid_ctx_set_interrupt_poll.argtypes = [vp, vp, vp]
+    L.rid_measure_i8_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.rid_ctx_last_ms.argtypes = [vp]
     L.rid_ctx_last_ms.restype = C.c_double
     L.rid_ctx_launches.argtypes = [vp]
@@ -78,6 +89,7 @@ def load() -> C.CDLL:
     L.rid_silhouette.argtypes = [vp, ip, C.c_int, ip, dp]
     L.rid_cmdscale.argtypes = [vp, C.c_int, C.c_double, C.c_int, dp, dp, ip]
     L.rid_knn.argtypes = [vp, C.c_int, ip, dp]
+    L.rid_r_bootstrap_samples.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int, ip, ip]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what include/raceid_b200.h declares
     _lib = L
@@ -102,6 +114,17 @@ def shard_rows(n: int, rank: int, world: int) -> tuple[int, int]:
     a, b = C.c_int(), C.c_int()
     _check(load().rid_shard_rows(n, rank, world, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def r_bootstrap_samples(n: int, bootnr: int, seed: int, subset_size: int = 0):
+    """The resamples clusterboot draws from R's generator (host-only C helper, no GPU): (concatenated int32 indices,
+    int32 lengths)."""
+    cap = n if subset_size <= 0 else min(n, int(subset_size))
+    cat = np.empty(max(bootnr * cap, 1), dtype=np.int32)
+    lens = np.zeros(max(bootnr, 1), dtype=np.int32)
+    _check(load().rid_r_bootstrap_samples(int(n), int(bootnr), int(seed) & 0xFFFFFFFF, int(subset_size), _p(cat), _p(lens)))
+    lens = lens[:bootnr]
+    return cat[:int(lens.sum())], lens
 
 
 def nccl_unique_id() -> bytes:
@@ -133,6 +156,31 @@ class Context:
     def sync(self):
         _check(load().rid_ctx_sync(self._h))
 
+    def request_abort(self):
+        """Ask the compute call running on this context (from another thread, or a signal handler) to stop: it returns
+        RID_ERR_INTERRUPTED (RaceIDError with code -6) at its next poll point."""
+        _check(load().rid_ctx_request_abort(self._h))
+
+    def clear_abort(self):
+        _check(load().rid_ctx_clear_abort(self._h))
+
+    def set_interrupt_poll(self, fn=None):
+        """fn() -> truthy to cancel; called on the calling thread between waves of GPU work (what the R stub does with
+        R_CheckUserInterrupt).  None removes the callback."""
+        if fn is None:
+            self._poll_keep = None
+            _check(load().rid_ctx_set_interrupt_poll(self._h, None, None))
+            return
+        cb = POLL_FN(lambda _arg: 1 if fn() else 0)
+        self._poll_keep = cb  # keep the thunk alive
+        _check(load().rid_ctx_set_interrupt_poll(self._h, C.cast(cb, C.c_void_p), None))
+
+    def measure_i8_peak(self) -> float:
+        """tcgen05.mma kind::i8 issue-rate ceiling measured on this GPU right now, TOP/s."""
+        v = C.c_double()
+        _check(load().rid_measure_i8_peak(self._h, C.byref(v)))
+        return v.value
+
     @property
     def last_ms(self) -> float:
         return load().rid_ctx_last_ms(self._h)
@@ -140,6 +188,13 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load().rid_ctx_launches(self._h))
+
+    @property
+    def swaps(self) -> int:
+        return int(load().rid_ctx_swaps(self._h))
+
+    def trim(self):
+        _check(load().rid_ctx_trim(self._h))
 
     PROF_KINDS = {"gram": 0, "scan_swap": 1, "scan_build": 2, "scan_group": 3, "prep": 4, "compact": 5, "gram_i8": 6, "scan_delta": 7}
 
@@ -286,9 +341,16 @@ class DistMatrix:
         return out
 
     def clusterboot(self, k: int, samples):
-        B = len(samples)
-        cat = _i32(np.concatenate(samples)) if B else np.zeros(1, dtype=np.int32)
-        lens = _i32([len(s) for s in samples]) if B else np.zeros(1, dtype=np.int32)
+        """samples: list of index vectors, or the (concatenated, lengths) pair r_bootstrap_samples returns."""
+        if isinstance(samples, tuple):
+            cat, lens = _i32(samples[0]), _i32(samples[1])
+            B = len(lens)
+            if B == 0:
+                cat, lens = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        else:
+            B = len(samples)
+            cat = _i32(np.concatenate(samples)) if B else np.zeros(1, dtype=np.int32)
+            lens = _i32([len(s) for s in samples]) if B else np.zeros(1, dtype=np.int32)
         part = np.zeros(self.N, dtype=np.int32)
         med = np.zeros(k, dtype=np.int32)
         br = np.zeros((max(B, 1), k))

@@ -7,7 +7,7 @@ R's LCG scrambling (RNG.c: RNG_Init / FixupSeeds / MT_genrand) and, for R >= 3.6
 on ceil(log2(n)) random bits taken 16 at a time (R_unif_index / rbits).
 
 PARITY UNPINNED against a live R (none in this image); pinned by R's well-known known-answer values in
-tests/test_rrng.py (set.seed(42); sample(1:10) etc.).
+tests/test_host_and_lib.py::test_rrng_known_answers (set.seed(42); sample(1:10) etc.).
 """
 from __future__ import annotations
 

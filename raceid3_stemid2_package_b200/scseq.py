@@ -78,23 +78,65 @@ class SCseq:
     fcol: list = field(default_factory=list)
     filterpar: dict = field(default_factory=dict)
     clusterpar: dict = field(default_factory=dict)
+    out: dict = field(default_factory=dict)
+    fcounts: object = None  # sparse input only: expdata[, kept cells] as CSC (what rid_dist_csc reads)
+
+    @classmethod
+    def from_filtered_counts(cls, counts_csc, genes=None, cells=None, features=None) -> "SCseq":
+        """An object in the state filterdata leaves it in when every cell passes `mintotal` and every gene is kept:
+        counts_csc is the genes x cells count matrix (scipy CSC; its arrays are used as they are, e.g. page-locked).
+        Used where the feature matrix is generated directly; `features` defaults to all genes."""
+        obj = cls.__new__(cls)
+        G, N = counts_csc.shape
+        obj.expdata = counts_csc
+        obj.genes_all = list(genes) if genes is not None else [f"g{i + 1}" for i in range(G)]
+        obj.cells_all = list(cells) if cells is not None else [f"c{i + 1}" for i in range(N)]
+        obj.cell_names = obj.cells_all
+        obj.counts = np.asarray(counts_csc.sum(axis=0)).ravel()
+        obj.fcounts = counts_csc
+        obj.ndata = None  # expdata / counts: built lazily by getfdata when a host consumer asks for it
+        obj.genes = obj.genes_all
+        obj.dimRed, obj.background, obj.filterpar, obj.clusterpar, obj.out = {}, {}, {}, {}, {}
+        obj.cluster = {"features": list(features) if features is not None else obj.genes_all}
+        obj.distances, obj.cpart, obj.medoids, obj.fcol = None, None, [], []
+        return obj
 
     def __post_init__(self):
-        x = np.asarray(self.expdata, dtype=np.float64)
+        # expdata may be dense or a scipy.sparse matrix: upstream it is a dgCMatrix (R/RaceID.R:72-83,
+        # Matrix(as.matrix(expdata), sparse=TRUE)); a sparse input stays sparse all the way to the device
+        if _is_sparse(self.expdata):
+            x = self.expdata.tocsc()
+            if x.dtype != np.float64:
+                x = x.astype(np.float64)
+            vals = x.data
+        else:
+            x = np.asarray(self.expdata, dtype=np.float64)
+            vals = x
         # validity (R/RaceID.R:54-69)
         if x.ndim != 2 or x.shape[0] < 2:
             raise ValueError("input data must have more than one row")
         if x.shape[1] < 2:
             raise ValueError("input data must have more than one column")
-        if np.isnan(x.min()):
+        if vals.size and np.isnan(vals.min()):
             raise ValueError("NAs are not allowed in input data")
-        if x.min() < 0:
+        if vals.size and vals.min() < 0:
             raise ValueError("negative values are not allowed in input data")
         self.expdata = x
         if not self.genes_all:
             self.genes_all = [f"g{i + 1}" for i in range(x.shape[0])]
         if not self.cells_all:
             self.cells_all = [f"c{i + 1}" for i in range(x.shape[1])]
+
+
+def _is_sparse(x) -> bool:
+    return hasattr(x, "tocsc") and hasattr(x, "indptr") or (hasattr(x, "tocsc") and hasattr(x, "nnz"))
+
+
+def _csc_div_cols(m, colvals):
+    """expdata / counts column-wise on a CSC matrix (true divisions, bit-identical to the dense `t(t(x) / counts)`)."""
+    from scipy.sparse import csc_matrix
+
+    return csc_matrix((m.data / np.repeat(colvals, np.diff(m.indptr)), m.indices, m.indptr), shape=m.shape)
 
 
 def _fitbackground(x: np.ndarray, names: list, mthr: float = -1.0):
@@ -142,13 +184,24 @@ def filterdata(object: SCseq, mintotal=3000, minexpr=5, minnumber=5, LBatch=None
     if LBatch is not None or CGenes is not None:
         raise NotImplementedError("batch-effect and CGenes arms of filterdata are outside the accelerated hot path")
     object.dimRed = {}
-    counts = object.expdata.sum(axis=0)
+    sparse = _is_sparse(object.expdata)
+    counts = np.asarray(object.expdata.sum(axis=0)).ravel()
     f = counts >= mintotal
     object.counts = counts[f]
     object.cell_names = [c for c, k in zip(object.cells_all, f) if k]
-    sub = object.expdata[:, f]
-    g = (sub >= minexpr).sum(axis=1) >= minnumber
-    object.ndata = sub / counts[f][None, :]
+    sub = object.expdata[:, f] if not f.all() else object.expdata
+    if sparse:
+        sub = sub.tocsc()
+        if minexpr > 0:
+            g = np.asarray((sub >= minexpr).sum(axis=1)).ravel() >= minnumber
+        else:
+            g = np.full(sub.shape[0], sub.shape[1] >= minnumber)
+        object.fcounts = sub                                  # raw counts of the kept cells: the device path's input
+        object.ndata = _csc_div_cols(sub, counts[f])
+        sub = None
+    else:
+        g = (sub >= minexpr).sum(axis=1) >= minnumber
+        object.ndata = sub / counts[f][None, :]
     genes = [n for n, k in zip(object.genes_all, g) if k]
     if FGenes:
         genes = [n for n in genes if n not in set(FGenes)]
@@ -156,7 +209,7 @@ def filterdata(object: SCseq, mintotal=3000, minexpr=5, minnumber=5, LBatch=None
     object.filterpar = dict(mintotal=mintotal, minexpr=minexpr, minnumber=minnumber, CGenes=CGenes, FGenes=FGenes,
                             BGenes=None, bmode=bmode)
     gi = _gene_index(object, genes)
-    fit, _ = _fitbackground(sub[gi, :], genes)
+    fit, _ = _fitbackground(sub[gi, :] if sub is not None else object.fcounts[gi, :].toarray(), genes)
     object.background["vfit"] = fit
     _, feats = _fitbackground(getfdata(object), genes)
     object.cluster["features"] = feats
@@ -170,6 +223,8 @@ def _gene_index(object: SCseq, names) -> np.ndarray:
 
 def getfdata(object: SCseq, g=None, n=None) -> np.ndarray:
     """getfdata (R/RaceID.R:723-728): (ndata * min(counts[n]))[fgenes, n] + 0.1, genes x cells."""
+    if object.ndata is None and object.fcounts is not None:
+        object.ndata = _csc_div_cols(object.fcounts, object.counts)
     if g is None:
         fgenes = object.genes
     else:
@@ -181,6 +236,8 @@ def getfdata(object: SCseq, g=None, n=None) -> np.ndarray:
         ns = set(n)
         cols = np.asarray([i for i, c in enumerate(object.cell_names) if c in ns], dtype=np.int64)
     gi = _gene_index(object, fgenes)
+    if _is_sparse(object.ndata):
+        return object.ndata[gi, :][:, cols].toarray() * object.counts[cols].min() + 0.1
     return object.ndata[np.ix_(gi, cols)] * object.counts[cols].min() + 0.1
 
 
@@ -200,16 +257,28 @@ def compdist(object: SCseq, metric="pearson", FSelect=True, knn=None, alpha=1, n
     if metric == "kendall":
         raise NotImplementedError("kendall is not part of the accelerated hot path")
     n = object.cluster.get("features") if FSelect else object.genes
-    if object.dimRed.get("x") is None:
-        x = getfdata(object, g=n)
-    else:
+    x = None
+    if object.dimRed.get("x") is not None:
         x = np.asarray(object.dimRed["x"], dtype=np.float64)
         if metric == "logpearson" and x.min() <= 0:
             metric = "pearson"
+    elif object.fcounts is None:
+        x = getfdata(object, g=n)
     old = object.distances
     if isinstance(old, _lib.DistMatrix):
         old.free()
-    dm = get_context().dist(x, metric)
+    if x is not None:
+        dm = get_context().dist(x, metric)
+    else:
+        # sparse object: the dgCMatrix triplet goes to the device as it is and getfdata (R/RaceID.R:723-728) is fused
+        # into the prep kernel's producer (rid_dist_csc) — no dense host matrix, no host transposes
+        fc = object.fcounts
+        if n is object.genes_all or len(n) == len(object.genes_all):
+            frows = np.arange(len(object.genes_all), dtype=np.int32)
+        else:
+            ns = set(n)
+            frows = np.asarray([i for i, gname in enumerate(object.genes_all) if gname in ns], dtype=np.int32)
+        dm = get_context().dist_csc(fc.indices, fc.indptr, fc.data, fc.shape[0], frows, object.counts, metric)
     if dm.n_zero_var:
         import warnings
 
@@ -245,9 +314,20 @@ def saturation_cln(logW: np.ndarray) -> int:
     return max(min(hit), 1)
 
 
-def bootstrap_samples(n: int, bootnr: int, rseed: int, samp=None):
+def bootstrap_samples(n: int, bootnr: int, rseed: int, samp=None, packed: bool = False):
     """The resamples fpc::clusterboot draws after set.seed(seed): sample(n,n,replace=TRUE) then unique() in
-    first-occurrence order ("boot"), or sample(n, subtuning, replace=FALSE) ("subset").  0-based."""
+    first-occurrence order ("boot"), or sample(n, subtuning, replace=FALSE) ("subset").  0-based.
+    Drawn by the library's host-only C restatement of R's generator (rid_r_bootstrap_samples; 13 M Mersenne-Twister
+    words at 100k cells x 50 resamples); `bootstrap_samples_py` is the Python mirror it is checked against.
+    packed=True returns the (concatenated, lengths) pair DistMatrix.clusterboot takes without re-packing."""
+    cat, lens = _lib.r_bootstrap_samples(int(n), int(bootnr), int(rseed), 0 if samp is None else int(samp))
+    if packed:
+        return cat, lens
+    return np.split(cat, np.cumsum(lens)[:-1]) if bootnr else []
+
+
+def bootstrap_samples_py(n: int, bootnr: int, rseed: int, samp=None):
+    """bootstrap_samples through the Python mirror of R's generator (rrng.py)."""
     rng = RRng(rseed)
     out = []
     for _ in range(bootnr):
@@ -298,8 +378,9 @@ def clustexp(object: SCseq, sat=True, samp=None, cln=None, clustnr=30, bootnr=50
                              cln=cln, rseed=rseed, FSelect=object.clusterpar.get("FSelect"), FUNcluster=FUNcluster)
     y = clustfun(object.distances, clustnr, bootnr, samp, sat, cln, rseed, FUNcluster, verbose)
     clb = y["clb"]
+    # (the single-cluster result carries no subsetmean: R's y$clb$subsetmean is NULL there, R/RaceID_utils.R:126-130)
     object.cluster = dict(kpart=clb["result"]["partition"],
-                          jaccard=clb["bootmean"] if samp is None else clb["subsetmean"], gap=y["gpr"], clb=clb,
+                          jaccard=clb.get("bootmean") if samp is None else clb.get("subsetmean"), gap=y["gpr"], clb=clb,
                           features=object.cluster.get("features"))
     k = int(np.max(clb["result"]["partition"]))
     object.fcol = list(RRng(111111).sample_int(k) - 1)  # set.seed(111111); sample(rainbow(k)) as a permutation
@@ -322,6 +403,20 @@ def clustfun(diM, clustnr=20, bootnr=50, samp=None, sat=True, cln=None, rseed=17
     if not (sat or cln > 0):
         return {"clb": None, "gpr": None}
     f = cln == 0
+    # the resamples depend on (N, bootnr, rseed, samp) only: draw them on a helper thread (the C helper releases the GIL)
+    # while the GPU runs the sweep
+    import threading
+
+    box = {}
+
+    def _draw():
+        try:
+            box["samples"] = bootstrap_samples(N, bootnr, int(rseed), samp, packed=True)
+        except BaseException as e:  # surfaced by the join below
+            box["error"] = e
+
+    drawer = threading.Thread(target=_draw, daemon=True)
+    drawer.start()
     if sat:
         rng = RRng(int(rseed))
         sub = None
@@ -339,8 +434,10 @@ def clustfun(diM, clustnr=20, bootnr=50, samp=None, sat=True, cln=None, rseed=17
     if cln <= 1:
         clb = {"result": {"partition": np.ones(N, dtype=np.int32)}, "bootmean": np.array([1.0])}
         return {"clb": clb, "gpr": gpr}
-    samples = bootstrap_samples(N, bootnr, int(rseed), samp)
-    r = dm.clusterboot(cln, samples)
+    drawer.join()
+    if "error" in box:
+        raise box["error"]
+    r = dm.clusterboot(cln, box["samples"])
     key = "boot" if samp is None else "subset"
     clb = {"result": {"partition": r["partition"], "nc": cln,
                       "result": {"pamobject": {"id.med": r["id_med"] + 1, "clustering": r["partition"]}, "nc": cln},
@@ -385,6 +482,100 @@ def tsne_initial_config(object: SCseq, k: int = 2) -> np.ndarray:
     if object.distances is None:
         raise ValueError("run compdist before comptsne (the dimRed arm of comptsne does not use a distance matrix)")
     return _as_dmat(object.distances).cmdscale(k)
+
+
+def outlier_distance_sample(object: SCseq, out=()) -> np.ndarray:
+    """`clp2p.cl` of findoutliers (R/RaceID.R:986-994): after `set.seed(clusterpar$rseed)`, for every cluster of `kpart`
+    `tcol <- sample(cells of the cluster, min(500, size))`, and the distances among the sampled cells that are not
+    outliers, `as.vector(t(object@distances[tcol', tcol']))`, are appended when more than one cell is left; zeros are
+    dropped.  The blocks are read from the device-resident matrix by cell NAME (rid_dmat_sub): D never leaves HBM."""
+    kpart = np.asarray(object.cluster["kpart"], dtype=np.int64)
+    names = object.cell_names if object.cell_names else [str(i) for i in range(len(kpart))]
+    dm = _as_dmat(object.distances)
+    pos = {c: i for i, c in enumerate(names)}
+    outset = set(out)
+    rng = RRng(int(object.clusterpar.get("rseed", 17000)))
+    chunks = []
+    for i in range(1, int(kpart.max()) + 1):
+        members = np.nonzero(kpart == i)[0]
+        if len(members) == 0:
+            # sample(character(0), 0) draws nothing
+            continue
+        pick = rng.sample_int(len(members), min(500, len(members)), replace=False) - 1
+        tcol = [names[members[j]] for j in pick]
+        keep = [c for c in tcol if c not in outset]
+        if len(keep) > 1:
+            idx = np.asarray([pos[c] for c in keep], dtype=np.int32)
+            chunks.append(dm.sub(idx, idx).reshape(-1))  # as.vector(t(M)): row-major
+    v = np.concatenate(chunks) if chunks else np.zeros(0)
+    return v[v > 0]
+
+
+def findoutliers_merge(object: SCseq, out, outdistquant=.95, verbose=False) -> SCseq:
+    """The distance-consuming half of findoutliers (R/RaceID.R:983-1060): `out` are the outlier cell names the negative
+    binomial model produced (R/RaceID.R:943-981; a statistical model outside the accelerated path).  Outliers are merged
+    into new clusters by their mutual distances `object@distances[out, out]` against the `outdistquant` quantile of the
+    within-cluster distance sample, then the final partition is refreshed (medoids by mean within-cluster distance,
+    every cell to its nearest medoid).  Both distance reads are sub-block gathers by cell name on the device."""
+    if not isinstance(outdistquant, (int, float)) or isinstance(outdistquant, bool):
+        raise ValueError("outdistquant has to be a number between 0 and 1")
+    if outdistquant < 0 or outdistquant > 1:
+        raise ValueError("outdistquant has to be a number between 0 and 1")
+    if object.cluster.get("kpart") is None or len(object.cluster["kpart"]) == 0:
+        raise ValueError("run clustexp before findoutliers")
+    kpart = np.asarray(object.cluster["kpart"], dtype=np.int64)
+    names = object.cell_names if object.cell_names else [str(i) for i in range(len(kpart))]
+    pos = {c: i for i, c in enumerate(names)}
+    out = list(out)
+    for c in out:
+        if c not in pos:
+            raise ValueError(f"subscript out of bounds: unknown cell {c!r}")
+    dm = _as_dmat(object.distances)
+    clp = outlier_distance_sample(object, out)
+    cpart = kpart.copy()
+    cadd = []
+    if len(out) == 1:
+        cadd = [out]
+    elif len(out) > 1:
+        if len(clp) == 0:
+            raise ValueError("missing value where TRUE/FALSE needed")  # quantile() / min() of an empty sample in R
+        q = float(np.quantile(clp, outdistquant))  # type 7, R's default
+        cmin = float(clp.min())
+        n = list(out)
+        idx = np.asarray([pos[c] for c in n], dtype=np.int32)
+        m = dm.sub(idx, idx)
+        for _ in range(len(out)):
+            if len(n) > 1:
+                mm = m.copy()
+                np.fill_diagonal(mm, np.inf)  # x[1:(length(x)-1)][-x[length(x)]]: the row without its own column
+                o = np.argsort(mm.min(axis=1), kind="stable")
+                m = m[np.ix_(o, o)]
+                n = [n[j] for j in o]
+                f = (m[:, 0] < q) | (m[:, 0] == cmin)
+                fi = np.nonzero(f)[0]
+                ind = np.asarray([0]) if len(fi) else np.zeros(0, dtype=np.int64)
+                if len(fi) > 1:
+                    ind = np.nonzero((m[np.ix_(fi, fi)] <= q).sum(axis=1) > len(fi) / 2)[0]
+                if len(fi) == 0:
+                    # n[f][1] is NA in R; nothing can be merged
+                    raise ValueError("no outlier lies below the distance quantile (n[f][ind] is NA in R)")
+                grp = [n[fi[j]] for j in ind]
+                cadd.append(grp)
+                g = np.asarray([c not in set(grp) for c in n])
+                n = [c for c, k in zip(n, g) if k]
+                m = m[np.ix_(g, g)]
+                if not g.any():
+                    break
+            elif len(n) == 1:
+                cadd.append(n)
+                break
+    for grp in cadd:
+        sel = np.asarray([pos[c] for c in grp], dtype=np.int64)
+        new = int(cpart.max()) + 1
+        if len(sel):
+            cpart[sel] = new
+    object.out = {"out": out, "cadd": cadd, "clp2p.cl": clp}
+    return refresh_partition(object, cpart)
 
 
 def refresh_partition(object: SCseq, cpart):

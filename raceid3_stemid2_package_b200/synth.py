@@ -11,7 +11,10 @@ from __future__ import annotations
 import numpy as np
 
 
-def synth_counts_numpy(n_cells: int, n_genes: int, n_clusters: int, seed: int):
+def synth_counts_numpy(n_cells: int, n_genes: int, n_clusters: int, seed: int, structure: str = "clusters"):
+    """structure "clusters": every cell follows the profile of its cluster.  "ring": every cell is a random mixture of
+    the profiles of cluster c and c+1 (a closed differentiation trajectory): a continuum without gaps, on which PAM's
+    BUILD is not already the local optimum and SWAP really has to work (7-9 exchanges per run at k = 30)."""
     rng = np.random.default_rng(seed)
     p = rng.lognormal(-8.5, 1.5, size=n_genes)
     p /= p.sum()
@@ -22,7 +25,11 @@ def synth_counts_numpy(n_cells: int, n_genes: int, n_clusters: int, seed: int):
         prof[c] /= prof[c].sum()
     lab = rng.integers(0, n_clusters, size=n_cells)
     L = np.maximum(rng.lognormal(np.log(8000.0), 0.35, size=n_cells), 3000.0)
-    counts = rng.poisson(L[:, None] * prof[lab] * (n_genes / 3000.0) ** 0)  # N x G
+    rate = prof[lab]
+    if structure == "ring":
+        a = rng.random(n_cells)[:, None]
+        rate = a * rate + (1.0 - a) * prof[(lab + 1) % n_clusters]
+    counts = rng.poisson(L[:, None] * rate)  # N x G
     return counts.astype(np.float64), lab
 
 
@@ -31,15 +38,16 @@ def transform_like_getfdata(counts_ng: np.ndarray) -> np.ndarray:
     return counts_ng / tot * tot.min() + 0.1
 
 
-def synth_features_numpy(n_cells, n_genes, n_clusters, seed):
+def synth_features_numpy(n_cells, n_genes, n_clusters, seed, structure: str = "clusters"):
     """N x G float64 feature matrix (cell-major) + true labels; zero-variance cells are impossible here because
     every cell has >= 3000 counts spread over the genes."""
-    c, lab = synth_counts_numpy(n_cells, n_genes, n_clusters, seed)
+    c, lab = synth_counts_numpy(n_cells, n_genes, n_clusters, seed, structure)
     return transform_like_getfdata(c), lab
 
 
-def synth_features_torch(n_cells, n_genes, n_clusters, seed, device):
-    """Same model, generated with torch on `device`; returns (x [N,G] float64 tensor, labels)."""
+def synth_features_torch(n_cells, n_genes, n_clusters, seed, device, structure: str = "clusters", want_counts: bool = False):
+    """Same model, generated with torch on `device`; returns (x [N,G] float64 tensor, labels), or with
+    want_counts=True (counts [N,G] float64 tensor, labels) — the raw UMI counts before the getfdata transform."""
     import torch
 
     g = torch.Generator(device=device)
@@ -56,10 +64,17 @@ def synth_features_torch(n_cells, n_genes, n_clusters, seed, device):
     L = torch.clamp(L, min=3000.0)
     x = torch.empty((n_cells, n_genes), dtype=torch.float64, device=device)
     step = 8192
+    mix = torch.rand(n_cells, generator=g, device=device, dtype=torch.float64) if structure == "ring" else None
     for s in range(0, n_cells, step):
         e = min(s + step, n_cells)
-        rate = (L[s:e, None] * prof[lab[s:e]]).to(torch.float32)
+        pr = prof[lab[s:e]]
+        if mix is not None:
+            a = mix[s:e, None]
+            pr = a * pr + (1.0 - a) * prof[(lab[s:e] + 1) % n_clusters]
+        rate = (L[s:e, None] * pr).to(torch.float32)
         x[s:e] = torch.poisson(rate, generator=g).to(torch.float64)
+    if want_counts:
+        return x, lab
     tot = x.sum(dim=1, keepdim=True)
     x = x / tot * tot.min() + 0.1
     return x, lab

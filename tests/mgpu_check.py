@@ -27,6 +27,9 @@ def main():
     x, _ = synth_features_numpy(n_cells, 300, 6, 11)
     x[17] = x[4]
     samples = rid.bootstrap_samples(n_cells, 3, 17000)
+    # bootmethod "subset" resamples (clustexp(samp=...)): sparse subsets, whose symmetric compaction reaches below the
+    # part of the peers' blocks a replica pulls first (the library then has to fetch the rest)
+    sparse_samples = rid.bootstrap_samples(n_cells, 2, 17000, samp=max(600, n_cells // 12))
     sub = np.arange(n_cells - 1, -1, -2).astype(np.int32)
 
     def run(c):
@@ -44,6 +47,8 @@ def main():
             out[metric + "_logW"] = dm.gap_sweep(8)
             cb = dm.clusterboot(4, samples)
             out[metric + "_boot"] = (cb["partition"], cb["id_med"], cb["bootresult"])
+            cs = dm.clusterboot(3, sparse_samples)
+            out[metric + "_boot_subset"] = (cs["partition"], cs["id_med"], cs["bootresult"])
             med, ids = dm.medoids(cb["partition"])
             out[metric + "_med"] = (med, ids, dm.refresh(med))
             out[metric + "_sil"] = dm.silhouette(cb["partition"])

@@ -10,17 +10,24 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,no_replica", [(2, "0"), (2, "1")])
-def test_row_sharded_results_identical_to_single_gpu(world, no_replica):
-    """no_replica=1 forces the cooperative schedule (every rank scans its row shard of every PAM problem, one all-reduce
-    per step); the default gathers the shards and spreads bootstrap replicates / sweep k values over the ranks."""
+@pytest.mark.parametrize("world,mode", [(2, "replica"), (2, "cooperative"), (2, "replica_upper"), (2, "sweep_replica")])
+def test_row_sharded_results_identical_to_single_gpu(world, mode):
+    """cooperative: RID_NO_REPLICA=1, every rank scans its row shard of every PAM problem, one all-reduce per step.
+    replica (default): the copy engines pull the peers' row blocks into a full copy per rank and the bootstrap
+    replicates are spread over the ranks; replica_upper makes the first pull partial at this small size
+    (RID_REPLICA_MARGIN=64: only the columns the symmetric compaction needs), so the fetch-the-rest path runs too;
+    sweep_replica also spreads the k values of the sweep over the replicas."""
     import torch
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ)
-    if no_replica == "1":
+    if mode == "cooperative":
         env["RID_NO_REPLICA"] = "1"
+    if mode == "replica_upper":
+        env["RID_REPLICA_MARGIN"] = "64"
+    if mode == "sweep_replica":
+        env["RID_SWEEP_REPLICA"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)

@@ -127,3 +127,82 @@ def test_rdata_reader_and_filterdata_on_bundled_fixture():
     g = load_golden("cfg1_intestinalDataSmall.npz")
     assert x.shape == g["x"].shape and np.array_equal(x, g["x"])
     assert abs(x.min() - 0.1) < 1e-12
+
+
+def test_c_sampler_equals_python_mirror_of_r_rng():
+    """rid_r_bootstrap_samples (host-only C restatement of R's Mersenne-Twister + rejection sampling + do_sample) against
+    the Python mirror that carries R's known answers, for both bootmethods and the awkward sizes (1, 2, 2^16, 2^16+1)."""
+    from raceid3_stemid2_package_b200 import lib
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples, bootstrap_samples_py
+
+    for n, B, seed, samp in [(1000, 4, 17000, None), (70001, 2, 42, None), (5000, 3, 7, 1200), (10, 3, 1, None), (2, 3, 1, None),
+                             (300, 2, 5, 1), (65536, 2, 9, None), (65537, 2, 9, None), (1, 2, 3, None), (50, 2, 8, 80)]:
+        a = bootstrap_samples(n, B, seed, samp)
+        b = bootstrap_samples_py(n, B, seed, samp)
+        assert len(a) == len(b) == B
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v), (n, B, seed, samp)
+    cat, lens = bootstrap_samples(1000, 4, 17000, packed=True)
+    assert lens.dtype == np.int32 and cat.dtype == np.int32 and int(lens.sum()) == len(cat)
+    assert lib.r_bootstrap_samples(10, 0, 1)[1].size == 0
+
+
+def test_bench_fp64_rows_restatement_matches_oracle(oracle):
+    """bench.py's parity_spot compares sampled rows of the device matrix with an FP64 numpy restatement of cor()/dist();
+    that restatement is held to the oracle here (all four metrics, ties, a duplicated cell)."""
+    import bench
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    x, _ = synth_features_numpy(90, 70, 3, 2)
+    x[11] = x[3]
+    for metric in ("pearson", "spearman", "logpearson", "euclidean"):
+        Do, _ = oracle.dist(np.ascontiguousarray(x.T), metric)
+        Z = bench.transform_rows_fp64(x, metric)
+        if metric == "euclidean":
+            ref = np.sqrt(((Z[:, None, :] - Z[None, :, :]) ** 2).sum(-1))
+        else:
+            ref = 1.0 - np.clip(Z @ Z.T, -1.0, 1.0)
+            np.fill_diagonal(ref, 0.0)
+        assert np.max(np.abs(ref - Do)) < 1e-12, metric
+    out = {"partition": np.arange(5), "id_med": np.array([1, 2]), "bootresult": np.ones((2, 3)), "logW": None}
+    d1 = bench.digest_of(out)
+    out["partition"] = out["partition"].astype(np.int64)
+    assert bench.digest_of(out) == d1 and len(d1) == 40
+    out["bootresult"][0, 0] = np.nextafter(1.0, 2.0)
+    assert bench.digest_of(out) != d1
+
+
+def test_sparse_scseq_filterdata_equals_dense():
+    """SCseq accepts a scipy sparse count matrix (upstream: dgCMatrix) and keeps it sparse; filterdata / getfdata give
+    the dense route's genes, features and values."""
+    import raceid3_stemid2_package_b200 as rid
+    from scipy.sparse import csc_matrix
+
+    rng = np.random.default_rng(15)
+    counts = rng.poisson(0.5, size=(300, 220)).astype(np.float64)
+    counts[:, counts.sum(0) == 0] = 1.0
+    a = rid.filterdata(rid.SCseq(counts), mintotal=150, minexpr=1, minnumber=3)
+    b = rid.filterdata(rid.SCseq(csc_matrix(counts)), mintotal=150, minexpr=1, minnumber=3)
+    assert 0 < len(a.cell_names) < 220 and a.cell_names == b.cell_names
+    assert a.genes == b.genes and a.cluster["features"] == b.cluster["features"]
+    assert np.array_equal(a.counts, b.counts)
+    assert np.array_equal(rid.getfdata(a), rid.getfdata(b))
+    assert np.array_equal(rid.getfdata(a, g=a.cluster["features"][:5], n=a.cell_names[:7]),
+                          rid.getfdata(b, g=a.cluster["features"][:5], n=a.cell_names[:7]))
+    c = rid.SCseq.from_filtered_counts(csc_matrix(counts))
+    tot = counts.sum(0)
+    assert np.array_equal(rid.getfdata(c), counts / tot * tot.min() + 0.1)
+    with pytest.raises(ValueError):
+        rid.SCseq(csc_matrix(-counts))
+
+
+def test_findoutliers_merge_validation_messages():
+    import raceid3_stemid2_package_b200 as rid
+
+    sc = rid.SCseq(np.ones((3, 4)))
+    with pytest.raises(ValueError, match="outdistquant has to be a number between 0 and 1"):
+        rid.findoutliers_merge(sc, [], outdistquant=2)
+    with pytest.raises(ValueError, match="outdistquant has to be a number between 0 and 1"):
+        rid.findoutliers_merge(sc, [], outdistquant="a")
+    with pytest.raises(ValueError, match="run clustexp before findoutliers"):
+        rid.findoutliers_merge(sc, [])
