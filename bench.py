@@ -434,7 +434,7 @@ def main():
             ms, wl = allmax([dev_ms, wall * 1e3])
             swaps = allsum([ctx.swaps - s0])[0]
             return {"ms_per_step": ms / steps, "wall_ms_per_step": wl / steps, "launches": ctx.launches - l0,
-                    "n_swaps_per_step": swaps / steps, "prof": prof}
+                    "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": ctx.stats()}
 
     # ---- headline: resident leg, W warm-up + K timed steps ---------------------------------------------------
     W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure)
@@ -641,6 +641,7 @@ def main():
     detail["clusters_found"] = int(state["partition"].max())
     detail["bootmean_min"] = float(np.min(state["bootmean"]))
     detail["roofline_all"] = roofs
+    detail["lib_stats_rank0_last_step"] = res["lib_stats_rank0_last_step"]
     detail["ceilings_measured_here"] = {"int8_tops": i8_peak, "fp64_dmma_tflops": dmma_peak, "read_only_stream_gbs": read_peak}
     if e2e_detail:
         detail["e2e"] = e2e_detail
@@ -660,6 +661,7 @@ def main():
             out = {"workload": workload_name(a, cells, metric, sat, bootnr, structure), "value": r["ms_per_step"] / 1e3, "unit": "s",
                    "steps": steps, "warmup": warmup, "result_digest": digest_of(Wl.state), "n_swaps_per_step": r["n_swaps_per_step"],
                    "gpu_launches_per_step": r["launches"] / steps, "bootmean_min": float(np.min(Wl.state["bootmean"])),
+                   "lib_stats_rank0_last_step": r["lib_stats_rank0_last_step"],
                    "phase_ms_last_step": {k: Wl.state.get(k) for k in ("t_dist", "t_sweep", "t_boot") if k in Wl.state}}
             rf = rooflines(r["prof"], r["ms_per_step"] * steps, cells, world)
             out["roofline"] = rf[0] if rf else None

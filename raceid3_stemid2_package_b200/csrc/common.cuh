@@ -49,6 +49,11 @@ struct rid_ctx {
     double last_ms = 0.0;
     long long launches = 0;
     long long swaps = 0; // accepted SWAP exchanges of every PAM run read back so far (bench.py's n_swaps)
+    // rid_ctx_stat: [0] swaps (mirror), [1] bootstrap replicates redone because they needed more SWAP iterations than were
+    // enqueued ahead, [2..4] ms of the last rid_clusterboot: c1 / wait for the replica pulls / replicates,
+    // [5] bytes the last replica pull moved over NVLink, [6] look-ahead iterations the last rid_clusterboot enqueued
+    double stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void *comm = nullptr; // ncclComm_t
     NcclApi *nccl = nullptr;
     // optional per-kernel profiling (rid_ctx_profile): CUDA-event pairs around the hot kernels, on `stream`
@@ -140,6 +145,7 @@ struct rid_dmat {
     // (cudaMemcpy2DAsync from the peers' IPC-mapped buffers on ctx->copy_stream), overlapping the kernels of the first
     // clustering phase.  replica_state: 0 nothing pulled, 1 columns >= replica_lo[s] of every peer block s (all the
     // symmetric compaction of a bootstrap replicate reads), 2 complete.
+    int world = 1, rank = 0; // the job geometry the matrix was created under (ctx->world is switched to 1 in local phases)
     u32 *full = nullptr;
     size_t full_bytes = 0;
     u32 *peer_full[16] = {nullptr};

@@ -142,8 +142,9 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    // peers may hold this rank's exported buffers mapped: everybody closes first, then everybody frees
-    if (ctx->world > 1 && ctx->comm && (!ctx->ipc.empty() || !ctx->exported.empty())) rid_ipc_release_all(ctx);
+    // (No collective here: a rank whose peers are already gone must still be able to leave.  Callers that destroy
+    // contexts while the job goes on call rid_ctx_trim first, which closes the mappings everywhere before anything is
+    // freed.)
     for (auto &m : ctx->ipc) cudaIpcCloseMemHandle(m.ptr);
     ctx->ipc.clear();
     ctx->exported.clear();
@@ -153,6 +154,7 @@ extern "C" int rid_ctx_destroy(rid_ctx *ctx)
     if (ctx->prof_dev) cudaFree(ctx->prof_dev);
     if (ctx->i8_tiles) cudaFree(ctx->i8_tiles);
     if (ctx->comm && ctx->nccl && ctx->nccl->CommDestroy) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
+    for (int i = 0; i < 4; ++i) if (ctx->phase_ev[i]) cudaEventDestroy(ctx->phase_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -172,6 +174,11 @@ extern "C" int rid_ctx_sync(rid_ctx *ctx)
 extern "C" double rid_ctx_last_ms(const rid_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
 extern "C" long long rid_ctx_launches(const rid_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" long long rid_ctx_swaps(const rid_ctx *ctx) { return ctx ? ctx->swaps : 0; }
+extern "C" double rid_ctx_stat(const rid_ctx *ctx, int which)
+{
+    if (!ctx || which < 0 || which >= 8) return 0.0;
+    return which == 0 ? (double)ctx->swaps : ctx->stat[which];
+}
 
 // Collective when world > 1: closes the peers' mappings, then gives every cached device buffer back to the driver.
 extern "C" int rid_ctx_trim(rid_ctx *ctx)

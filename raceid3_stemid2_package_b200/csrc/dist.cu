@@ -424,6 +424,8 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
     rid_dmat *dm = new rid_dmat();
     dm->ctx = ctx;
     dm->N = N;
+    dm->world = ctx->world;
+    dm->rank = ctx->rank;
     shard_rows(N, ctx->rank, ctx->world, &dm->row0, &dm->row1);
     dm->ld = round_up((size_t)N, 128);
     size_t nloc = (size_t)(dm->row1 - dm->row0);
@@ -501,17 +503,18 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
 int rid_replica_start(rid_dmat *dm)
 {
     rid_ctx *ctx = dm->ctx;
-    if (ctx->world == 1 || !dm->full || !dm->peers_ok || dm->replica_state != 0) return RID_OK;
+    if (dm->world == 1 || !dm->full || !dm->peers_ok || dm->replica_state != 0) return RID_OK;
     if (!dm->replica_ev) RID_CUDA(cudaEventCreateWithFlags(&dm->replica_ev, cudaEventDisableTiming));
     RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->stream));
     RID_CUDA(cudaStreamWaitEvent(ctx->copy_stream, dm->replica_ev, 0));
     const bool whole = getenv("RID_REPLICA_FULL") != nullptr;
+    double pulled = 0.0;
     const int margin = getenv("RID_REPLICA_MARGIN") ? std::max(0, atoi(getenv("RID_REPLICA_MARGIN"))) : RID_REPLICA_MARGIN;
     bool all_whole = true;
-    for (int i = 1; i < ctx->world; ++i) {
-        const int s = (ctx->rank + i) % ctx->world; // staggered: in round i every source serves one destination
+    for (int i = 1; i < dm->world; ++i) {
+        const int s = (dm->rank + i) % dm->world; // staggered: in round i every source serves one destination
         int r0, r1;
-        shard_rows(dm->N, s, ctx->world, &r0, &r1);
+        shard_rows(dm->N, s, dm->world, &r0, &r1);
         if (r1 <= r0) continue;
         size_t lo = whole ? 0 : (size_t)std::max(0, r0 - margin) & ~(size_t)31;
         dm->replica_lo[s] = (int)lo;
@@ -519,8 +522,10 @@ int rid_replica_start(rid_dmat *dm)
         const size_t off = (size_t)s * dm->alloc_rows * dm->ld + lo;
         RID_CUDA(cudaMemcpy2DAsync(dm->full + off, dm->ld * sizeof(u32), dm->peer_full[s] + off, dm->ld * sizeof(u32),
                                    (dm->ld - lo) * sizeof(u32), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        pulled += (double)(dm->ld - lo) * sizeof(u32) * (double)(r1 - r0);
     }
-    dm->replica_lo[ctx->rank] = 0;
+    ctx->stat[5] = pulled;
+    dm->replica_lo[dm->rank] = 0;
     RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->copy_stream));
     dm->replica_state = all_whole ? 2 : 1;
     return RID_OK;
@@ -529,13 +534,13 @@ int rid_replica_start(rid_dmat *dm)
 int rid_replica_complete(rid_dmat *dm)
 {
     rid_ctx *ctx = dm->ctx;
-    if (ctx->world == 1 || !dm->full) return RID_OK;
+    if (dm->world == 1 || !dm->full) return RID_OK;
     if (dm->replica_state == 0) RID_TRY(rid_replica_start(dm));
     if (dm->replica_state == 2) return RID_OK;
-    for (int i = 1; i < ctx->world; ++i) {
-        const int s = (ctx->rank + i) % ctx->world;
+    for (int i = 1; i < dm->world; ++i) {
+        const int s = (dm->rank + i) % dm->world;
         int r0, r1;
-        shard_rows(dm->N, s, ctx->world, &r0, &r1);
+        shard_rows(dm->N, s, dm->world, &r0, &r1);
         const size_t lo = (size_t)dm->replica_lo[s];
         if (r1 <= r0 || lo == 0) continue;
         const size_t off = (size_t)s * dm->alloc_rows * dm->ld;
@@ -566,7 +571,7 @@ extern "C" int rid_dmat_free(rid_dmat *dm)
     if (dm->xraw) rid_pool_free(ctx, dm->xraw, dm->xraw_bytes);
     if (dm->full) rid_pool_free(ctx, dm->full, dm->full_bytes);
     else rid_pool_free(ctx, dm->D, dm->alloc_rows * dm->ld * sizeof(u32));
-    if (ctx->world > 1 && ctx->live_sharded > 0) ctx->live_sharded--;
+    if (dm->world > 1 && ctx->live_sharded > 0) ctx->live_sharded--;
     delete dm;
     return RID_OK;
 }

@@ -1787,7 +1787,7 @@ static int replica_begin(rid_dmat *dm, FullReplica *R)
 {
     rid_ctx *ctx = dm->ctx;
     R->active = false;
-    if (ctx->world == 1 || !dm->full || !dm->peers_ok || getenv("RID_NO_REPLICA")) return RID_OK;
+    if (dm->world == 1 || ctx->world == 1 || !dm->full || !dm->peers_ok || getenv("RID_NO_REPLICA")) return RID_OK;
     RID_TRY(rid_replica_start(dm)); // (no-op when the pulls are already under way)
     if (dm->replica_state == 0) return RID_OK;
     RID_CUDA(cudaStreamWaitEvent(ctx->stream, dm->replica_ev, 0));
@@ -1799,7 +1799,7 @@ static int replica_begin(rid_dmat *dm, FullReplica *R)
         v->row1 = dm->N;
         v->ld = dm->ld;
         v->D = dm->full;
-        v->alloc_rows = (size_t)ctx->world * dm->alloc_rows;
+        v->alloc_rows = (size_t)dm->world * dm->alloc_rows;
         v->bits = dm->bits;
         v->step = dm->step;
         v->parent = dm;
@@ -1834,7 +1834,7 @@ static void replica_end(FullReplica *R)
 // first cell of the super-tile row that holds the block's first subset cell.
 static bool replica_upper_suffices(const rid_dmat *parent, const std::vector<int> &ccells)
 {
-    const int world = parent->ctx->world > 1 ? parent->ctx->world : (int)(((size_t)parent->N + parent->alloc_rows - 1) / parent->alloc_rows);
+    const int world = parent->world;
     const size_t per = parent->alloc_rows;
     for (int s = 0; s < world && s < 16; ++s) {
         const int lo = parent->replica_lo[s];
@@ -2078,8 +2078,12 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     int c1_swaps = 0;
     int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
     if (rc != RID_OK) return rc;
+    for (int i = 0; i < 4; ++i)
+        if (!ctx->phase_ev[i]) RID_CUDA(cudaEventCreate(&ctx->phase_ev[i]));
+    RID_CUDA(cudaEventRecord(ctx->phase_ev[0], ctx->stream)); // c1 done
     FullReplica R;
     RID_TRY(replica_begin(dm, &R));
+    RID_CUDA(cudaEventRecord(ctx->phase_ev[1], ctx->stream)); // the replica (if any) has arrived
     rid_dmat *work = R.active ? R.full : dm; // the matrix the bootstrap PAM runs read
     const int nshare = R.active ? R.saved_world : 1, myshare = R.active ? R.saved_rank : 0;
     replica_local(&R, true);
@@ -2208,7 +2212,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             const int *slot = pin + (i - i0) * slot_ints;
             const PamState *st = (const PamState *)(slot + tab_off - 64);
             if (st->done) { ctx->swaps += st->nswaps; jaccard_row(slot + tab_off, mine[i]); }
-            else rc = run_sync(mine[i], nullptr); // more swaps than were enqueued ahead (rare): redo this one the plain way
+            else { ctx->stat[1] += 1.0; rc = run_sync(mine[i], nullptr); } // more swaps than were enqueued ahead (rare): redo this one the plain way
         }
     }
     if (d_tabs) cudaFree(d_tabs);
@@ -2231,7 +2235,16 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     }
     replica_end(&R);
     if (rc != RID_OK) return rc;
-    return rid_time_end(ctx);
+    RID_CUDA(cudaEventRecord(ctx->phase_ev[2], ctx->stream));
+    RID_TRY(rid_time_end(ctx));
+    {
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev0, ctx->phase_ev[0]);
+        cudaEventElapsedTime(&b, ctx->phase_ev[0], ctx->phase_ev[1]);
+        cudaEventElapsedTime(&c, ctx->phase_ev[1], ctx->phase_ev[2]);
+        ctx->stat[2] = a; ctx->stat[3] = b; ctx->stat[4] = c; ctx->stat[6] = (double)ahead;
+    }
+    return RID_OK;
 }
 
 extern "C" int rid_medoids(rid_dmat *dm, const int *labels, int N, int *medoid_idx, int *cluster_ids, int *n_clusters)

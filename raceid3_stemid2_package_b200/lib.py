@@ -21,7 +21,7 @@ SYMBOLS = [
     "rid_ctx_last_ms", "rid_ctx_launches", "rid_dist", "rid_dist_csc", "rid_dmat_from_host", "rid_dmat_free", "rid_dmat_info",
     "rid_shard_rows", "rid_ctx_profile", "rid_ctx_profile_get", "rid_ctx_event_record", "rid_ctx_event_elapsed_ms", "rid_measure_dmma_peak", "rid_measure_read_peak",
     "rid_dmat_sub", "rid_pam", "rid_gap_sweep", "rid_clusterboot", "rid_medoids", "rid_refresh", "rid_within_disp", "rid_knn", "rid_silhouette", "rid_cmdscale",
-    "rid_ctx_request_abort", "rid_ctx_clear_abort", "rid_ctx_set_interrupt_poll", "rid_measure_i8_peak", "rid_r_bootstrap_samples", "rid_ctx_swaps", "rid_ctx_trim",
+    "rid_ctx_request_abort", "rid_ctx_clear_abort", "rid_ctx_set_interrupt_poll", "rid_measure_i8_peak", "rid_r_bootstrap_samples", "rid_ctx_swaps", "rid_ctx_trim", "rid_ctx_stat",
 ]
 
 INTERRUPTED = -6  # RID_ERR_INTERRUPTED
@@ -57,6 +57,8 @@ def load() -> C.CDLL:
     L.rid_ctx_swaps.argtypes = [vp]
     L.rid_ctx_swaps.restype = C.c_longlong
     L.rid_ctx_trim.argtypes = [vp]
+    L.rid_ctx_stat.argtypes = [vp, C.c_int]
+    L.rid_ctx_stat.restype = C.c_double
     L.rid_ctx_request_abort.argtypes = [vp]
     L.rid_ctx_clear_abort.argtypes = [vp]
     L.rid_ctx_set_interrupt_poll.argtypes = [vp, vp, vp]
@@ -192,6 +194,10 @@ class Context:
     @property
     def swaps(self) -> int:
         return int(load().rid_ctx_swaps(self._h))
+
+    def stats(self) -> dict:
+        names = ("swaps", "boot_redone", "c1_ms", "replica_wait_ms", "replicates_ms", "replica_pull_bytes", "boot_ahead")
+        return {n: load().rid_ctx_stat(self._h, i) for i, n in enumerate(names)}
 
     def trim(self):
         _check(load().rid_ctx_trim(self._h))
