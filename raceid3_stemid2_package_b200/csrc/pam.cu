@@ -108,6 +108,12 @@ struct PamWs {
     int *hist2 = nullptr; // [3 * K2MAX]: counts, bases, cursors of the pair keys
     u64 *acc2 = nullptr;
     int *chg_count = nullptr; // rows whose cap changed in the last BUILD step
+    // lazy BUILD (complete views): per candidate column an upper bound of its gain, the step it was last exact at, the
+    // "cap dropped in the last step" flag; lz_thr = {stage-A threshold, best exact gain so far, rows evaluated, -}
+    u64 *lz_ub = nullptr;
+    int *lz_stamp = nullptr;
+    unsigned char *lz_chg = nullptr;
+    u64 *lz_thr = nullptr;
     // host mirrors for the current subset
     int m = 0, nls = 0;
     // the two pooled slabs every device array above is carved from
@@ -138,6 +144,7 @@ static size_t ws_carve_base(PamWs *w, char *base)
     carve(p, w->d_po, nl); carve(p, w->d_qo, nl); carve(p, w->d_pn, nl); carve(p, w->d_qn, nl);
     carve(p, w->hist2, (size_t)3 * K2MAX);
     carve(p, w->subset_cells, N); carve(p, w->colmap, N); carve(p, w->src_rows, nl);
+    carve(p, w->lz_ub, N + 128); carve(p, w->lz_stamp, N + 128); carve(p, w->lz_chg, N + 128); carve(p, w->lz_thr, 4);
     return (size_t)(p - base);
 }
 
@@ -1161,6 +1168,207 @@ __global__ void k_contingency(const int *__restrict__ subset, const int *__restr
     if (p < m) atomicAdd(&tab[part_slot[subset[p]] * k + lab_pos[p]], 1);
 }
 
+
+// ---- lazy BUILD ---------------------------------------------------------------------------------------------------
+// BUILD's gain of candidate h, g(h) = sum_j max(cap_j - D[j][h], 0), can only shrink when medoids are added (caps only
+// drop), so a gain that was exact at an earlier step is an upper bound now.  From the third pick on, a complete view
+// (one GPU holds every row, rows and columns are the same list) therefore evaluates exactly only the candidates that can
+// still win -- by symmetry g(h) is a reduction over ROW h, one contiguous read -- instead of rescanning every row whose
+// cap dropped:
+//   stage A: the candidates whose cap did not drop in the last step and whose bound lies within 2^-6 of the largest
+//            such bound are made exact; L = the best exact gain among them;
+//   stage B: every candidate whose bound is still >= L is made exact.  Now every candidate that is not exact has
+//            gain <= bound < L <= best, so the arg max over the exact ones (ties: largest position, like
+//            `ammax <= beter[i]`) is the arg max over all candidates: the pick is identical to a full evaluation.
+#define LZ_THREADS 256
+#define LZ_LOCAL 512
+
+// after the second pick's selection (SP = sum_j min(D[j][h], cap_j) is exact for the caps BEFORE that pick):
+// bound[h] = sum_j cap_j - SP[h]
+__global__ void __launch_bounds__(1024)
+k_lazy_init(const u64 *__restrict__ SP, const u32 *__restrict__ capP, int m, u64 *ub, int *stamp, unsigned char *chg, u64 *thr)
+{
+    __shared__ u64 sh[32];
+    u64 s = 0;
+    for (int t = threadIdx.x; t < m; t += blockDim.x) s += capP[t];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) sh[0] = s;
+    }
+    __syncthreads();
+    const u64 td = sh[0];
+    for (int h = threadIdx.x; h < m; h += blockDim.x) {
+        const u64 sp = SP[h];
+        ub[h] = td >= sp ? td - sp : 0ull;
+        stamp[h] = -1;
+        chg[h] = 0;
+    }
+    if (threadIdx.x == 0) { thr[0] = 0ull; thr[1] = 0ull; }
+}
+
+struct LzBest { u64 g; int pos, h; };
+__device__ __forceinline__ bool lz_better(const LzBest &a, const LzBest &b) // a beats b
+{
+    if (a.h < 0) return false;
+    if (b.h < 0) return true;
+    if (a.g != b.g) return a.g > b.g;
+    return a.pos > b.pos; // upstream BUILD: the largest index wins ties
+}
+__device__ __forceinline__ LzBest lz_block_best(LzBest v, LzBest *sh)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        LzBest b;
+        b.g = __shfl_down_sync(0xffffffffu, v.g, o);
+        b.pos = __shfl_down_sync(0xffffffffu, v.pos, o);
+        b.h = __shfl_down_sync(0xffffffffu, v.h, o);
+        if (lz_better(b, v)) v = b;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        LzBest e;
+        e.g = 0; e.pos = -1; e.h = -1;
+        v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : e;
+        for (int o = 16; o > 0; o >>= 1) {
+            LzBest b;
+            b.g = __shfl_down_sync(0xffffffffu, v.g, o);
+            b.pos = __shfl_down_sync(0xffffffffu, v.pos, o);
+            b.h = __shfl_down_sync(0xffffffffu, v.h, o);
+            if (lz_better(b, v)) v = b;
+        }
+        if (threadIdx.x == 0) sh[0] = v;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// One CTA.  finish_step >= 0: the pick of that step = arg max of the gains that are exact at it; the medoid is
+// installed and the caps drop along its row (D is symmetric: column h* of the point rows is row h*).
+// prepare != 0: thresholds of the next step's stage A.
+__global__ void __launch_bounds__(1024)
+k_lazy_serial(const u32 *__restrict__ M, size_t ld, int m, const int *__restrict__ pos_of, u32 *capP, unsigned char *is_med,
+              int *med, int *medpos, PamState *st, u64 *ub, const int *__restrict__ stamp, unsigned char *chg, u64 *thr,
+              int finish_step, int prepare)
+{
+    __shared__ LzBest shb[32];
+    if (finish_step >= 0) {
+        LzBest v;
+        v.g = 0; v.pos = -1; v.h = -1;
+        for (int h = threadIdx.x; h < m; h += blockDim.x) {
+            if (stamp[h] == finish_step && !is_med[h]) {
+                LzBest c;
+                c.g = ub[h]; c.pos = pos_of[h]; c.h = h;
+                if (lz_better(c, v)) v = c;
+            }
+        }
+        v = lz_block_best(v, shb);
+        const int hs = v.h; // (>= 0: stage A always evaluates at least the candidate with the largest bound)
+        if (threadIdx.x == 0 && hs >= 0) {
+            const int s = st->nmed;
+            med[s] = hs;
+            medpos[s] = v.pos;
+            is_med[hs] = 1;
+            st->nmed = s + 1;
+            st->best_h = hs; st->best_slot = s; st->best_val = v.g;
+        }
+        __syncthreads();
+        if (hs >= 0) {
+            const u32 *row = M + (size_t)hs * ld;
+            for (int t = threadIdx.x; t < m; t += blockDim.x) {
+                const u32 d = row[t], old = capP[t];
+                chg[t] = d < old ? 1 : 0;
+                if (d < old) capP[t] = d;
+            }
+        }
+        __syncthreads();
+    }
+    if (prepare) {
+        // the largest bound among the candidates whose own cap did not just drop (those are the stale ones: the cluster
+        // the last pick covers); without any such candidate, among all of them
+        u64 a = 0, b = 0;
+        for (int h = threadIdx.x; h < m; h += blockDim.x) {
+            if (is_med[h]) continue;
+            const u64 u = ub[h];
+            b = u > b ? u : b;
+            if (!chg[h]) a = u > a ? u : a;
+        }
+        LzBest v;
+        v.g = a; v.pos = 0; v.h = 0;
+        v = lz_block_best(v, shb);
+        a = v.g;
+        v.g = b; v.pos = 0; v.h = 0;
+        v = lz_block_best(v, shb);
+        b = v.g;
+        if (threadIdx.x == 0) {
+            const u64 top = a ? a : b;
+            thr[0] = top - (top >> 6);
+            thr[1] = 0ull;  // L: best exact gain of the step (atomicMax by the evaluations)
+            thr[3] = a ? 0ull : 1ull; // 1: no unchanged candidate is left, stage A looks at all of them
+        }
+    }
+}
+
+// stage 0 (A): candidates with bound >= thr[0] whose cap did not just drop; stage 1 (B): bound >= thr[1] = L.
+// A CTA checks a strided share of the candidates, then makes its eligible ones exact, one row each.
+__global__ void __launch_bounds__(LZ_THREADS)
+k_lazy_eval(const u32 *__restrict__ M, size_t ld, int m, const u32 *__restrict__ capP, const unsigned char *__restrict__ is_med,
+            const unsigned char *__restrict__ chg, u64 *ub, int *stamp, int step, int stage, u64 *thr, u64 *prof_dev)
+{
+    __shared__ int sh_list[LZ_LOCAL];
+    __shared__ int sh_n;
+    __shared__ u64 sh_red[LZ_THREADS / 32];
+    if (threadIdx.x == 0) sh_n = 0;
+    __syncthreads();
+    const u64 t = thr[stage];
+    const bool all = stage == 1 || thr[3] != 0ull;
+    for (int i = threadIdx.x; (long long)i * gridDim.x + blockIdx.x < m; i += LZ_THREADS) {
+        const int h = i * gridDim.x + blockIdx.x;
+        if (!is_med[h] && stamp[h] != step && ub[h] >= t && (all || !chg[h])) {
+            const int q = atomicAdd(&sh_n, 1);
+            if (q < LZ_LOCAL) sh_list[q] = h;
+        }
+    }
+    __syncthreads();
+    const int n = min(sh_n, LZ_LOCAL); // (the grid is sized so that a CTA's share never exceeds LZ_LOCAL)
+    const int m4 = m & ~3;
+    for (int q = 0; q < n; ++q) {
+        const int h = sh_list[q];
+        const u32 *row = M + (size_t)h * ld;
+        u64 acc = 0;
+        for (int c = threadIdx.x * 4; c < m4; c += LZ_THREADS * 4) {
+            const uint4 d = ld_stream(row + c);
+            const uint4 cp = *reinterpret_cast<const uint4 *>(capP + c);
+            acc += (u64)(cp.x - min(d.x, cp.x)) + (u64)(cp.y - min(d.y, cp.y)) + (u64)(cp.z - min(d.z, cp.z)) +
+                   (u64)(cp.w - min(d.w, cp.w));
+        }
+        if (threadIdx.x < m - m4) {
+            const u32 d = row[m4 + threadIdx.x], cp = capP[m4 + threadIdx.x];
+            acc += (u64)(cp - min(d, cp));
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh_red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 g = 0;
+#pragma unroll
+            for (int wv = 0; wv < LZ_THREADS / 32; ++wv) g += sh_red[wv];
+            ub[h] = g;
+            stamp[h] = step;
+            atomicMax((unsigned long long *)&thr[1], (unsigned long long)g);
+            if (prof_dev) {
+                atomicAdd((unsigned long long *)prof_dev, (unsigned long long)m);
+                atomicAdd((unsigned long long *)prof_dev + 1, (unsigned long long)ld);
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // host orchestration
 // ----------------------------------------------------------------------------------------------------------
@@ -1412,7 +1620,12 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
     rid_ctx *ctx = dm->ctx;
     u64 *SP = w->acc + 4, *AQ0 = SP + w->ld;
     auto sel_build = k_select<true>;
-    for (int s = k_from; s < k_to; ++s) {
+    // lazy evaluation from the third pick on (see k_lazy_eval): complete views only -- every row on this GPU, rows and
+    // columns the same list in the same order (the compact copy, or the whole matrix)
+    const bool lazy = k_from == 0 && k_to > 2 && ctx->world == 1 && w->nls == w->m && dm->row0 == 0 &&
+                      (w->compact || w->m == dm->N) && !getenv("RID_BUILD_FULL");
+    const int k_scan_to = lazy ? 2 : k_to;
+    for (int s = k_from; s < k_scan_to; ++s) {
         if (s == 0) {
             if (!w->sp0_ready) {
                 RID_TRY(zero_acc(dm, w, 0, 0));
@@ -1431,9 +1644,28 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
                w->is_med, w->blockbest, w->state, 0, s > 0 ? AQ0 : (u64 *)nullptr, w->chg_count,
                ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr);
+        if (lazy && s == 1) // SP is exact for the caps before this pick: the gains it implies bound every later gain
+            LAUNCH(ctx, k_lazy_init, 1, 1024, 0, SP, w->capP, w->m, w->lz_ub, w->lz_stamp, w->lz_chg, w->lz_thr);
         if (w->nls)
             LAUNCH(ctx, k_build_update, nblk(w->nls, 256), 256, 0, w->mat, w->ld, w->rows, w->nls, w->capP,
                    w->state, w->chg_count, w->s_row, w->s_capP, w->s_capQ, w->s_grp);
+        RID_CUDA(cudaGetLastError());
+    }
+    if (lazy) {
+        // a CTA of the evaluation kernels checks ceil(m / grid) candidates: at most LZ_LOCAL
+        const int grid = std::max(std::min(w->m, ctx->sm_count * 8), (w->m + LZ_LOCAL - 1) / LZ_LOCAL);
+        u64 *pd = ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr;
+        for (int s = 2; s <= k_to; ++s) {
+            // finishes step s - 1 (pick + caps) when that was a lazy step, prepares step s
+            LAUNCH(ctx, k_lazy_serial, 1, 1024, 0, w->mat, w->ld, w->m, w->pos_of, w->capP, w->is_med, w->med, w->medpos,
+                   w->state, w->lz_ub, w->lz_stamp, w->lz_chg, w->lz_thr, s > 2 ? s - 1 : -1, s < k_to ? 1 : 0);
+            if (s == k_to) break;
+            cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_BUILD);
+            for (int stage = 0; stage < 2; ++stage)
+                LAUNCH(ctx, k_lazy_eval, grid, LZ_THREADS, 0, w->mat, w->ld, w->m, w->capP, w->is_med, w->lz_chg, w->lz_ub,
+                       w->lz_stamp, s, stage, w->lz_thr, pd);
+            rid_prof_end(ctx, pe, RID_PROF_SCAN_BUILD, 0.0, 0.0);
+        }
         RID_CUDA(cudaGetLastError());
     }
     return RID_OK;

@@ -357,3 +357,54 @@ def test_int8_peak_measurement_is_sane(ctx):
     """rid_measure_i8_peak (bench.py's tensor ceiling): between half and 1.3x the nominal 4.5 POP/s dense int8 rate."""
     v = ctx.measure_i8_peak()
     assert 1500.0 < v < 6000.0, v
+
+
+@pytest.mark.parametrize("case", ["clusters", "ties", "curve", "subset_compact", "euclid31"])
+def test_build_lazy_equals_full_rescan(ctx, oracle, case, monkeypatch):
+    """BUILD's lazy evaluation (exact gains only for the candidates whose upper bound can still win, from the third pick
+    on) against the incremental rescans (RID_BUILD_FULL=1) and the oracle: identical picks, including exact ties
+    (largest index wins) and the 31-bit grid."""
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    rng = np.random.default_rng(11)
+    subset = None
+    if case == "clusters":
+        x, _ = synth_features_numpy(1500, 200, 7, 3)
+        dm = ctx.dist_cellmajor(x, "pearson")
+        ks = (3, 8, 25)
+    elif case == "ties":
+        D = rng.integers(1, 4, size=(300, 300)).astype(np.float64)  # three distinct values: ties everywhere
+        D = np.triu(D, 1)
+        D = D + D.T
+        dm = ctx.from_matrix(D)
+        ks = (3, 9, 40)
+    elif case == "curve":
+        t = np.sort(rng.uniform(0, 1, 900))
+        P = np.stack([t, np.sin(7 * t), np.cos(3 * t) * t]) + rng.normal(0, 0.01, (3, 900))
+        dm = ctx.dist(P, "euclidean")
+        ks = (4, 12, 30)
+    elif case == "subset_compact":
+        x, _ = synth_features_numpy(1800, 150, 5, 8)
+        x[100] = x[7]
+        dm = ctx.dist_cellmajor(x, "spearman")
+        subset = rng.permutation(1800)[:1100].astype(np.int32)  # 1100^2 words > 1 MB: the compact symmetric copy
+        ks = (3, 10)
+    else:
+        P = rng.normal(size=(700, 4)) * 900.0
+        D = np.sqrt(((P[:, None, :] - P[None, :, :]) ** 2).sum(-1))
+        dm = ctx.from_matrix(D)
+        ks = (5, 17)
+    Dg = dm.as_matrix()
+    for k in ks:
+        monkeypatch.delenv("RID_BUILD_FULL", raising=False)
+        a = dm.pam(k, subset=subset)
+        monkeypatch.setenv("RID_BUILD_FULL", "1")
+        b = dm.pam(k, subset=subset)
+        monkeypatch.delenv("RID_BUILD_FULL", raising=False)
+        o = oracle.pam(Dg, k, subset=subset)
+        for r in (a, b):
+            assert np.array_equal(r["id_med"], o["id_med"]) and np.array_equal(r["clustering"], o["clustering"])
+            assert r["n_swaps"] == o["n_swaps"] and np.allclose(r["objective"], o["objective"], rtol=1e-13, atol=1e-13)
+    lw = dm.gap_sweep(12, subset=subset)
+    assert np.max(np.abs(lw - oracle.gap_sweep(Dg, 12, subset=subset))) < 1e-12
+    dm.free()
