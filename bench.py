@@ -422,8 +422,11 @@ def main():
             barrier()
             ctx.event_record(0)
             t0 = time.perf_counter()
+            walls = []
             for _ in range(steps):
+                ts = time.perf_counter()
                 self.step()
+                walls.append((time.perf_counter() - ts) * 1e3)
             ctx.event_record(1)
             barrier()
             wall = time.perf_counter() - t0
@@ -434,7 +437,8 @@ def main():
             ms, wl = allmax([dev_ms, wall * 1e3])
             swaps = allsum([ctx.swaps - s0])[0]
             return {"ms_per_step": ms / steps, "wall_ms_per_step": wl / steps, "launches": ctx.launches - l0,
-                    "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": ctx.stats()}
+                    "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": ctx.stats(),
+                    "step_wall_ms_rank0": walls}
 
     # ---- headline: resident leg, W warm-up + K timed steps ---------------------------------------------------
     W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure)
@@ -642,6 +646,7 @@ def main():
     detail["bootmean_min"] = float(np.min(state["bootmean"]))
     detail["roofline_all"] = roofs
     detail["lib_stats_rank0_last_step"] = res["lib_stats_rank0_last_step"]
+    detail["step_wall_ms_rank0"] = res["step_wall_ms_rank0"]
     detail["ceilings_measured_here"] = {"int8_tops": i8_peak, "fp64_dmma_tflops": dmma_peak, "read_only_stream_gbs": read_peak}
     if e2e_detail:
         detail["e2e"] = e2e_detail

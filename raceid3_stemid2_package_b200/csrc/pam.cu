@@ -1622,8 +1622,13 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
     auto sel_build = k_select<true>;
     // lazy evaluation from the third pick on (see k_lazy_eval): complete views only -- every row on this GPU, rows and
     // columns the same list in the same order (the compact copy, or the whole matrix)
+    // OPT-IN (RID_BUILD_LAZY=1): exact, but measured 2.6x SLOWER than the incremental rescans on the benchmark data
+    // (19 ms instead of 6.5 ms of BUILD per bootstrap replicate at cfg4): in a few thousand dimensions every new medoid
+    // lowers the caps of 1/(s+1) of ALL points, so every candidate's gain keeps shrinking and bounds that are a few
+    // steps old certify nothing -- stage B ends up re-evaluating most rows.  Kept for low-dimensional / well-separated
+    // inputs and as a cross-check of the incremental path (tests/test_gpu_round2.py).
     const bool lazy = k_from == 0 && k_to > 2 && ctx->world == 1 && w->nls == w->m && dm->row0 == 0 &&
-                      (w->compact || w->m == dm->N) && !getenv("RID_BUILD_FULL");
+                      (w->compact || w->m == dm->N) && getenv("RID_BUILD_LAZY") != nullptr;
     const int k_scan_to = lazy ? 2 : k_to;
     for (int s = k_from; s < k_scan_to; ++s) {
         if (s == 0) {

@@ -361,9 +361,9 @@ def test_int8_peak_measurement_is_sane(ctx):
 
 @pytest.mark.parametrize("case", ["clusters", "ties", "curve", "subset_compact", "euclid31"])
 def test_build_lazy_equals_full_rescan(ctx, oracle, case, monkeypatch):
-    """BUILD's lazy evaluation (exact gains only for the candidates whose upper bound can still win, from the third pick
-    on) against the incremental rescans (RID_BUILD_FULL=1) and the oracle: identical picks, including exact ties
-    (largest index wins) and the 31-bit grid."""
+    """BUILD's opt-in lazy evaluation (RID_BUILD_LAZY=1: exact gains only for the candidates whose upper bound can still
+    win, from the third pick on) against the default incremental rescans and the oracle: identical picks, including
+    exact ties (largest index wins) and the 31-bit grid."""
     from raceid3_stemid2_package_b200.synth import synth_features_numpy
 
     rng = np.random.default_rng(11)
@@ -396,11 +396,10 @@ def test_build_lazy_equals_full_rescan(ctx, oracle, case, monkeypatch):
         ks = (5, 17)
     Dg = dm.as_matrix()
     for k in ks:
-        monkeypatch.delenv("RID_BUILD_FULL", raising=False)
+        monkeypatch.setenv("RID_BUILD_LAZY", "1")
         a = dm.pam(k, subset=subset)
-        monkeypatch.setenv("RID_BUILD_FULL", "1")
+        monkeypatch.delenv("RID_BUILD_LAZY", raising=False)
         b = dm.pam(k, subset=subset)
-        monkeypatch.delenv("RID_BUILD_FULL", raising=False)
         o = oracle.pam(Dg, k, subset=subset)
         for r in (a, b):
             assert np.array_equal(r["id_med"], o["id_med"]) and np.array_equal(r["clustering"], o["clustering"])
