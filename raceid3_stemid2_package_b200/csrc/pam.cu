@@ -94,6 +94,12 @@ struct PamWs {
     const u32 *mat = nullptr;
     bool compact = false;
     bool sp0_ready = false;     // the compaction pass already left BUILD's step-0 sums in acc
+    // BUILD's first pick known before the compaction (rid_clusterboot computes the step-0 column sums of ALL replicates in
+    // a few batched passes over the resident matrix): the compaction then accumulates the sums of the SECOND step,
+    // sum_j min(D[j][h], D[j][h0]), and the full rescan that step used to cost disappears
+    bool sp1_ready = false;
+    const int2 *first_dev = nullptr; // (cell, position) of the first medoid, on the device
+    u32 *firstcap = nullptr;         // [nloc] D[j][h0] by compact row
     u32 *cbuf = nullptr;        // compact copy (owned subset rows x ldc)
     size_t cbuf_bytes = 0;
     int *subset_cells = nullptr; // [N] cell by position (== subset unless compact)
@@ -145,6 +151,7 @@ static size_t ws_carve_base(PamWs *w, char *base)
     carve(p, w->hist2, (size_t)3 * K2MAX);
     carve(p, w->subset_cells, N); carve(p, w->colmap, N); carve(p, w->src_rows, nl);
     carve(p, w->lz_ub, N + 128); carve(p, w->lz_stamp, N + 128); carve(p, w->lz_chg, N + 128); carve(p, w->lz_thr, 4);
+    carve(p, w->firstcap, nl + 128);
     return (size_t)(p - base);
 }
 
@@ -933,10 +940,11 @@ k_wk_batch(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows, c
 #pragma unroll
                 for (int q = 0; q < WB; ++q) {
                     const u32 eq = __vcmpeq4(clab[q], (u32)sh_lab[q][r + u] * 0x01010101u); // 0xFF per equal byte
-                    p32[q][0] += d[u].x & (0u - (eq & 1u));
-                    p32[q][1] += d[u].y & (0u - ((eq >> 8) & 1u));
-                    p32[q][2] += d[u].z & (0u - ((eq >> 16) & 1u));
-                    p32[q][3] += d[u].w & (0u - ((eq >> 24) & 1u));
+                    // byte c of eq spread over a word by one PRMT (selector 8|c: replicate the byte's sign bit)
+                    p32[q][0] += d[u].x & __byte_perm(eq, 0u, 0x8888u);
+                    p32[q][1] += d[u].y & __byte_perm(eq, 0u, 0x9999u);
+                    p32[q][2] += d[u].z & __byte_perm(eq, 0u, 0xAAAAu);
+                    p32[q][3] += d[u].w & __byte_perm(eq, 0u, 0xBBBBu);
                 }
                 if ((u % FLUSH) == FLUSH - 1) {
 #pragma unroll
@@ -1062,10 +1070,13 @@ k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows
 #define CS_S 512       // super-tile edge (compact rows and columns)
 #define CS_R 32        // rows staged per transposition
 #define CS_THREADS 256
-#define CS_SMEM (CS_S * CS_R * 4 + CS_S * 8 + CS_S * 4)
+// CAPS: `cap` (by compact index) holds D[j][h0] for the first medoid h0 and the sums become BUILD's second-step sums
+// sum_j min(D[j][h], cap_j): the tile's column sums with the caps of its rows, the mirrored tile's with those of its columns.
+#define CS_SMEM (CS_S * CS_R * 4 + CS_S * 8 + CS_S * 4 + 2 * CS_S * 4)
+template <bool CAPS>
 __global__ void __launch_bounds__(CS_THREADS, 2)
 k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccells, u32 *__restrict__ out, size_t ldc,
-              int m, u64 *__restrict__ SP0)
+              int m, u64 *__restrict__ SP0, const u32 *__restrict__ cap)
 {
     const int bj = blockIdx.x, bi = blockIdx.y;
     if (bi > bj) return;
@@ -1073,6 +1084,8 @@ k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccel
     uint4 *tile = reinterpret_cast<uint4 *>(cs_smem);                   // [CS_S columns][8 chunks of 4 rows], swizzled
     u64 *rowacc = reinterpret_cast<u64 *>(cs_smem + CS_S * CS_R * 4);   // [CS_S] row sums of the super-tile
     int *sh_src = reinterpret_cast<int *>(rowacc + CS_S);               // [CS_S] source row of each tile row
+    u32 *rowcap = reinterpret_cast<u32 *>(sh_src + CS_S);               // [CS_S] caps of the tile's rows / columns (CAPS)
+    u32 *colcap = rowcap + CS_S;
     const bool mirror = bi < bj;
     const int tid = threadIdx.x;
     const int I0 = bi * CS_S, J0 = bj * CS_S;
@@ -1080,6 +1093,10 @@ k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccel
     for (int i = tid; i < CS_S; i += CS_THREADS) {
         sh_src[i] = ccells[I0 + min(i, nr - 1)];
         rowacc[i] = 0ull;
+        if (CAPS) {
+            rowcap[i] = I0 + i < m ? cap[I0 + i] : 0u;
+            colcap[i] = J0 + i < m ? cap[J0 + i] : 0u;
+        }
     }
     __syncthreads();
     const int t = tid & 127, h = tid >> 7;
@@ -1113,8 +1130,14 @@ k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccel
                 for (int c = 0; c < 4; ++c) v[u][c] = (row_in && keep[c]) ? v[u][c] : 0u;
                 if (row_in && col_in)
                     *reinterpret_cast<uint4 *>(out + (size_t)(I0 + r + u) * ldc + c0) = make_uint4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                if (CAPS) {
+                    const u32 rc = rowcap[min(r + u, CS_S - 1)];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) p32[c] += v[u][c];
+                    for (int c = 0; c < 4; ++c) p32[c] += min(v[u][c], rc);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) p32[c] += v[u][c];
+                }
                 if (u & 1) { // two rows of q < 2^31 fit 32 bits
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { sum[c] += p32[c]; p32[c] = 0; }
@@ -1139,7 +1162,12 @@ k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccel
                 const int cc = p * 32 + warp * 4 + (lane >> 3);
                 const uint4 x = tile[cc * 8 + (q ^ ((cc >> 2) & 7))];
                 if (J0 + cc < m) *reinterpret_cast<uint4 *>(out + (size_t)(J0 + cc) * ldc + I0 + rs + 4 * q) = x;
-                racc[0] += x.x; racc[1] += x.y; racc[2] += x.z; racc[3] += x.w;
+                if (CAPS) {
+                    const u32 cc_cap = colcap[cc];
+                    racc[0] += min(x.x, cc_cap); racc[1] += min(x.y, cc_cap); racc[2] += min(x.z, cc_cap); racc[3] += min(x.w, cc_cap);
+                } else {
+                    racc[0] += x.x; racc[1] += x.y; racc[2] += x.z; racc[3] += x.w;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1369,6 +1397,116 @@ k_lazy_eval(const u32 *__restrict__ M, size_t ld, int m, const u32 *__restrict__
     }
 }
 
+
+// ---- BUILD's first pick of MANY subsets in a few passes over the resident matrix ------------------------------------
+// Step 0 of BUILD needs the column sums over the subset's rows, SP0_b[h] = sum_{j in S_b} D[j][h].  For the bootstrap
+// replicates of one clusterboot call the subsets are known up front, so the sums of BP replicates are taken in ONE pass
+// over the rows this rank owns (a row contributes to the replicates whose bit is set in its mask): 50 replicates cost 5
+// passes instead of a share of 50 compaction passes, and each replicate's first medoid is known before its compaction.
+#define CSB 10
+template <int FLUSH>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_colsum_batch(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chunk,
+               const unsigned short *__restrict__ mask /* [nrows]: bit b = the row belongs to replicate b of the batch */,
+               u64 *__restrict__ out /* [CSB][ld] */)
+{
+    __shared__ unsigned short sh_m[SCAN_MAXROWS];
+    const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+    const bool active = col < ld;
+    u64 acc[CSB][4];
+    u32 p32[CSB][4];
+#pragma unroll
+    for (int b = 0; b < CSB; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[b][c] = 0; p32[b][c] = 0; }
+    bool any = false;
+    for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < nrows; chunk += gridDim.y) {
+        const int r_begin = chunk * rows_per_chunk;
+        const int nr = min(nrows - r_begin, rows_per_chunk);
+        const int nr8 = (nr + 7) & ~7;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr8; i += SCAN_THREADS) sh_m[i] = i < nr ? mask[r_begin + i] : (unsigned short)0;
+        __syncthreads();
+        if (!active) continue;
+        any = true;
+        for (int r = 0; r < nr8; r += 8) {
+            uint4 d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                d[u] = sh_m[r + u] ? ld_stream(D + (size_t)(r_begin + r + u) * ld + col) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned mk = sh_m[r + u]; // uniform across the CTA
+#pragma unroll
+                for (int b = 0; b < CSB; ++b)
+                    if ((mk >> b) & 1u) { p32[b][0] += d[u].x; p32[b][1] += d[u].y; p32[b][2] += d[u].z; p32[b][3] += d[u].w; }
+                if ((u % FLUSH) == FLUSH - 1) {
+#pragma unroll
+                    for (int b = 0; b < CSB; ++b)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { acc[b][c] += p32[b][c]; p32[b][c] = 0; }
+                }
+            }
+        }
+    }
+    if (!any) return;
+#pragma unroll
+    for (int b = 0; b < CSB; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (acc[b][c]) red_add_u64(out + (size_t)b * ld + col + c, acc[b][c]);
+}
+
+// one CTA per replicate: arg min of SP0 over the replicate's cells, ties to the LARGEST position (cand_better_build)
+__global__ void __launch_bounds__(256)
+k_first_medoid(const u64 *__restrict__ sp0 /* [.][ld] */, size_t ld, const int *__restrict__ cat, const long long *__restrict__ off,
+               const int *__restrict__ rep_of_slot, int2 *__restrict__ first /* by replicate */)
+{
+    __shared__ Cand sh[32];
+    const int b = rep_of_slot[blockIdx.x];
+    const int *cells = cat + off[b];
+    const int m = (int)(off[b + 1] - off[b]);
+    const u64 *sp = sp0 + (size_t)blockIdx.x * ld;
+    Cand best;
+    best.val = ~0ull; best.p = -1; best.mp = 0; best.slot = 0;
+    for (int p = threadIdx.x; p < m; p += blockDim.x) {
+        Cand x;
+        x.val = sp[cells[p]]; x.p = p; x.mp = 0; x.slot = 0;
+        if (cand_better_build(x, best)) best = x;
+    }
+    best = cand_reduce_block<true>(best, sh);
+    if (threadIdx.x == 0) first[b] = make_int2(cells[best.p], best.p);
+}
+
+// cap[c] = D[cell_c][h0] for the compact columns c of a replicate; read as D[min][max] so that a replica that holds only
+// the upper part of the peers' row blocks serves it
+__global__ void k_first_caps(const u32 *__restrict__ D, size_t ld, const int2 *__restrict__ first, const int *__restrict__ ccells,
+                             int m, u32 *__restrict__ cap)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const int h0 = first->x, cell = ccells[c];
+    const int lo = min(h0, cell), hi = max(h0, cell);
+    cap[c] = D[(size_t)lo * ld + hi];
+}
+
+// the first medoid of a run whose compaction already produced the second step's sums: caps, medoid tables, state
+__global__ void k_install_first(const int2 *__restrict__ first, const int *__restrict__ subset /* column by position */,
+                                const u32 *__restrict__ cap, int nls, u32 *capP, int *med, int *medpos, unsigned char *is_med,
+                                PamState *st)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) capP[t] = cap[t];
+    if (t == 0) {
+        const int p0 = first->y, c0 = subset[p0];
+        med[0] = c0;
+        medpos[0] = p0;
+        is_med[c0] = 1;
+        st->nmed = 1;
+        st->best_h = c0; st->best_slot = 0;
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // host orchestration
 // ----------------------------------------------------------------------------------------------------------
@@ -1468,7 +1606,7 @@ static int replica_need_whole(rid_dmat *dm)
     return RID_OK;
 }
 
-static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = nullptr)
+static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = nullptr, const int2 *first = nullptr)
 {
     rid_ctx *ctx = dm->ctx;
     const int N = dm->N, m = H.m;
@@ -1505,6 +1643,7 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
             RID_CUDA(cudaMemcpyAsync(w->subset_cells, stage_table(pin, H.cells), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             // SP (BUILD step 0) is accumulated by the compaction pass
             RID_CUDA(cudaMemsetAsync(w->acc, 0, (4 + ldc) * sizeof(u64), ctx->stream));
+            w->sp1_ready = false;
             if (w->nls) {
                 RID_CUDA(cudaMemcpyAsync(w->rows, stage_table(pin, H.iota), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
                 RID_CUDA(cudaMemcpyAsync(w->rows_pos, stage_table(pin, H.rows_pos), (size_t)w->nls * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -1516,10 +1655,22 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 if (sym) {
                     // (per device and cheap: set on every call rather than once per process)
-                    RID_CUDA(cudaFuncSetAttribute(k_compact_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+                    auto kc0 = k_compact_sym<false>;
+                    auto kc1 = k_compact_sym<true>;
+                    RID_CUDA(cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+                    RID_CUDA(cudaFuncSetAttribute(kc1, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
                     const unsigned nb = (unsigned)((m + CS_S - 1) / CS_S);
-                    LAUNCH(ctx, k_compact_sym, dim3(nb, nb), CS_THREADS, CS_SMEM, dm->D, dm->ld, w->colmap, w->cbuf, ldc, m,
-                           w->acc + 4);
+                    if (first) {
+                        // the first medoid is known: its distances cap every term, the sums are those of BUILD's second step
+                        LAUNCH(ctx, k_first_caps, nblk(m, 256), 256, 0, dm->D, dm->ld, first, w->colmap, m, w->firstcap);
+                        LAUNCH(ctx, kc1, dim3(nb, nb), CS_THREADS, CS_SMEM, dm->D, dm->ld, w->colmap, w->cbuf, ldc, m,
+                               w->acc + 4, w->firstcap);
+                        w->sp1_ready = true;
+                        w->first_dev = first;
+                    } else {
+                        LAUNCH(ctx, kc0, dim3(nb, nb), CS_THREADS, CS_SMEM, dm->D, dm->ld, w->colmap, w->cbuf, ldc, m,
+                               w->acc + 4, (const u32 *)nullptr);
+                    }
                     // useful bytes: the upper triangle gathered once + the square written; requested: the source spans
                     // of the gathered tiles (whole sectors: ~N/m source columns per compact column) + the square
                     const double tri = 0.5 * (double)m * ((double)m + 1.0);
@@ -1546,6 +1697,7 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
     RID_TRY(replica_need_whole(dm)); // (whole rows are read)
     w->compact = false;
     w->sp0_ready = false;
+    w->sp1_ready = false;
     w->mat = dm->D;
     w->ld = dm->ld;
     const int *h_cells = stage_table(pin, H.cells);
@@ -1630,8 +1782,20 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
     const bool lazy = k_from == 0 && k_to > 2 && ctx->world == 1 && w->nls == w->m && dm->row0 == 0 &&
                       (w->compact || w->m == dm->N) && getenv("RID_BUILD_LAZY") != nullptr;
     const int k_scan_to = lazy ? 2 : k_to;
-    for (int s = k_from; s < k_scan_to; ++s) {
-        if (s == 0) {
+    // the compaction already produced the sums of the second pick (first medoid known up front): install the first medoid
+    // and go straight to that pick's selection
+    const bool have_first = w->sp1_ready && w->sp0_ready && k_from == 0 && k_to >= 2;
+    w->sp1_ready = false;
+    if (have_first) {
+        w->sp0_ready = false;
+        LAUNCH(ctx, k_install_first, nblk(std::max(w->nls, 1), 256), 256, 0, w->first_dev, w->subset, w->firstcap, w->nls, w->capP,
+               w->med, w->medpos, w->is_med, w->state);
+        RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream)); // the delta buffer of the next pick's rescan
+    }
+    for (int s = have_first ? 1 : k_from; s < k_scan_to; ++s) {
+        if (have_first && s == 1) {
+            // SP is exact already: nothing to rescan, nothing to subtract
+        } else if (s == 0) {
             if (!w->sp0_ready) {
                 RID_TRY(zero_acc(dm, w, 0, 0));
                 RID_TRY((launch_scan<0>(dm, w, w->rows, w->capP, nullptr, nullptr, w->nls, nullptr, 0, RID_PROF_SCAN_BUILD)));
@@ -1647,7 +1811,7 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         }
         // picks the next medoid; for s > 0 it first applies SP -= AQ0 (and clears AQ0 and the changed-row counter)
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
-               w->is_med, w->blockbest, w->state, 0, s > 0 ? AQ0 : (u64 *)nullptr, w->chg_count,
+               w->is_med, w->blockbest, w->state, 0, (s > 0 && !(have_first && s == 1)) ? AQ0 : (u64 *)nullptr, w->chg_count,
                ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr);
         if (lazy && s == 1) // SP is exact for the caps before this pick: the gains it implies bound every later gain
             LAUNCH(ctx, k_lazy_init, 1, 1024, 0, SP, w->capP, w->m, w->lz_ub, w->lz_stamp, w->lz_chg, w->lz_thr);
@@ -2300,6 +2464,59 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
     return rid_time_end(ctx);
 }
 
+// BUILD's first pick of every bootstrap replicate, before any replicate starts: the step-0 column sums of CSB replicates
+// per pass over this rank's rows (k_colsum_batch), summed over the ranks, then the arg min per replicate
+// (k_first_medoid).  Runs on the sharded matrix with the real world size (before any switch to a replica).
+// d_first[b] = (cell, position) for every replicate b; d_cat / d_off are the samples on the device.
+static int boot_first_medoids(rid_dmat *dm, const int *samples, const int *sample_len, int B, int2 *d_first, int *d_cat,
+                              long long *d_off, u64 *d_sp0 /* [CSB][ld] */, int *d_rep /* [CSB] */,
+                              unsigned short *d_mask /* [nloc] */)
+{
+    rid_ctx *ctx = dm->ctx;
+    const int nloc = dm->row1 - dm->row0;
+    std::vector<long long> off(B + 1, 0);
+    for (int b = 0; b < B; ++b) off[b + 1] = off[b] + sample_len[b];
+    RID_CUDA(cudaMemcpyAsync(d_cat, samples, (size_t)off[B] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<unsigned short> hm((size_t)std::max(nloc, 1));
+    int strips = (int)((dm->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
+    int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
+    int rpc = std::min(std::max((((nloc + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
+    dim3 grid(strips, std::max(1, std::min((nloc + rpc - 1) / rpc, want_y * 2)));
+    for (int b0 = 0; b0 < B; b0 += CSB) {
+        const int nb = std::min(CSB, B - b0);
+        std::fill(hm.begin(), hm.end(), (unsigned short)0);
+        int rep[CSB];
+        for (int r = 0; r < CSB; ++r) rep[r] = b0 + std::min(r, nb - 1);
+        for (int r = 0; r < nb; ++r) {
+            const int *sp = samples + off[b0 + r];
+            const int len = sample_len[b0 + r];
+            for (int p = 0; p < len; ++p) {
+                const int h = sp[p];
+                if (h < 0 || h >= dm->N) { rid_set_error("bootstrap sample index %d out of range", h); return RID_ERR_ARG; }
+                if (h >= dm->row0 && h < dm->row1) hm[h - dm->row0] |= (unsigned short)(1u << r);
+            }
+        }
+        // (pageable sources: staged by the time the calls return, so hm / rep may be rewritten for the next batch)
+        if (nloc) RID_CUDA(cudaMemcpyAsync(d_mask, hm.data(), (size_t)nloc * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemcpyAsync(d_rep, rep, sizeof(rep), cudaMemcpyHostToDevice, ctx->stream));
+        RID_CUDA(cudaMemsetAsync(d_sp0, 0, (size_t)CSB * dm->ld * sizeof(u64), ctx->stream));
+        if (nloc) {
+            cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_BUILD);
+            auto k8 = k_colsum_batch<8>;
+            auto k2 = k_colsum_batch<2>;
+            if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask, d_sp0);
+            else LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask, d_sp0);
+            rid_prof_end(ctx, pe, RID_PROF_SCAN_BUILD, (double)nloc * (double)dm->N * 4.0, (double)nloc * (double)dm->ld * 4.0);
+        }
+        RID_CUDA(cudaGetLastError());
+        RID_TRY(rid_allreduce_u64(ctx, d_sp0, (size_t)CSB * dm->ld));
+        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep, d_first);
+        RID_CUDA(cudaGetLastError());
+    }
+    return RID_OK;
+}
+
 extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const int *sample_len, int B, int *partition,
                                int *medoids, double *bootresult)
 {
@@ -2318,6 +2535,36 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     for (int i = 0; i < 4; ++i)
         if (!ctx->phase_ev[i]) RID_CUDA(cudaEventCreate(&ctx->phase_ev[i]));
     RID_CUDA(cudaEventRecord(ctx->phase_ev[0], ctx->stream)); // c1 done
+    // BUILD's first pick of every replicate, in a few batched passes over this rank's rows (see boot_first_medoids); only
+    // the enqueue-only schedule on a complete view consumes it
+    char *first_buf = nullptr;
+    size_t first_bytes = 0;
+    int2 *d_first = nullptr;
+    {
+        const bool want_first = B > 0 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") && !getenv("RID_BOOT_SYNC") &&
+                                !getenv("RID_NO_FIRST") &&
+                                (ctx->world == 1 || (dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")));
+        if (want_first) {
+            long long tot = 0;
+            for (int b = 0; b < B; ++b) tot += sample_len[b];
+            const int nloc = dm->row1 - dm->row0;
+            auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+            const size_t o_first = 0, o_off = o_first + al((size_t)B * sizeof(int2)), o_rep = o_off + al((size_t)(B + 1) * sizeof(long long)),
+                         o_sp0 = o_rep + al(CSB * sizeof(int)), o_mask = o_sp0 + al((size_t)CSB * dm->ld * sizeof(u64)),
+                         o_cat = o_mask + al((size_t)std::max(nloc, 1) * sizeof(unsigned short));
+            first_bytes = std::max<size_t>(o_cat + al((size_t)std::max<long long>(tot, 1) * sizeof(int)), (size_t)256 << 10);
+            if (rid_pool_alloc(ctx, (void **)&first_buf, first_bytes) != cudaSuccess) { cudaGetLastError(); first_buf = nullptr; }
+            int all_ok = 0;
+            RID_TRY(rid_agree_all(ctx, first_buf != nullptr, &all_ok)); // (every rank takes the same path)
+            if (!all_ok && first_buf) { rid_pool_free(ctx, first_buf, first_bytes); first_buf = nullptr; }
+            if (first_buf) {
+                d_first = (int2 *)(first_buf + o_first);
+                rc = boot_first_medoids(dm, samples, sample_len, B, d_first, (int *)(first_buf + o_cat), (long long *)(first_buf + o_off),
+                                        (u64 *)(first_buf + o_sp0), (int *)(first_buf + o_rep), (unsigned short *)(first_buf + o_mask));
+                if (rc != RID_OK) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, first_buf, first_bytes); return rc; }
+            }
+        }
+    }
     FullReplica R;
     RID_TRY(replica_begin(dm, &R));
     RID_CUDA(cudaEventRecord(ctx->phase_ev[1], ctx->stream)); // the replica (if any) has arrived
@@ -2414,7 +2661,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         PamWs *w = nullptr;
         RID_TRY(ws_get(work, k, &w));
         int n_delta = 0;
-        RID_TRY(pam_install_subset(work, w, H, slot));
+        RID_TRY(pam_install_subset(work, w, H, slot, d_first ? d_first + b : (const int2 *)nullptr));
         RID_TRY(pam_begin(work, w));
         RID_TRY(pam_build(work, w, 0, k));
         RID_TRY(pam_swap_enqueue(work, w, k, ahead, &n_delta));
@@ -2471,6 +2718,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         cudaFree(d_br);
     }
     replica_end(&R);
+    if (first_buf) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, first_buf, first_bytes); }
     if (rc != RID_OK) return rc;
     RID_CUDA(cudaEventRecord(ctx->phase_ev[2], ctx->stream));
     RID_TRY(rid_time_end(ctx));

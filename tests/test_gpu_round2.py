@@ -407,3 +407,42 @@ def test_build_lazy_equals_full_rescan(ctx, oracle, case, monkeypatch):
     lw = dm.gap_sweep(12, subset=subset)
     assert np.max(np.abs(lw - oracle.gap_sweep(Dg, 12, subset=subset))) < 1e-12
     dm.free()
+
+
+@pytest.mark.parametrize("metric", ["pearson", "euclidean"])
+def test_clusterboot_first_pick_batched_and_fused(ctx, oracle, metric, monkeypatch):
+    """rid_clusterboot takes BUILD's step-0 column sums of all replicates in batched passes over the resident matrix
+    (10 replicates per pass), so every replicate's first medoid is known before its compaction, which then accumulates
+    the second step's sums directly (no full rescan for that step).  Identical to the oracle and to the plain flow
+    (RID_NO_FIRST=1); 12 replicates = two batches; resamples large enough for the compact symmetric copy; the euclidean
+    case runs on the 31-bit grid."""
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    N, B, k = 1500, 12, 6
+    if metric == "pearson":
+        x, _ = synth_features_numpy(N, 180, k, 33)
+        x[1200] = x[3]  # duplicated cells: tied column sums
+        dm = ctx.dist_cellmajor(x, metric)
+    else:
+        rng = np.random.default_rng(4)
+        t = np.sort(rng.uniform(0, 1, N))
+        P = np.stack([t, np.sin(7 * t), np.cos(3 * t) * t]) + rng.normal(0, 0.01, (3, N))
+        dm = ctx.dist(P * 50.0, metric)
+    Dg = dm.as_matrix()
+    samples = bootstrap_samples(N, B, 17000)
+    assert min(len(s) for s in samples) ** 2 * 4 >= 1 << 20
+    ro = oracle.clusterboot(Dg, k, samples)
+    for no_first in (False, True):
+        if no_first:
+            monkeypatch.setenv("RID_NO_FIRST", "1")
+        r = dm.clusterboot(k, samples)
+        monkeypatch.delenv("RID_NO_FIRST", raising=False)
+        assert np.array_equal(r["partition"], ro["partition"]) and np.array_equal(r["id_med"], ro["id_med"])
+        assert np.array_equal(r["bootresult"], ro["bootresult"])
+    # "subset" resamples (no replacement, arbitrary order: the first pick's tie rule follows the POSITIONS)
+    sub = bootstrap_samples(N, 3, 99, samp=900)
+    r = dm.clusterboot(4, sub)
+    ro = oracle.clusterboot(Dg, 4, sub)
+    assert np.array_equal(r["partition"], ro["partition"]) and np.array_equal(r["bootresult"], ro["bootresult"])
+    dm.free()
