@@ -426,11 +426,15 @@ def main():
             barrier()
             ctx.event_record(0)
             t0 = time.perf_counter()
-            walls = []
+            walls, step_stats = [], []
             for _ in range(steps):
                 ts = time.perf_counter()
                 self.step()
                 walls.append((time.perf_counter() - ts) * 1e3)
+                st_ = ctx.stats()
+                step_stats.append([round(self.state.get("t_dist", 0.0), 1), round(self.state.get("t_sweep", 0.0), 1),
+                                   round(st_["c1_ms"], 1), round(st_["first_picks_and_replica_wait_ms"], 1),
+                                   round(st_["replicates_ms"], 1), round(st_["replicates_host_enqueue_ms"], 1)])
             ctx.event_record(1)
             barrier()
             wall = time.perf_counter() - t0
@@ -442,7 +446,8 @@ def main():
             swaps = allsum([ctx.swaps - s0])[0]
             return {"ms_per_step": ms / steps, "wall_ms_per_step": wl / steps, "launches": ctx.launches - l0,
                     "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": ctx.stats(),
-                    "step_wall_ms_rank0": walls}
+                    "step_wall_ms_rank0": walls,
+                    "step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms": step_stats}
 
     # ---- headline: resident leg, W warm-up + K timed steps ---------------------------------------------------
     W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure)
@@ -651,6 +656,7 @@ def main():
     detail["roofline_all"] = roofs
     detail["lib_stats_rank0_last_step"] = res["lib_stats_rank0_last_step"]
     detail["step_wall_ms_rank0"] = res["step_wall_ms_rank0"]
+    detail["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"] = res["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"]
     detail["ceilings_measured_here"] = {"int8_tops": i8_peak, "fp64_dmma_tflops": dmma_peak, "read_only_stream_gbs": read_peak}
     if e2e_detail:
         detail["e2e"] = e2e_detail
@@ -670,7 +676,8 @@ def main():
             out = {"workload": workload_name(a, cells, metric, sat, bootnr, structure), "value": r["ms_per_step"] / 1e3, "unit": "s",
                    "steps": steps, "warmup": warmup, "result_digest": digest_of(Wl.state), "n_swaps_per_step": r["n_swaps_per_step"],
                    "gpu_launches_per_step": r["launches"] / steps, "bootmean_min": float(np.min(Wl.state["bootmean"])),
-                   "lib_stats_rank0_last_step": r["lib_stats_rank0_last_step"],
+                   "lib_stats_rank0_last_step": r["lib_stats_rank0_last_step"], "step_wall_ms_rank0": r["step_wall_ms_rank0"],
+                   "step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms": r["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"],
                    "phase_ms_last_step": {k: Wl.state.get(k) for k in ("t_dist", "t_sweep", "t_boot") if k in Wl.state}}
             rf = rooflines(r["prof"], r["ms_per_step"] * steps, cells, world)
             out["roofline"] = rf[0] if rf else None

@@ -61,6 +61,10 @@ struct rid_ctx {
     struct ProfRec { int kind; cudaEvent_t a, b; double work; double traffic; };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
+    // finished records folded into per-kind totals (their events go back to the pool): a long timed region never has to
+    // create events on the fly
+    struct ProfAcc { long long n = 0; double ms = 0, work = 0, traffic = 0; };
+    ProfAcc prof_acc[16];
     // device-side work counters of the passes whose row count is only known on the device (never read back while a
     // clustering call is in flight): [0] rows x subset size, [1] rows x pitch of the incremental BUILD passes,
     // [2], [3] the same for the incremental SWAP passes

@@ -198,6 +198,24 @@ int rid_time_begin(rid_ctx *ctx)
     return RID_OK;
 }
 
+// every recorded bracket has completed (the stream was just synchronised): add them to the per-kind totals and recycle
+// their events
+static void prof_fold(rid_ctx *ctx)
+{
+    for (auto &r : ctx->prof) {
+        float msf = 0.f;
+        if (cudaEventElapsedTime(&msf, r.a, r.b) == cudaSuccess && r.kind >= 0 && r.kind < 16) {
+            auto &a = ctx->prof_acc[r.kind];
+            a.n += 1; a.ms += msf; a.work += r.work; a.traffic += r.traffic;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+}
+
 int rid_time_end(rid_ctx *ctx)
 {
     RID_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -205,6 +223,11 @@ int rid_time_end(rid_ctx *ctx)
     float ms = 0.f;
     RID_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+    // (only when the pool of pre-created events runs low: reading back a step's ~5 000 brackets takes a few ms of host time)
+    if (ctx->prof_on && ctx->prof_pool.size() < 12288 && ctx->prof.size() > 2048) {
+        RID_CUDA(cudaStreamSynchronize(ctx->stream));
+        prof_fold(ctx);
+    }
     return RID_OK;
 }
 
@@ -328,13 +351,14 @@ extern "C" int rid_ctx_profile(rid_ctx *ctx, int enable)
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
     ctx->prof.clear();
+    for (auto &a : ctx->prof_acc) a = rid_ctx::ProfAcc();
     if (enable && !ctx->prof_dev) RID_CUDA(cudaMalloc(&ctx->prof_dev, 4 * sizeof(u64)));
     if (ctx->prof_dev) RID_CUDA(cudaMemsetAsync(ctx->prof_dev, 0, 4 * sizeof(u64), ctx->stream));
     ctx->prof_on = enable; // bit k set = record kernels of kind k (enable = -1: every kind)
     // create the events up front: cudaEventCreate inside the timed region costs more than the kernels it brackets
     if (enable) {
         const bool many = enable != -1 && (enable & ((1 << RID_PROF_SCAN_BUILD) | (1 << RID_PROF_SCAN_DELTA)));
-        const size_t want = enable == -1 ? 40960 : (many ? 16384 : 2048);
+        const size_t want = enable == -1 ? 40960 : (many ? 24576 : 2048);
         while (ctx->prof_pool.size() < want) {
             cudaEvent_t e = nullptr;
             if (cudaEventCreateWithFlags(&e, cudaEventDefault) != cudaSuccess) break;
@@ -356,8 +380,9 @@ extern "C" int rid_ctx_profile_get(rid_ctx *ctx, int kind, long long *launches, 
     if (!ctx || kind < 0 || kind >= RID_PROF_NKINDS) return RID_ERR_ARG;
     RID_CUDA(cudaSetDevice(ctx->device));
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
-    long long n = 0;
-    double t = 0, w = 0, tr = 0;
+    prof_fold(ctx);
+    long long n = ctx->prof_acc[kind].n;
+    double t = ctx->prof_acc[kind].ms, w = ctx->prof_acc[kind].work, tr = ctx->prof_acc[kind].traffic;
     for (auto &r : ctx->prof)
         if (r.kind == kind) {
             float msf = 0.f;

@@ -119,6 +119,74 @@ k_prep(const double *__restrict__ x, int G, int N, int Gp, int metric, double *_
     if (threadIdx.x == 0) zero_var[c] = ss > 0.0 ? 0 : 1;
 }
 
+// Spearman through a sort: one CTA per cell, bitonic sort of (value, gene) in shared memory (G padded to a power of two
+// with +inf), then for every sorted position the tie group [lo, hi) by two binary searches: 2*rank = lo + hi + 1 (the
+// average of the ranks lo+1 .. hi), an exact integer like the counting kernel's 2*#less + #equal + 1 -- O(G log^2 G)
+// per cell instead of O(G^2): 100k cells x 3k genes take ~3 ms instead of ~250 ms.  G <= 16384 (196 KB of shared memory).
+#define RANK_THREADS 512
+__global__ void __launch_bounds__(RANK_THREADS)
+k_prep_rank_sort(const double *__restrict__ x, int G, int P /* power of two >= G */, int Gp, double *__restrict__ Z,
+                 unsigned char *__restrict__ zero_var)
+{
+    extern __shared__ double sh_keys[];              // [P]
+    int *sh_idx = reinterpret_cast<int *>(sh_keys + P); // [P]
+    __shared__ double sh_red[RANK_THREADS / 32];
+    const int c = blockIdx.x;
+    const double *col = x + (size_t)c * G;
+    double *zrow = Z + (size_t)c * Gp;
+    for (int i = threadIdx.x; i < P; i += RANK_THREADS) {
+        sh_keys[i] = i < G ? col[i] : __longlong_as_double(0x7ff0000000000000LL);
+        sh_idx[i] = i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += RANK_THREADS) {
+                // the t-th pair of this stage: i has bit j clear, partner i | j
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool asc = (i & k) == 0;
+                const double a = sh_keys[i], b = sh_keys[p];
+                if ((a > b) == asc && a != b) {
+                    sh_keys[i] = b; sh_keys[p] = a;
+                    const int ia = sh_idx[i];
+                    sh_idx[i] = sh_idx[p]; sh_idx[p] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < G; i += RANK_THREADS) {
+        const double v = sh_keys[i];
+        int lo = 0, hi = G; // lower_bound
+        int a = 0, b = i;   // first position with key == v lies in [0, i]
+        while (a < b) { const int mid = (a + b) >> 1; if (sh_keys[mid] < v) a = mid + 1; else b = mid; }
+        lo = a;
+        a = i + 1; b = G;   // first position with key > v lies in [i + 1, G]
+        while (a < b) { const int mid = (a + b) >> 1; if (sh_keys[mid] <= v) a = mid + 1; else b = mid; }
+        hi = a;
+        const double cv = (double)(lo + hi + 1 - (G + 1)); // 2 * (rank - mean rank), exact
+        zrow[sh_idx[i]] = cv;
+        ss += cv * cv; // exact: integers below 2^53
+    }
+    // block sum (RANK_THREADS threads)
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) sh_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        ss = threadIdx.x < RANK_THREADS / 32 ? sh_red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
+        if (threadIdx.x == 0) sh_red[0] = ss;
+    }
+    __syncthreads();
+    ss = sh_red[0];
+    const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+    __syncthreads(); // every zrow write of this CTA is done (different threads wrote them)
+    for (int k = threadIdx.x; k < G; k += RANK_THREADS) zrow[k] *= inv;
+    if (threadIdx.x == 0) zero_var[c] = ss > 0.0 ? 0 : 1;
+}
+
 __global__ void k_max_f64(const double *__restrict__ x, int n, double *out)
 {
     __shared__ double sh[256];
@@ -656,7 +724,16 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
         DCHK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
     {
         cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_PREP);
-        LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
+        if (metric == RID_SPEARMAN && G <= 16384 && !getenv("RID_RANK_COUNT")) {
+            // ranks by sorting (RID_RANK_COUNT=1 keeps the O(G^2) counting kernel, which also serves 16384 < G <= 25600)
+            int P = 2;
+            while (P < G) P <<= 1;
+            const size_t smem = (size_t)P * (sizeof(double) + sizeof(int));
+            DCHK(cudaFuncSetAttribute(k_prep_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(ctx, k_prep_rank_sort, N, RANK_THREADS, smem, xd, G, P, Gp, Z, zv);
+        } else {
+            LAUNCH(ctx, k_prep, N, PREP_THREADS, prep_smem, xd, G, N, Gp, metric, Z, zv, nrm2);
+        }
         rid_prof_end(ctx, pe, RID_PROF_PREP, (double)G * N * 16.0, (double)G * N * 32.0);
     }
     DCHK(cudaGetLastError());

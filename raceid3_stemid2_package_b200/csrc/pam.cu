@@ -17,6 +17,7 @@
 #include <limits.h>
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <future>
@@ -2674,6 +2675,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         RID_CUDA(cudaGetLastError());
         return RID_OK;
     };
+    double host_enqueue_ms = 0.0; // host time spent inside the enqueue calls (a stalled host shows up here)
     if (!mine.empty() && rc == RID_OK) launch_prep(0);
     for (size_t i0 = 0; i0 < mine.size() && rc == RID_OK; i0 += wave) {
         const size_t i1 = std::min(mine.size(), i0 + wave);
@@ -2682,8 +2684,13 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             if (i == i0 || !pipelined) rc = rid_check_abort(ctx, !R.active);
             if (rc != RID_OK) break;
             if (i + 1 < mine.size()) launch_prep(i + 1);
-            if (pipelined) rc = enqueue(mine[i], prep[i & 1], pin + (i - i0) * slot_ints, d_tabs + (i - i0) * (size_t)k * k);
-            else rc = run_sync(mine[i], &prep[i & 1]);
+            if (pipelined) {
+                struct timespec ta, tb;
+                clock_gettime(CLOCK_MONOTONIC, &ta);
+                rc = enqueue(mine[i], prep[i & 1], pin + (i - i0) * slot_ints, d_tabs + (i - i0) * (size_t)k * k);
+                clock_gettime(CLOCK_MONOTONIC, &tb);
+                host_enqueue_ms += (tb.tv_sec - ta.tv_sec) * 1e3 + (tb.tv_nsec - ta.tv_nsec) * 1e-6;
+            } else rc = run_sync(mine[i], &prep[i & 1]);
         }
         if (!pipelined || rc != RID_OK) continue;
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -2727,7 +2734,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         cudaEventElapsedTime(&a, ctx->ev0, ctx->phase_ev[0]);
         cudaEventElapsedTime(&b, ctx->phase_ev[0], ctx->phase_ev[1]);
         cudaEventElapsedTime(&c, ctx->phase_ev[1], ctx->phase_ev[2]);
-        ctx->stat[2] = a; ctx->stat[3] = b; ctx->stat[4] = c; ctx->stat[6] = (double)ahead;
+        ctx->stat[2] = a; ctx->stat[3] = b; ctx->stat[4] = c; ctx->stat[6] = (double)ahead; ctx->stat[7] = host_enqueue_ms;
     }
     return RID_OK;
 }

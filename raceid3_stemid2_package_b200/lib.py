@@ -196,7 +196,8 @@ class Context:
         return int(load().rid_ctx_swaps(self._h))
 
     def stats(self) -> dict:
-        names = ("swaps", "boot_redone", "c1_ms", "replica_wait_ms", "replicates_ms", "replica_pull_bytes", "boot_ahead")
+        names = ("swaps", "boot_redone", "c1_ms", "first_picks_and_replica_wait_ms", "replicates_ms", "replica_pull_bytes", "boot_ahead",
+                 "replicates_host_enqueue_ms")
         return {n: load().rid_ctx_stat(self._h, i) for i, n in enumerate(names)}
 
     def trim(self):

@@ -9,7 +9,19 @@
 #include "raceid_b200.h"
 using namespace Rcpp;
 
-static void rid_check(int rc) { if (rc != RID_OK) Rcpp::stop(rid_last_error()); }   // -> R condition
+// RID_ERR_INTERRUPTED: the user pressed Ctrl-C while a call was running (see rid_poll_user_interrupt): re-raise it as
+// R's own interrupt condition, like cluster::pam's R_CheckUserInterrupt does; everything else -> R error condition
+static void rid_check(int rc) {
+    if (rc == RID_ERR_INTERRUPTED) Rcpp::checkUserInterrupt();
+    if (rc != RID_OK) Rcpp::stop(rid_last_error());
+}
+
+// The library polls this between waves of GPU work, on the R main thread (the thread that made the .Call).
+// R_CheckUserInterrupt longjmps on an interrupt, which must not unwind through the library's frames, so it runs inside
+// R_ToplevelExec (FALSE = it was interrupted); the library then drains the GPU, frees its work buffers and returns
+// RID_ERR_INTERRUPTED, which rid_check turns back into the interrupt.
+static void rid_check_interrupt_fn(void*) { R_CheckUserInterrupt(); }
+static int rid_poll_user_interrupt(void*) { return R_ToplevelExec(rid_check_interrupt_fn, nullptr) == FALSE; }
 
 static void ctx_finalizer(rid_ctx* c)   { rid_ctx_destroy(c); }
 static void dmat_finalizer(rid_dmat* d) { rid_dmat_free(d); }
@@ -20,6 +32,7 @@ typedef XPtr<rid_dmat, PreserveStorage, dmat_finalizer> DmatPtr;
 SEXP rid_context(int device = 0) {
     rid_ctx* c = nullptr;
     rid_check(rid_ctx_create(device, 0, 1, nullptr, &c));
+    rid_check(rid_ctx_set_interrupt_poll(c, rid_poll_user_interrupt, nullptr));   // long calls stay interruptible
     return CtxPtr(c, true);
 }
 

@@ -446,3 +446,31 @@ def test_clusterboot_first_pick_batched_and_fused(ctx, oracle, metric, monkeypat
     ro = oracle.clusterboot(Dg, 4, sub)
     assert np.array_equal(r["partition"], ro["partition"]) and np.array_equal(r["bootresult"], ro["bootresult"])
     dm.free()
+
+
+def test_spearman_rank_by_sort_equals_counting_kernel(ctx, oracle, monkeypatch):
+    """The sort-based rank kernel (bitonic sort in shared memory + tie groups by binary search, O(G log^2 G) per cell)
+    against the O(G^2) counting kernel (RID_RANK_COUNT=1): bit-identical matrices; heavy ties (sparse counts), G not a
+    power of two, G = 2, a constant cell (zero variance -> NA)."""
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    for (N, G, seed) in ((400, 333, 1), (257, 2, 2), (300, 1025, 3), (150, 4096, 4)):
+        x, _ = synth_features_numpy(N, max(G, 8), 4, seed)
+        x = np.ascontiguousarray(x[:, :G])
+        x[5] = 0.1  # all values tied: zero variance
+        if G > 2:
+            x[7, : G // 2] = x[7, 0]  # one huge tie group
+        monkeypatch.delenv("RID_RANK_COUNT", raising=False)
+        a = ctx.dist_cellmajor(x, "spearman")
+        Da = a.as_matrix()
+        a.free()
+        monkeypatch.setenv("RID_RANK_COUNT", "1")
+        b = ctx.dist_cellmajor(x, "spearman")
+        Db = b.as_matrix()
+        b.free()
+        monkeypatch.delenv("RID_RANK_COUNT", raising=False)
+        assert np.array_equal(np.isnan(Da), np.isnan(Db)) and np.isnan(Da[5, 0]) and a.n_zero_var == b.n_zero_var == 1
+        ok = ~np.isnan(Da)
+        assert np.array_equal(Da[ok], Db[ok])
+        Do, nz = oracle.dist(np.ascontiguousarray(x.T), "spearman")
+        assert nz == 1 and np.max(np.abs(Da[ok] - Do[ok])) <= DIST_TOL
