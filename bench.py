@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--bootnr", type=int, default=50)
     ap.add_argument("--seed", type=int, default=1004)
     ap.add_argument("--structure", default="clusters", choices=["clusters", "ring"])
+    ap.add_argument("--clusters", type=int, default=0, help="true clusters / profiles of the synthetic data (0: cln)")
     ap.add_argument("--cpu-cells", type=int, default=0,
                     help="cells in the CPU sample (0: 2500 for the 1-thread leg, ~10 s; 6000 for the all-threads reference arm)")
     ap.add_argument("--cpu-bootnr", type=int, default=2)
@@ -450,7 +451,7 @@ def main():
                     "step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms": step_stats}
 
     # ---- headline: resident leg, W warm-up + K timed steps ---------------------------------------------------
-    W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure)
+    W = Workload(N, a.metric, bool(a.sat), a.bootnr, a.seed, a.structure, a.clusters or None)
     for _ in range(a.warmup):
         W.step()
     barrier()

@@ -940,12 +940,13 @@ k_wk_batch(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows, c
             for (int u = 0; u < 8; ++u) {
 #pragma unroll
                 for (int q = 0; q < WB; ++q) {
-                    const u32 eq = __vcmpeq4(clab[q], (u32)sh_lab[q][r + u] * 0x01010101u); // 0xFF per equal byte
-                    // byte c of eq spread over a word by one PRMT (selector 8|c: replicate the byte's sign bit)
-                    p32[q][0] += d[u].x & __byte_perm(eq, 0u, 0x8888u);
-                    p32[q][1] += d[u].y & __byte_perm(eq, 0u, 0x9999u);
-                    p32[q][2] += d[u].z & __byte_perm(eq, 0u, 0xAAAAu);
-                    p32[q][3] += d[u].w & __byte_perm(eq, 0u, 0xBBBBu);
+                    // one bit per equal byte; the masked add is a multiply-add by that bit: IMAD runs on the FMA pipe, so the
+                    // integer pipe (half rate, and what bounded this kernel at 2.7 TB/s) only extracts the bits
+                    const u32 b4 = __vcmpeq4(clab[q], (u32)sh_lab[q][r + u] * 0x01010101u) & 0x01010101u;
+                    p32[q][0] += d[u].x * __byte_perm(b4, 0u, 0x4440u);
+                    p32[q][1] += d[u].y * __byte_perm(b4, 0u, 0x4441u);
+                    p32[q][2] += d[u].z * __byte_perm(b4, 0u, 0x4442u);
+                    p32[q][3] += d[u].w * __byte_perm(b4, 0u, 0x4443u);
                 }
                 if ((u % FLUSH) == FLUSH - 1) {
 #pragma unroll
