@@ -439,8 +439,8 @@ __global__ void k_diff_scatter(const int *__restrict__ rows, const u32 *__restri
     }
 }
 
-template <int FLUSH, int MINB>
-__global__ void __launch_bounds__(SCAN_THREADS, MINB)
+template <int FLUSH>
+__global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_delta(const u32 *__restrict__ D, size_t ld, const int *__restrict__ d_row, const int *__restrict__ d_key,
              const u32 *__restrict__ d_po, const u32 *__restrict__ d_qo, const u32 *__restrict__ d_pn,
              const u32 *__restrict__ d_qn, const int *__restrict__ nrows_dev, int rows_per_chunk, int k,
@@ -1075,8 +1075,8 @@ k_compact(const u32 *__restrict__ D, size_t ld, const int *__restrict__ src_rows
 // CAPS: `cap` (by compact index) holds D[j][h0] for the first medoid h0 and the sums become BUILD's second-step sums
 // sum_j min(D[j][h], cap_j): the tile's column sums with the caps of its rows, the mirrored tile's with those of its columns.
 #define CS_SMEM (CS_S * CS_R * 4 + CS_S * 8 + CS_S * 4 + 2 * CS_S * 4)
-template <bool CAPS, int MINB>
-__global__ void __launch_bounds__(CS_THREADS, MINB)
+template <bool CAPS>
+__global__ void __launch_bounds__(CS_THREADS, 2)
 k_compact_sym(const u32 *__restrict__ D, size_t ld, const int *__restrict__ ccells, u32 *__restrict__ out, size_t ldc,
               int m, u64 *__restrict__ SP0, const u32 *__restrict__ cap)
 {
@@ -1657,11 +1657,10 @@ static int pam_install_subset(rid_dmat *dm, PamWs *w, HostSubset &H, int *pin = 
                 cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_COMPACT);
                 if (sym) {
                     // (per device and cheap: set on every call rather than once per process)
-                    // RID_COMPACT_OCC=3: 80 registers (some spills) and three CTAs per SM instead of two at 128 registers
-                    // (ncu: the kernel is latency-bound at 25 % warps active: long-scoreboard 8.3, barrier 2.3 per issue)
-                    static const bool occ3 = getenv("RID_COMPACT_OCC") && atoi(getenv("RID_COMPACT_OCC")) == 3;
-                    auto kc0 = occ3 ? k_compact_sym<false, 3> : k_compact_sym<false, 2>;
-                    auto kc1 = occ3 ? k_compact_sym<true, 3> : k_compact_sym<true, 2>;
+                    // (tried: __launch_bounds__(256, 3) = 80 registers with spills, three CTAs per SM instead of two: 6.70 ms
+                    // instead of 5.23 ms per launch -- the spills cost more than the extra resident warps give)
+                    auto kc0 = k_compact_sym<false>;
+                    auto kc1 = k_compact_sym<true>;
                     RID_CUDA(cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
                     RID_CUDA(cudaFuncSetAttribute(kc1, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
                     const unsigned nb = (unsigned)((m + CS_S - 1) / CS_S);
@@ -1914,11 +1913,10 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
         dim3 grid(strips, std::min(chunks, want_y * 2));
         u64 *SP2 = w->acc2 + 4, *AQ2 = SP2 + w->ld;
         cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_DELTA);
-        // MINB = 5: 96 registers (a few spilled words) and five CTAs per SM instead of four at 128 registers: the pass is
-        // latency-bound (ncu: 24 % warps active, long-scoreboard stalls), more resident warps help; RID_DELTA_OCC=4 = before
-        static const bool occ4 = getenv("RID_DELTA_OCC") && atoi(getenv("RID_DELTA_OCC")) == 4;
-        auto d8 = occ4 ? k_scan_delta<8, 4> : k_scan_delta<8, 5>;
-        auto d2 = occ4 ? k_scan_delta<2, 4> : k_scan_delta<2, 5>;
+        // (tried: __launch_bounds__(128, 5) = 96 registers, five CTAs per SM instead of four: 0.323 vs 0.322 ms per launch,
+        // no difference -- occupancy is not what holds this pass at 0.79 of the copy peak)
+        auto d8 = k_scan_delta<8>;
+        auto d2 = k_scan_delta<2>;
         if (dm->bits <= 28)
             LAUNCH(ctx, d8, grid, SCAN_THREADS, 0, w->mat, w->ld, w->d_row, w->d_key, w->d_po, w->d_qo, w->d_pn, w->d_qn,
                    w->chg_count, rpc, k, SP2, AQ2, w->state);

@@ -10,7 +10,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,mode", [(2, "replica"), (2, "cooperative"), (2, "replica_upper"), (2, "sweep_replica")])
+@pytest.mark.parametrize("world,mode", [(2, "replica"), (2, "cooperative"), (2, "replica_upper"), (2, "sweep_replica"),
+                                        (8, "replica_upper"), (8, "cooperative")])
 def test_row_sharded_results_identical_to_single_gpu(world, mode):
     """cooperative: RID_NO_REPLICA=1, every rank scans its row shard of every PAM problem, one all-reduce per step.
     replica (default): the copy engines pull the peers' row blocks into a full copy per rank and the bootstrap
@@ -26,6 +27,8 @@ def test_row_sharded_results_identical_to_single_gpu(world, mode):
         env["RID_NO_REPLICA"] = "1"
     if mode == "replica_upper":
         env["RID_REPLICA_MARGIN"] = "64"
+    if world > 2:
+        env["MGPU_CELLS"] = "6000"
     if mode == "sweep_replica":
         env["RID_SWEEP_REPLICA"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
