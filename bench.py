@@ -510,7 +510,8 @@ def main():
         torch.cuda.synchronize()
         counts_csc = csc_matrix((data, indices, indptr), shape=(G, N), copy=False)
         sc = rid.SCseq.from_filtered_counts(counts_csc)
-        h2d = int(data.nbytes + indices.nbytes + indptr.nbytes + N * 8 + G * 4)
+        # (several ranks: each uploads the non-zeros of its own slice of the cells; the small tables go up on every rank)
+        h2d = int(data.nbytes + indices.nbytes + world * (indptr.nbytes + N * 8 + G * 4))
 
         def api_step():
             rid.compdist(sc, metric=a.metric)

@@ -111,6 +111,7 @@ int rid_replica_complete(rid_dmat *dm);
 int rid_check_abort(rid_ctx *ctx, bool collective);
 int rid_barrier(rid_ctx *ctx);
 int rid_allgather(rid_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int rid_bcast_ranges(rid_ctx *ctx, void *buf, const size_t *off /* [world + 1] byte offsets */);
 
 // cudaMalloc/cudaFree through the context's reuse pool (exact-size match)
 cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes);

@@ -29,6 +29,9 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -48,6 +51,9 @@ static NcclApi *nccl_api()
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
             api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
         }
     }
@@ -456,6 +462,23 @@ int rid_allgather(rid_ctx *ctx, const void *send, void *recv, size_t bytes_per_r
     }
     if (!ctx->nccl->AllGather) { rid_set_error("ncclAllGather is not available"); return RID_ERR_CUDA; }
     RID_NCCL(ctx->nccl, ctx->nccl->AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->comm, ctx->stream));
+    return RID_OK;
+}
+
+// Every rank holds the byte range [off[r], off[r+1]) of `buf` that rank r produced (uploaded); afterwards every rank holds
+// all of them: one in-place broadcast per rank, grouped.  Returns RID_ERR_UNSUPPORTED if the NCCL entry points are missing.
+int rid_bcast_ranges(rid_ctx *ctx, void *buf, const size_t *off)
+{
+    if (ctx->world == 1) return RID_OK;
+    if (!ctx->nccl->Broadcast || !ctx->nccl->GroupStart || !ctx->nccl->GroupEnd) return RID_ERR_UNSUPPORTED;
+    RID_NCCL(ctx->nccl, ctx->nccl->GroupStart());
+    for (int r = 0; r < ctx->world; ++r) {
+        const size_t n = off[r + 1] - off[r];
+        if (!n) continue;
+        char *p = (char *)buf + off[r];
+        RID_NCCL(ctx->nccl, ctx->nccl->Broadcast(p, p, n, ncclUint8, r, (ncclComm_t)ctx->comm, ctx->stream));
+    }
+    RID_NCCL(ctx->nccl, ctx->nccl->GroupEnd());
     return RID_OK;
 }
 

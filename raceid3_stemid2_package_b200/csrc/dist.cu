@@ -821,7 +821,10 @@ extern "C" int rid_dist(rid_ctx *ctx, const double *x, int G, int N, int metric,
     }
     // every shard is complete on every rank (both tensor paths end with a barrier): the copy engines start pulling the
     // other ranks' row blocks into the replica while the first clustering phase runs on the shard
-    if (ctx->world > 1 && dm->full) {
+    // When to start: measured at 8 GPUs, the 19 GB per rank of pulls and the latency-bound cooperative phases slow each
+    // other down (k sweep 56 ms alone, 91 ms next to the pulls; c1 7.9 vs 15.6 ms), so the pulls start as late as they
+    // can still hide: at the end of the sweep / the beginning of clusterboot (pam.cu).  RID_REPLICA_EAGER=1: right here.
+    if (ctx->world > 1 && dm->full && getenv("RID_REPLICA_EAGER")) {
         // (the pulls need the peers' pointers, and with those both paths have just passed their closing barrier)
         if ((rc = rid_replica_start(dm)) != RID_OK) return fail(rc);
     }
@@ -906,7 +909,8 @@ extern "C" int rid_dmat_from_host(rid_ctx *ctx, const double *D, int N, rid_dmat
     dm->has_na = h;
     if (ctx->world > 1 && dm->full && dm->peers_ok) {
         // every rank has imported its own rows: let the copy engines fetch the others
-        if ((rc = rid_barrier(ctx)) != RID_OK || (rc = rid_replica_start(dm)) != RID_OK) { rid_dmat_free(dm); return rc; }
+        if ((rc = rid_barrier(ctx)) != RID_OK) { rid_dmat_free(dm); return rc; }
+        if (getenv("RID_REPLICA_EAGER") && (rc = rid_replica_start(dm)) != RID_OK) { rid_dmat_free(dm); return rc; }
     }
     *out = dm;
     return RID_OK;
@@ -1096,10 +1100,34 @@ extern "C" int rid_dist_csc(rid_ctx *ctx, const int *row_idx, const int *col_ptr
     }
     d_v = (double *)(stage + o_v); d_c = (double *)(stage + o_c); d_i = (int *)(stage + o_i); d_p = (int *)(stage + o_p);
     d_f = (int *)(stage + o_f);
-    cudaMemcpyAsync(d_i, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    // Several ranks: every rank uploads only the non-zeros of its 1/world slice of the cells over PCIe and the slices
+    // are exchanged over NVLink (one in-place broadcast per rank) -- eight full 2 GB uploads through one host's memory
+    // were a third of the 8-GPU end-to-end step.  RID_FULL_UPLOAD=1: every rank uploads everything.
+    bool sliced = ctx->world > 1 && !getenv("RID_FULL_UPLOAD");
+    if (sliced) {
+        const size_t cells_per = ((size_t)N + ctx->world - 1) / ctx->world;
+        std::vector<size_t> off_i(ctx->world + 1), off_v(ctx->world + 1);
+        for (int r = 0; r <= ctx->world; ++r) {
+            const size_t c = std::min(cells_per * (size_t)r, (size_t)N);
+            off_i[r] = (size_t)col_ptr[c] * sizeof(int);
+            off_v[r] = (size_t)col_ptr[c] * sizeof(double);
+        }
+        const size_t lo = off_i[ctx->rank] / sizeof(int), hi = off_i[ctx->rank + 1] / sizeof(int);
+        if (hi > lo) {
+            cudaMemcpyAsync(d_i + lo, row_idx + lo, (hi - lo) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(d_v + lo, val + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        }
+        rc = rid_bcast_ranges(ctx, d_i, off_i.data());
+        if (rc == RID_OK) rc = rid_bcast_ranges(ctx, d_v, off_v.data());
+        if (rc == RID_ERR_UNSUPPORTED) { sliced = false; rc = RID_OK; } // (the same answer on every rank: one library)
+        else if (rc != RID_OK) return done(rc);
+    }
+    if (!sliced) {
+        cudaMemcpyAsync(d_i, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_v, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
     cudaMemcpyAsync(d_p, col_ptr, ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_f, feat.data(), (size_t)n_rows_all * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_v, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_c, counts, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     LAUNCH(ctx, k_csc_to_features, N, 256, 0, d_i, d_p, d_v, d_f, G, d_c, mincount, d_x);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {

@@ -2456,6 +2456,8 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
                           R.active ? R.saved_rank : 0);
     replica_local(&R, false);
     if (R.active) rc = agree_interrupt(ctx, rc);
+    // the sweep is usually followed by clusterboot: its replica starts to fill now, behind the host work in between
+    if (rc == RID_OK && ctx->world > 1 && dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")) rc = rid_replica_start(dm);
     if (R.active && rc == RID_OK) {
         double *d_lw = nullptr;
         if (cudaMalloc(&d_lw, (size_t)Kmax * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
@@ -2534,6 +2536,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     int N = dm->N;
     RID_TRY(rid_time_begin(ctx));
     // c1 = PAM on all cells: every rank scans its own row shard (1/world of the bytes), before any replica exists
+    // the copy engines start (or go on) pulling the peers' row blocks while c1 and the first picks run on the shard
+    if (ctx->world > 1 && dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")) RID_TRY(rid_replica_start(dm));
     std::vector<int> med_pos(k);
     int c1_swaps = 0;
     int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);

@@ -31,9 +31,20 @@ def main():
     # part of the peers' blocks a replica pulls first (the library then has to fetch the rest)
     sparse_samples = rid.bootstrap_samples(n_cells, 2, 17000, samp=max(600, n_cells // 12))
     sub = np.arange(n_cells - 1, -1, -2).astype(np.int32)
+    # the sparse route (rid_dist_csc): every rank uploads the non-zeros of its slice of the cells, slices go round over NVLink
+    from scipy.sparse import csr_matrix
+    from raceid3_stemid2_package_b200.synth import synth_counts_numpy
+    cnt, _ = synth_counts_numpy(n_cells, 300, 6, 11)
+    csr = csr_matrix(cnt)  # CSR of cells x genes == CSC of genes x cells
+    tot = cnt.sum(axis=1)
 
     def run(c):
         out = {}
+        dmc = c.dist_csc(csr.indices, csr.indptr, csr.data, 300, np.arange(300, dtype=np.int32), tot, "pearson")
+        out["csc_blk"] = dmc.sub(rows=np.array([0, 7, n_cells // 2 + 1, n_cells - 1], dtype=np.int32))
+        r = dmc.pam(3)
+        out["csc_pam3"] = (r["id_med"], r["clustering"])
+        dmc.free()
         for metric in ("pearson", "euclidean"):
             dm = c.dist_cellmajor(x, metric)
             r0, r1 = dm.row0, dm.row1
