@@ -445,8 +445,14 @@ def main():
                 ctx.profile(False)
             ms, wl = allmax([dev_ms, wall * 1e3])
             swaps = allsum([ctx.swaps - s0])[0]
+            st_last = ctx.stats()
+            mx = allmax([st_last["c1_ms"], st_last["first_picks_and_replica_wait_ms"], st_last["replicates_ms"], st_last["replica_pull_ms"]])
+            mn = allmax([-st_last["replicates_ms"], -st_last["replica_pull_ms"]])
+            stats_ranks = {"max_c1_ms": mx[0], "max_first_picks_and_replica_wait_ms": mx[1], "max_replicates_ms": mx[2],
+                           "max_replica_pull_ms": mx[3], "min_replicates_ms": -mn[0], "min_replica_pull_ms": -mn[1]}
             return {"ms_per_step": ms / steps, "wall_ms_per_step": wl / steps, "launches": ctx.launches - l0,
-                    "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": ctx.stats(),
+                    "n_swaps_per_step": swaps / steps, "prof": prof, "lib_stats_rank0_last_step": st_last,
+                    "lib_stats_over_ranks_last_step": stats_ranks,
                     "step_wall_ms_rank0": walls,
                     "step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms": step_stats}
 
@@ -657,6 +663,7 @@ def main():
     detail["bootmean_min"] = float(np.min(state["bootmean"]))
     detail["roofline_all"] = roofs
     detail["lib_stats_rank0_last_step"] = res["lib_stats_rank0_last_step"]
+    detail["lib_stats_over_ranks_last_step"] = res["lib_stats_over_ranks_last_step"]
     detail["step_wall_ms_rank0"] = res["step_wall_ms_rank0"]
     detail["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"] = res["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"]
     detail["ceilings_measured_here"] = {"int8_tops": i8_peak, "fp64_dmma_tflops": dmma_peak, "read_only_stream_gbs": read_peak}
@@ -679,6 +686,7 @@ def main():
                    "steps": steps, "warmup": warmup, "result_digest": digest_of(Wl.state), "n_swaps_per_step": r["n_swaps_per_step"],
                    "gpu_launches_per_step": r["launches"] / steps, "bootmean_min": float(np.min(Wl.state["bootmean"])),
                    "lib_stats_rank0_last_step": r["lib_stats_rank0_last_step"], "step_wall_ms_rank0": r["step_wall_ms_rank0"],
+                   "lib_stats_over_ranks_last_step": r["lib_stats_over_ranks_last_step"],
                    "step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms": r["step_phases_rank0_dist_sweep_c1_first_replicates_hostenqueue_ms"],
                    "phase_ms_last_step": {k: Wl.state.get(k) for k in ("t_dist", "t_sweep", "t_boot") if k in Wl.state}}
             rf = rooflines(r["prof"], r["ms_per_step"] * steps, cells, world)

@@ -70,7 +70,8 @@ long long rid_ctx_swaps(const rid_ctx *ctx);
 /* Diagnostics (bench.py): 0 swaps, 1 bootstrap replicates redone (more SWAP iterations needed than were enqueued ahead),
  * 2-4 milliseconds of the last rid_clusterboot spent in c1 / in the batched first picks + waiting for the replica
  * pulls / in the replicates, 5 bytes the last replica pull moved over NVLink, 6 look-ahead iterations enqueued per
- * replicate, 7 host milliseconds spent inside the enqueue calls of the replicates. */
+ * replicate, 7 host milliseconds spent inside the enqueue calls of the replicates, 8 milliseconds the last replica pull
+ * took on the copy stream. */
 double rid_ctx_stat(const rid_ctx *ctx, int which);
 /* Give the cached device buffers back to the driver (collective when world > 1: call it on every rank). */
 int rid_ctx_trim(rid_ctx *ctx);

@@ -52,7 +52,7 @@ struct rid_ctx {
     // rid_ctx_stat: [0] swaps (mirror), [1] bootstrap replicates redone because they needed more SWAP iterations than were
     // enqueued ahead, [2..4] ms of the last rid_clusterboot: c1 / wait for the replica pulls / replicates,
     // [5] bytes the last replica pull moved over NVLink, [6] look-ahead iterations the last rid_clusterboot enqueued
-    double stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // [8] ms the last replica pull took on the copy stream
     cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void *comm = nullptr; // ncclComm_t
     NcclApi *nccl = nullptr;
@@ -160,6 +160,7 @@ struct rid_dmat {
     int replica_state = 0;
     int replica_lo[16] = {0};
     cudaEvent_t replica_ev = nullptr;
+    cudaEvent_t pull_t0 = nullptr, pull_t1 = nullptr; // timing of the first pull (diagnostics)
     rid_dmat *replica_view = nullptr; // the "one GPU owns every row" view of `full` the bootstrap PAM runs use
     // euclidean only: the raw feature matrix (N x Gx doubles, one row per cell) kept so that exported distances are
     // recomputed in FP64 difference form when the fixed-point step alone would exceed the 1e-6 budget

@@ -182,7 +182,7 @@ extern "C" long long rid_ctx_launches(const rid_ctx *ctx) { return ctx ? ctx->la
 extern "C" long long rid_ctx_swaps(const rid_ctx *ctx) { return ctx ? ctx->swaps : 0; }
 extern "C" double rid_ctx_stat(const rid_ctx *ctx, int which)
 {
-    if (!ctx || which < 0 || which >= 8) return 0.0;
+    if (!ctx || which < 0 || which >= 12) return 0.0;
     return which == 0 ? (double)ctx->swaps : ctx->stat[which];
 }
 

@@ -575,6 +575,8 @@ int rid_replica_start(rid_dmat *dm)
     if (!dm->replica_ev) RID_CUDA(cudaEventCreateWithFlags(&dm->replica_ev, cudaEventDisableTiming));
     RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->stream));
     RID_CUDA(cudaStreamWaitEvent(ctx->copy_stream, dm->replica_ev, 0));
+    if (!dm->pull_t0) { RID_CUDA(cudaEventCreate(&dm->pull_t0)); RID_CUDA(cudaEventCreate(&dm->pull_t1)); }
+    RID_CUDA(cudaEventRecord(dm->pull_t0, ctx->copy_stream));
     const bool whole = getenv("RID_REPLICA_FULL") != nullptr;
     double pulled = 0.0;
     const int margin = getenv("RID_REPLICA_MARGIN") ? std::max(0, atoi(getenv("RID_REPLICA_MARGIN"))) : RID_REPLICA_MARGIN;
@@ -594,6 +596,7 @@ int rid_replica_start(rid_dmat *dm)
     }
     ctx->stat[5] = pulled;
     dm->replica_lo[dm->rank] = 0;
+    RID_CUDA(cudaEventRecord(dm->pull_t1, ctx->copy_stream));
     RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->copy_stream));
     dm->replica_state = all_whole ? 2 : 1;
     return RID_OK;
@@ -636,6 +639,7 @@ extern "C" int rid_dmat_free(rid_dmat *dm)
     }
     rid_pam_ws_free(dm->ws, ctx);
     if (dm->replica_ev) cudaEventDestroy(dm->replica_ev);
+    if (dm->pull_t0) { cudaEventDestroy(dm->pull_t0); cudaEventDestroy(dm->pull_t1); }
     if (dm->xraw) rid_pool_free(ctx, dm->xraw, dm->xraw_bytes);
     if (dm->full) rid_pool_free(ctx, dm->full, dm->full_bytes);
     else rid_pool_free(ctx, dm->D, dm->alloc_rows * dm->ld * sizeof(u32));

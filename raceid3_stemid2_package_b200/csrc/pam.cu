@@ -2475,51 +2475,71 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
 // BUILD's first pick of every bootstrap replicate, before any replicate starts: the step-0 column sums of CSB replicates
 // per pass over this rank's rows (k_colsum_batch), summed over the ranks, then the arg min per replicate
 // (k_first_medoid).  Runs on the sharded matrix with the real world size (before any switch to a replica).
+// The row masks of all batches are built on a helper thread while c1 runs (boot_first_masks): with several ranks a pass
+// takes about a millisecond, and building a batch's mask between the passes left the GPU waiting for the host.
+struct FirstMasks {
+    int err = 0;
+    char msg[96] = {0};
+    int nbatch = 0;
+    std::vector<unsigned short> mask; // [nbatch][nloc]
+    std::vector<int> rep;             // [nbatch][CSB] replicate of every slot (padding repeats the batch's last one)
+    std::vector<long long> off;       // [B + 1]
+};
+static void boot_first_masks(FirstMasks *M, int N, int row0, int row1, const int *samples, const int *sample_len, int B)
+{
+    const int nloc = row1 - row0;
+    M->nbatch = (B + CSB - 1) / CSB;
+    M->off.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) M->off[b + 1] = M->off[b] + sample_len[b];
+    M->mask.assign((size_t)M->nbatch * std::max(nloc, 1), 0);
+    M->rep.assign((size_t)M->nbatch * CSB, 0);
+    for (int t = 0; t < M->nbatch; ++t) {
+        const int b0 = t * CSB, nb = std::min(CSB, B - b0);
+        unsigned short *hm = M->mask.data() + (size_t)t * std::max(nloc, 1);
+        for (int r = 0; r < CSB; ++r) M->rep[(size_t)t * CSB + r] = b0 + std::min(r, nb - 1);
+        for (int r = 0; r < nb; ++r) {
+            const int *sp = samples + M->off[b0 + r];
+            const int len = sample_len[b0 + r];
+            for (int p = 0; p < len; ++p) {
+                const int h = sp[p];
+                if (h < 0 || h >= N) { M->err = RID_ERR_ARG; snprintf(M->msg, sizeof(M->msg), "bootstrap sample index %d out of range", h); return; }
+                if (h >= row0 && h < row1) hm[h - row0] |= (unsigned short)(1u << r);
+            }
+        }
+    }
+}
+
 // d_first[b] = (cell, position) for every replicate b; d_cat / d_off are the samples on the device.
-static int boot_first_medoids(rid_dmat *dm, const int *samples, const int *sample_len, int B, int2 *d_first, int *d_cat,
-                              long long *d_off, u64 *d_sp0 /* [CSB][ld] */, int *d_rep /* [CSB] */,
-                              unsigned short *d_mask /* [nloc] */)
+static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samples, int B, int2 *d_first, int *d_cat,
+                              long long *d_off, u64 *d_sp0 /* [CSB][ld] */, int *d_rep /* [nbatch][CSB] */,
+                              unsigned short *d_mask /* [nbatch][nloc] */)
 {
     rid_ctx *ctx = dm->ctx;
     const int nloc = dm->row1 - dm->row0;
-    std::vector<long long> off(B + 1, 0);
-    for (int b = 0; b < B; ++b) off[b + 1] = off[b] + sample_len[b];
-    RID_CUDA(cudaMemcpyAsync(d_cat, samples, (size_t)off[B] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    RID_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<unsigned short> hm((size_t)std::max(nloc, 1));
+    if (M.err) { rid_set_error("%s", M.msg); return M.err; }
+    // (pageable sources: staged by the time the calls return)
+    RID_CUDA(cudaMemcpyAsync(d_cat, samples, (size_t)M.off[B] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(d_off, M.off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(d_rep, M.rep.data(), M.rep.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (nloc) RID_CUDA(cudaMemcpyAsync(d_mask, M.mask.data(), (size_t)M.nbatch * nloc * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
     int strips = (int)((dm->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
     int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
     int rpc = std::min(std::max((((nloc + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
     dim3 grid(strips, std::max(1, std::min((nloc + rpc - 1) / rpc, want_y * 2)));
-    for (int b0 = 0; b0 < B; b0 += CSB) {
-        const int nb = std::min(CSB, B - b0);
-        std::fill(hm.begin(), hm.end(), (unsigned short)0);
-        int rep[CSB];
-        for (int r = 0; r < CSB; ++r) rep[r] = b0 + std::min(r, nb - 1);
-        for (int r = 0; r < nb; ++r) {
-            const int *sp = samples + off[b0 + r];
-            const int len = sample_len[b0 + r];
-            for (int p = 0; p < len; ++p) {
-                const int h = sp[p];
-                if (h < 0 || h >= dm->N) { rid_set_error("bootstrap sample index %d out of range", h); return RID_ERR_ARG; }
-                if (h >= dm->row0 && h < dm->row1) hm[h - dm->row0] |= (unsigned short)(1u << r);
-            }
-        }
-        // (pageable sources: staged by the time the calls return, so hm / rep may be rewritten for the next batch)
-        if (nloc) RID_CUDA(cudaMemcpyAsync(d_mask, hm.data(), (size_t)nloc * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
-        RID_CUDA(cudaMemcpyAsync(d_rep, rep, sizeof(rep), cudaMemcpyHostToDevice, ctx->stream));
+    for (int t = 0; t < M.nbatch; ++t) {
+        const int nb = std::min(CSB, B - t * CSB);
         RID_CUDA(cudaMemsetAsync(d_sp0, 0, (size_t)CSB * dm->ld * sizeof(u64), ctx->stream));
         if (nloc) {
             cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_BUILD);
             auto k8 = k_colsum_batch<8>;
             auto k2 = k_colsum_batch<2>;
-            if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask, d_sp0);
-            else LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask, d_sp0);
+            if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
+            else LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
             rid_prof_end(ctx, pe, RID_PROF_SCAN_BUILD, (double)nloc * (double)dm->N * 4.0, (double)nloc * (double)dm->ld * 4.0);
         }
         RID_CUDA(cudaGetLastError());
         RID_TRY(rid_allreduce_u64(ctx, d_sp0, (size_t)CSB * dm->ld));
-        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep, d_first);
+        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep + (size_t)t * CSB, d_first);
         RID_CUDA(cudaGetLastError());
     }
     return RID_OK;
@@ -2538,41 +2558,44 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     // c1 = PAM on all cells: every rank scans its own row shard (1/world of the bytes), before any replica exists
     // the copy engines start (or go on) pulling the peers' row blocks while c1 and the first picks run on the shard
     if (ctx->world > 1 && dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")) RID_TRY(rid_replica_start(dm));
+    // BUILD's first pick of every replicate comes from a few batched passes over this rank's rows (boot_first_medoids);
+    // only the enqueue-only schedule on a complete view consumes it.  The row masks are built while c1 runs.
+    const bool want_first = B > 0 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") && !getenv("RID_BOOT_SYNC") &&
+                            !getenv("RID_NO_FIRST") &&
+                            (ctx->world == 1 || (dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")));
+    FirstMasks fmasks;
+    std::future<void> fmask_fut;
+    if (want_first)
+        fmask_fut = std::async(std::launch::async, boot_first_masks, &fmasks, N, dm->row0, dm->row1, samples, sample_len, B);
     std::vector<int> med_pos(k);
     int c1_swaps = 0;
     int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
+    if (fmask_fut.valid()) fmask_fut.wait();
     if (rc != RID_OK) return rc;
     for (int i = 0; i < 4; ++i)
         if (!ctx->phase_ev[i]) RID_CUDA(cudaEventCreate(&ctx->phase_ev[i]));
     RID_CUDA(cudaEventRecord(ctx->phase_ev[0], ctx->stream)); // c1 done
-    // BUILD's first pick of every replicate, in a few batched passes over this rank's rows (see boot_first_medoids); only
-    // the enqueue-only schedule on a complete view consumes it
     char *first_buf = nullptr;
     size_t first_bytes = 0;
     int2 *d_first = nullptr;
-    {
-        const bool want_first = B > 0 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") && !getenv("RID_BOOT_SYNC") &&
-                                !getenv("RID_NO_FIRST") &&
-                                (ctx->world == 1 || (dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")));
-        if (want_first) {
-            long long tot = 0;
-            for (int b = 0; b < B; ++b) tot += sample_len[b];
-            const int nloc = dm->row1 - dm->row0;
-            auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-            const size_t o_first = 0, o_off = o_first + al((size_t)B * sizeof(int2)), o_rep = o_off + al((size_t)(B + 1) * sizeof(long long)),
-                         o_sp0 = o_rep + al(CSB * sizeof(int)), o_mask = o_sp0 + al((size_t)CSB * dm->ld * sizeof(u64)),
-                         o_cat = o_mask + al((size_t)std::max(nloc, 1) * sizeof(unsigned short));
-            first_bytes = std::max<size_t>(o_cat + al((size_t)std::max<long long>(tot, 1) * sizeof(int)), (size_t)256 << 10);
-            if (rid_pool_alloc(ctx, (void **)&first_buf, first_bytes) != cudaSuccess) { cudaGetLastError(); first_buf = nullptr; }
-            int all_ok = 0;
-            RID_TRY(rid_agree_all(ctx, first_buf != nullptr, &all_ok)); // (every rank takes the same path)
-            if (!all_ok && first_buf) { rid_pool_free(ctx, first_buf, first_bytes); first_buf = nullptr; }
-            if (first_buf) {
-                d_first = (int2 *)(first_buf + o_first);
-                rc = boot_first_medoids(dm, samples, sample_len, B, d_first, (int *)(first_buf + o_cat), (long long *)(first_buf + o_off),
-                                        (u64 *)(first_buf + o_sp0), (int *)(first_buf + o_rep), (unsigned short *)(first_buf + o_mask));
-                if (rc != RID_OK) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, first_buf, first_bytes); return rc; }
-            }
+    if (want_first) {
+        const int nloc = dm->row1 - dm->row0;
+        const long long tot = fmasks.off.empty() ? 0 : fmasks.off[B];
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t o_first = 0, o_off = o_first + al((size_t)B * sizeof(int2)), o_rep = o_off + al((size_t)(B + 1) * sizeof(long long)),
+                     o_sp0 = o_rep + al((size_t)std::max(fmasks.nbatch, 1) * CSB * sizeof(int)),
+                     o_mask = o_sp0 + al((size_t)CSB * dm->ld * sizeof(u64)),
+                     o_cat = o_mask + al((size_t)std::max(fmasks.nbatch, 1) * std::max(nloc, 1) * sizeof(unsigned short));
+        first_bytes = std::max<size_t>(o_cat + al((size_t)std::max<long long>(tot, 1) * sizeof(int)), (size_t)256 << 10);
+        if (rid_pool_alloc(ctx, (void **)&first_buf, first_bytes) != cudaSuccess) { cudaGetLastError(); first_buf = nullptr; }
+        int all_ok = 0;
+        RID_TRY(rid_agree_all(ctx, first_buf != nullptr, &all_ok)); // (every rank takes the same path)
+        if (!all_ok && first_buf) { rid_pool_free(ctx, first_buf, first_bytes); first_buf = nullptr; }
+        if (first_buf) {
+            d_first = (int2 *)(first_buf + o_first);
+            rc = boot_first_medoids(dm, fmasks, samples, B, d_first, (int *)(first_buf + o_cat), (long long *)(first_buf + o_off),
+                                    (u64 *)(first_buf + o_sp0), (int *)(first_buf + o_rep), (unsigned short *)(first_buf + o_mask));
+            if (rc != RID_OK) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, first_buf, first_bytes); return rc; }
         }
     }
     FullReplica R;
@@ -2744,6 +2767,11 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         cudaEventElapsedTime(&b, ctx->phase_ev[0], ctx->phase_ev[1]);
         cudaEventElapsedTime(&c, ctx->phase_ev[1], ctx->phase_ev[2]);
         ctx->stat[2] = a; ctx->stat[3] = b; ctx->stat[4] = c; ctx->stat[6] = (double)ahead; ctx->stat[7] = host_enqueue_ms;
+        if (dm->pull_t0 && cudaEventQuery(dm->pull_t1) == cudaSuccess) {
+            float pm = 0.f;
+            if (cudaEventElapsedTime(&pm, dm->pull_t0, dm->pull_t1) == cudaSuccess) ctx->stat[8] = pm;
+        }
+        cudaGetLastError();
     }
     return RID_OK;
 }
