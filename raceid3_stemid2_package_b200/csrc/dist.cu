@@ -563,11 +563,36 @@ static int dmat_alloc(rid_ctx *ctx, int N, rid_dmat **out)
     return RID_OK;
 }
 
-// Pull the other ranks' row blocks into dm->full with the copy engines.  Call after the barrier that ends the distance
-// kernels (every shard complete everywhere).  Only columns >= replica_lo[s] of block s are fetched at first: the
-// symmetric compaction of a bootstrap replicate reads nothing else (plus a margin for its diagonal super-tiles);
-// rid_replica_complete fetches the rest on demand.  One-sided: no rank waits for another here.
+// Fill dm->full with what the bootstrap replicates read of the other ranks' row blocks.  Call after the barrier that
+// ends the distance kernels (every shard complete everywhere).  One-sided: no rank waits for another here.
+//
+// The symmetric compaction of a replicate reads, of row block s, only the columns >= (first row of s) - margin (upper
+// triangle plus a margin for its diagonal super-tiles); rid_replica_complete fetches the rest on demand.  Fetching that
+// upper part of every block from its owner would make rank 0 send seven times its whole block and rank W-1 almost
+// nothing (measured at 8 GPUs: 27 ms of pulls on rank 0, 68 ms on the slowest rank, and the early ranks' replicates
+// slowed down by the peers still reading their memory).  D is symmetric, so block (s, t), s < t, also exists transposed
+// as block (t, s) in the shard of t's owner: each off-diagonal block is fetched from whichever of its two holders keeps
+// the senders balanced (the same circulant rule for every reader) -- as it is, by the copy engines
+// (cudaMemcpy2DAsync from the owner of s), or transposed on the way by a small kernel that reads the peer's rows over
+// NVLink (k_pull_transpose from the owner of t).  Blocks (s, me) are transposes of this rank's own rows: no NVLink.
 #define RID_REPLICA_MARGIN 4096
+__global__ void __launch_bounds__(256)
+k_pull_transpose(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t ld, int nr /* rows of src = columns of dst */,
+                 int nc /* columns of src = rows of dst */)
+{
+    __shared__ u32 tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = by + j, c = bx + threadIdx.x;
+        tile[j][threadIdx.x] = (r < nr && c < nc) ? src[(size_t)r * ld + c] : 0u;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = bx + j, c = by + threadIdx.x; // dst row = src column, dst column = src row
+        if (r < nc && c < nr) dst[(size_t)r * ld + c] = tile[threadIdx.x][j];
+    }
+}
+
 int rid_replica_start(rid_dmat *dm)
 {
     rid_ctx *ctx = dm->ctx;
@@ -578,24 +603,61 @@ int rid_replica_start(rid_dmat *dm)
     if (!dm->pull_t0) { RID_CUDA(cudaEventCreate(&dm->pull_t0)); RID_CUDA(cudaEventCreate(&dm->pull_t1)); }
     RID_CUDA(cudaEventRecord(dm->pull_t0, ctx->copy_stream));
     const bool whole = getenv("RID_REPLICA_FULL") != nullptr;
+    const bool direct_only = whole || getenv("RID_REPLICA_DIRECT") != nullptr; // every block from the owner of its rows
     double pulled = 0.0;
     const int margin = getenv("RID_REPLICA_MARGIN") ? std::max(0, atoi(getenv("RID_REPLICA_MARGIN"))) : RID_REPLICA_MARGIN;
+    const int W = dm->world, me = dm->rank;
+    const size_t per = dm->alloc_rows, pitch = dm->ld * sizeof(u32);
+    // block (s, t), s < t: from the owner of s as it is (true) or from the owner of t, transposed (false)
+    auto fwd = [&](int s, int t) {
+        if (direct_only) return true;
+        if (t == me) return false; // a transpose of this rank's own rows
+        const int d = t - s;
+        return 2 * d < W || (2 * d == W && (((s + t) & 1) == 0));
+    };
+    auto copy_cols = [&](int s, size_t c0, size_t c1, int rows) -> int { // columns [c0, c1) of row block s from its owner
+        if (c1 <= c0 || rows <= 0) return RID_OK;
+        const size_t off = (size_t)s * per * dm->ld + c0;
+        RID_CUDA(cudaMemcpy2DAsync(dm->full + off, pitch, dm->peer_full[s] + off, pitch, (c1 - c0) * sizeof(u32), (size_t)rows,
+                                   cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        pulled += (double)(c1 - c0) * sizeof(u32) * (double)rows;
+        return RID_OK;
+    };
     bool all_whole = true;
-    for (int i = 1; i < dm->world; ++i) {
-        const int s = (dm->rank + i) % dm->world; // staggered: in round i every source serves one destination
+    for (int i = 1; i < W; ++i) {
+        const int s = (me + i) % W; // staggered: in round i every source serves one destination
         int r0, r1;
-        shard_rows(dm->N, s, dm->world, &r0, &r1);
+        shard_rows(dm->N, s, W, &r0, &r1);
         if (r1 <= r0) continue;
-        size_t lo = whole ? 0 : (size_t)std::max(0, r0 - margin) & ~(size_t)31;
+        const size_t lo = whole ? 0 : (size_t)std::max(0, r0 - margin) & ~(size_t)31;
         dm->replica_lo[s] = (int)lo;
         if (lo) all_whole = false;
-        const size_t off = (size_t)s * dm->alloc_rows * dm->ld + lo;
-        RID_CUDA(cudaMemcpy2DAsync(dm->full + off, dm->ld * sizeof(u32), dm->peer_full[s] + off, dm->ld * sizeof(u32),
-                                   (dm->ld - lo) * sizeof(u32), (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, ctx->copy_stream));
-        pulled += (double)(dm->ld - lo) * sizeof(u32) * (double)(r1 - r0);
+        // runs of column blocks taken as they are from the owner of s: the diagonal block (with its margin) and every
+        // block t > s with fwd(s, t)
+        size_t run0 = lo, run1 = std::min(dm->ld, (size_t)(s + 1) * per);
+        for (int t = s + 1; t < W; ++t) {
+            int q0, q1;
+            shard_rows(dm->N, t, W, &q0, &q1);
+            if (q1 <= q0) break;
+            const size_t c0 = (size_t)t * per, c1 = t == W - 1 ? dm->ld : std::min(dm->ld, (size_t)(t + 1) * per);
+            if (fwd(s, t)) {
+                if (run1 == c0) run1 = c1;
+                else { RID_TRY(copy_cols(s, run0, run1, r1 - r0)); run0 = c0; run1 = c1; }
+            } else {
+                // transposed from the owner of t: its rows [q0, q1) x columns [r0, r1) -> my rows [r0, r1) x columns [q0, q1)
+                const u32 *src = (t == me ? dm->full : dm->peer_full[t]) + (size_t)t * per * dm->ld + (size_t)s * per;
+                u32 *dst = dm->full + (size_t)s * per * dm->ld + (size_t)t * per;
+                dim3 grid((unsigned)((r1 - r0 + 31) / 32), (unsigned)((q1 - q0 + 31) / 32));
+                k_pull_transpose<<<grid, dim3(32, 8), 0, ctx->copy_stream>>>(src, dst, dm->ld, q1 - q0, r1 - r0);
+                ctx->launches++;
+                if (t != me) pulled += (double)(q1 - q0) * (double)(r1 - r0) * sizeof(u32);
+            }
+        }
+        RID_TRY(copy_cols(s, run0, run1, r1 - r0));
     }
+    RID_CUDA(cudaGetLastError());
     ctx->stat[5] = pulled;
-    dm->replica_lo[dm->rank] = 0;
+    dm->replica_lo[me] = 0;
     RID_CUDA(cudaEventRecord(dm->pull_t1, ctx->copy_stream));
     RID_CUDA(cudaEventRecord(dm->replica_ev, ctx->copy_stream));
     dm->replica_state = all_whole ? 2 : 1;
