@@ -462,7 +462,7 @@ def main():
         W.step()
     barrier()
     clocks = ClockSampler(local)
-    if rank == 0:  # one sampler per job: eight concurrent pollers slow every rank's driver calls down
+    if rank == 0 and not os.environ.get("BENCH_NO_NVML"):  # one sampler per job: eight concurrent pollers slow every rank's driver calls down
         clocks.start()
     # inside the timed region the kernels of the roofline objects are bracketed with CUDA events (pre-created); the
     # per-kind breakdown of everything comes from one extra, untimed step below

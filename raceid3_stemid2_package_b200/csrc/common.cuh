@@ -117,6 +117,24 @@ int rid_bcast_ranges(rid_ctx *ctx, void *buf, const size_t *off /* [world + 1] b
 cudaError_t rid_pool_alloc(rid_ctx *ctx, void **p, size_t bytes);
 void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes);
 void rid_pool_trim(rid_ctx *ctx);
+// Short-lived device buffers of the clustering calls (label tables, contingency tables, ...) go through the same pool
+// with their size rounded up to a power of two >= 256 KB, so that a steady-state call makes NO cudaMalloc / cudaFree:
+// those go through the driver's resource manager, where they queue behind whatever else is talking to it (a monitoring
+// process polling the GPUs is enough) -- measured as random 0.1-1.2 s stalls of single sweep / clusterboot calls.
+static inline size_t rid_tmp_size(size_t bytes)
+{
+    size_t s = (size_t)256 << 10;
+    while (s < bytes) s <<= 1;
+    return s;
+}
+template <class T> static inline cudaError_t rid_tmp_alloc(rid_ctx *ctx, T **p, size_t bytes)
+{
+    void *q = nullptr;
+    cudaError_t e = rid_pool_alloc(ctx, &q, rid_tmp_size(bytes));
+    *p = e == cudaSuccess ? reinterpret_cast<T *>(q) : nullptr;
+    return e;
+}
+static inline void rid_tmp_free(rid_ctx *ctx, void *p, size_t bytes) { if (p) rid_pool_free(ctx, p, rid_tmp_size(bytes)); }
 
 // kinds for rid_ctx_profile_get
 enum { RID_PROF_GRAM = 0, RID_PROF_SCAN_SWAP = 1, RID_PROF_SCAN_BUILD = 2, RID_PROF_SCAN_GROUP = 3, RID_PROF_PREP = 4,
@@ -167,6 +185,14 @@ struct rid_dmat {
     double *xraw = nullptr;
     size_t xraw_bytes = 0;
     int xraw_G = 0, xraw_ld = 0;
+    // PAM results on ALL cells that rid_gap_sweep produced on this (immutable) matrix, by k.  clustexp(sat=TRUE) runs
+    // the sweep and then fpc::clusterboot, whose first step is the very same pam(as.dist(D), cln) call
+    // (R/RaceID_utils.R:113 and :132 -> pamkdCBI): rid_clusterboot takes c1 from here instead of repeating it.
+    struct PamMemo {
+        int k = 0, nswaps = 0;
+        std::vector<int> labels, medoids; // cstat numbering (1-based labels by cell; medoid cell of cluster c)
+    };
+    std::vector<PamMemo> pam_memo;
 };
 
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

@@ -287,7 +287,7 @@ void rid_pool_free(rid_ctx *ctx, void *p, size_t bytes)
         if (rid_tracing()) fprintf(stderr, "[rid] small cudaFree %.3f MB took %.2f ms\n", bytes / 1e6, now_ms() - t0);
         return;
     }
-    if (ctx->pool.size() >= 16) { // full: drop the buffer that has waited longest, the steady-state sizes stay cached
+    if (ctx->pool.size() >= 64) { // full: drop the buffer that has waited longest, the steady-state sizes stay cached
         for (size_t i = 0; i < ctx->pool.size(); ++i) {
             if (is_exported(ctx, ctx->pool[i].p)) continue; // a peer may have it mapped (CUDA IPC)
             cudaFree(ctx->pool[i].p);

@@ -2326,7 +2326,7 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     RID_CUDA(cudaMemcpyAsync(order.data(), w->med, (size_t)Kmax * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RID_CUDA(cudaStreamSynchronize(ctx->stream));
     int *d_order = nullptr;
-    RID_CUDA(cudaMalloc(&d_order, (size_t)Kmax * sizeof(int)));
+    RID_CUDA(rid_tmp_alloc(ctx, &d_order, (size_t)Kmax * sizeof(int)));
     RID_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     int rc = RID_OK;
     // Labels of every k this rank owns are kept by column (bytes); W.k is then evaluated for WB values of k per pass
@@ -2337,9 +2337,11 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     u64 *d_S = nullptr;
     std::vector<int> ks;
     if (batched) {
-        if (cudaMalloc(&d_lab, (size_t)Kmax * lab_pitch) != cudaSuccess || cudaMalloc(&d_S, (size_t)WB * w->ld * sizeof(u64)) != cudaSuccess) {
+        if (rid_tmp_alloc(ctx, &d_lab, (size_t)Kmax * lab_pitch) != cudaSuccess ||
+            rid_tmp_alloc(ctx, &d_S, (size_t)WB * w->ld * sizeof(u64)) != cudaSuccess) {
             cudaGetLastError();
-            cudaFree(d_lab); cudaFree(d_S); cudaFree(d_order);
+            rid_tmp_free(ctx, d_lab, (size_t)Kmax * lab_pitch); rid_tmp_free(ctx, d_S, (size_t)WB * w->ld * sizeof(u64));
+            rid_tmp_free(ctx, d_order, (size_t)Kmax * sizeof(int));
             rid_set_error("rid_gap_sweep: out of device memory");
             return RID_ERR_NOMEM;
         }
@@ -2379,8 +2381,22 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
             } else {
                 rc = sweep_chain_step(dm, w, k, B, &hs);
             }
-            std::vector<int> slot;
-            if (rc == RID_OK) rc = pam_collect_labels(dm, w, slot);
+            std::vector<int> slot, h_medpos(k);
+            const bool memo = rc == RID_OK && subset == nullptr && nshare == 1 && !dm->parent && !getenv("RID_NO_MEMO");
+            if (memo && cudaMemcpyAsync(h_medpos.data(), w->medpos, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                rc = RID_ERR_CUDA;
+            if (rc == RID_OK) rc = pam_collect_labels(dm, w, slot); // (synchronises the stream)
+            if (memo && rc == RID_OK) {
+                // PAM(k) on all cells is what clusterboot starts with (c1): keep it with the matrix
+                rid_dmat::PamMemo mm;
+                mm.k = k; mm.nswaps = hs.nswaps;
+                mm.labels.resize(m); mm.medoids.resize(k);
+                number_clusters(slot, k, h_medpos, mm.labels.data(), mm.medoids.data());
+                bool found = false;
+                for (auto &o : dm->pam_memo)
+                    if (o.k == k) { o = std::move(mm); found = true; break; }
+                if (!found) dm->pam_memo.push_back(std::move(mm));
+            }
         }
         if (rc != RID_OK) break;
         if (batched) {
@@ -2427,9 +2443,10 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
             logW[k - 1] = log(0.5 * (double)tot);
         }
     }
-    cudaFree(d_lab);
-    cudaFree(d_S);
-    cudaFree(d_order);
+    // (pooled buffers: every later user is ordered behind this work on ctx->stream)
+    rid_tmp_free(ctx, d_lab, (size_t)Kmax * lab_pitch);
+    rid_tmp_free(ctx, d_S, (size_t)WB * w->ld * sizeof(u64));
+    rid_tmp_free(ctx, d_order, (size_t)Kmax * sizeof(int));
     if (b_buf) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, b_buf, b_bytes); }
     return rc;
 }
@@ -2460,12 +2477,12 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
     if (rc == RID_OK && ctx->world > 1 && dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")) rc = rid_replica_start(dm);
     if (R.active && rc == RID_OK) {
         double *d_lw = nullptr;
-        if (cudaMalloc(&d_lw, (size_t)Kmax * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
+        if (rid_tmp_alloc(ctx, &d_lw, (size_t)Kmax * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
         if (rc == RID_OK && cudaMemcpyAsync(d_lw, logW, (size_t)Kmax * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
         if (rc == RID_OK) rc = rid_allreduce_f64(ctx, d_lw, (size_t)Kmax);
         if (rc == RID_OK && (cudaMemcpyAsync(logW, d_lw, (size_t)Kmax * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
                              cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = RID_ERR_CUDA;
-        cudaFree(d_lw);
+        rid_tmp_free(ctx, d_lw, (size_t)Kmax * sizeof(double));
     }
     replica_end(&R);
     if (rc != RID_OK) return rc;
@@ -2569,7 +2586,21 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         fmask_fut = std::async(std::launch::async, boot_first_masks, &fmasks, N, dm->row0, dm->row1, samples, sample_len, B);
     std::vector<int> med_pos(k);
     int c1_swaps = 0;
-    int rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
+    int rc = RID_OK;
+    const rid_dmat::PamMemo *memo = nullptr;
+    if (!getenv("RID_NO_MEMO"))
+        for (const auto &o : dm->pam_memo)
+            if (o.k == k && (int)o.labels.size() == N) memo = &o;
+    if (memo) {
+        // the k sweep of the same clustexp call already ran pam(as.dist(D), k) on all cells (rid_gap_sweep): identical call,
+        // identical result -- c1 is not repeated
+        std::copy(memo->labels.begin(), memo->labels.end(), partition);
+        std::copy(memo->medoids.begin(), memo->medoids.end(), med_pos.begin());
+        c1_swaps = memo->nswaps;
+        ctx->stat[9] += 1.0;
+    } else {
+        rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
+    }
     if (fmask_fut.valid()) fmask_fut.wait();
     if (rc != RID_OK) return rc;
     for (int i = 0; i < 4; ++i)
@@ -2605,8 +2636,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     const int nshare = R.active ? R.saved_world : 1, myshare = R.active ? R.saved_rank : 0;
     replica_local(&R, true);
     int *d_part = nullptr, *d_tab = nullptr;
-    if (rc == RID_OK && (cudaMalloc(&d_part, (size_t)N * sizeof(int)) != cudaSuccess ||
-                         cudaMalloc(&d_tab, (size_t)k * k * sizeof(int)) != cudaSuccess)) {
+    if (rc == RID_OK && (rid_tmp_alloc(ctx, &d_part, (size_t)N * sizeof(int)) != cudaSuccess ||
+                         rid_tmp_alloc(ctx, &d_tab, (size_t)k * k * sizeof(int)) != cudaSuccess)) {
         rid_set_error("rid_clusterboot: out of device memory");
         rc = RID_ERR_NOMEM;
     }
@@ -2672,7 +2703,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         // (at most 16 replicates per wave: the cancellation poll runs between waves)
         wave = std::max<size_t>(2, std::min<size_t>(std::min<size_t>(mine.size(), 16), budget / (slot_ints * sizeof(int))));
         pin = (int *)rid_pinned(ctx, wave * slot_ints * sizeof(int));
-        if (!pin || cudaMalloc(&d_tabs, wave * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
+        if (!pin || rid_tmp_alloc(ctx, &d_tabs, wave * (size_t)k * k * sizeof(int)) != cudaSuccess) { cudaGetLastError(); pipelined = false; }
     }
     auto run_sync = [&](int b, HostSubset *H) -> int { // one replicate, start to finish, results on the host
         const int m = sample_len[b];
@@ -2738,10 +2769,10 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
             else { ctx->stat[1] += 1.0; rc = run_sync(mine[i], nullptr); } // more swaps than were enqueued ahead (rare): redo this one the plain way
         }
     }
-    if (d_tabs) cudaFree(d_tabs);
+    rid_tmp_free(ctx, d_tabs, wave * (size_t)k * k * sizeof(int));
     if (fut.valid()) fut.wait();
-    cudaFree(d_part);
-    cudaFree(d_tab);
+    rid_tmp_free(ctx, d_part, (size_t)N * sizeof(int));
+    rid_tmp_free(ctx, d_tab, (size_t)k * k * sizeof(int));
     replica_local(&R, false);
     if (R.active) rc = agree_interrupt(ctx, rc);
     if (rc != RID_OK) cudaStreamSynchronize(ctx->stream);
@@ -2749,12 +2780,12 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         // every rank holds the columns of its own replicates and zeros elsewhere: one sum makes them whole
         double *d_br = nullptr;
         const size_t nb = (size_t)k * B;
-        if (cudaMalloc(&d_br, nb * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
+        if (rid_tmp_alloc(ctx, &d_br, nb * sizeof(double)) != cudaSuccess) rc = RID_ERR_NOMEM;
         if (rc == RID_OK && cudaMemcpyAsync(d_br, bootresult, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
         if (rc == RID_OK) rc = rid_allreduce_f64(ctx, d_br, nb);
         if (rc == RID_OK && (cudaMemcpyAsync(bootresult, d_br, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
                              cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = RID_ERR_CUDA;
-        cudaFree(d_br);
+        rid_tmp_free(ctx, d_br, nb * sizeof(double));
     }
     replica_end(&R);
     if (first_buf) { cudaStreamSynchronize(ctx->stream); rid_pool_free(ctx, first_buf, first_bytes); }

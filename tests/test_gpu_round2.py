@@ -474,3 +474,50 @@ def test_spearman_rank_by_sort_equals_counting_kernel(ctx, oracle, monkeypatch):
         assert np.array_equal(Da[ok], Db[ok])
         Do, nz = oracle.dist(np.ascontiguousarray(x.T), "spearman")
         assert nz == 1 and np.max(np.abs(Da[ok] - Do[ok])) <= DIST_TOL
+
+
+def test_clusterboot_takes_c1_from_the_sweep(ctx, oracle, monkeypatch):
+    """clustexp(sat=TRUE) runs clusGapExt's pam(as.dist(D), k) for k = 1..clustnr and then fpc::clusterboot, whose c1
+    is the very same pam(as.dist(D), cln) call (R/RaceID_utils.R:113,132).  rid_gap_sweep leaves its full-set results
+    with the matrix and rid_clusterboot takes c1 from there: identical to the oracle and to RID_NO_MEMO=1, for a k
+    inside the sweep; a k outside the sweep, a sweep on a sample of the cells (`samp`) and a fresh matrix all run c1."""
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    N, B = 1400, 4
+    x, _ = synth_features_numpy(N, 150, 7, 5, "ring")  # a continuum: SWAP really iterates
+    dm = ctx.dist_cellmajor(x, "pearson")
+    Dg = dm.as_matrix()
+    samples = bootstrap_samples(N, B, 17000)
+
+    def hits():
+        return ctx.stats()["c1_taken_from_sweep"]
+
+    h0 = hits()
+    r_plain = dm.clusterboot(5, samples)  # nothing memoised yet
+    assert hits() == h0
+    sub = np.random.default_rng(1).permutation(N)[:700].astype(np.int32)
+    dm.gap_sweep(6, subset=sub)  # a sweep on a sample of the cells says nothing about the full set
+    r_sub = dm.clusterboot(5, samples)
+    assert hits() == h0
+    lw = dm.gap_sweep(6)
+    assert np.max(np.abs(lw - oracle.gap_sweep(Dg, 6))) < 1e-12
+    r_memo = dm.clusterboot(5, samples)
+    assert hits() == h0 + 1
+    r_out = dm.clusterboot(8, samples)  # k beyond the sweep
+    assert hits() == h0 + 1
+    monkeypatch.setenv("RID_NO_MEMO", "1")
+    r_off = dm.clusterboot(5, samples)
+    monkeypatch.delenv("RID_NO_MEMO", raising=False)
+    assert hits() == h0 + 1
+    ro = oracle.clusterboot(Dg, 5, samples)
+    for r in (r_plain, r_sub, r_memo, r_off):
+        assert np.array_equal(r["partition"], ro["partition"]) and np.array_equal(r["id_med"], ro["id_med"])
+        assert np.array_equal(r["bootresult"], ro["bootresult"])
+    ro8 = oracle.clusterboot(Dg, 8, samples)
+    assert np.array_equal(r_out["partition"], ro8["partition"]) and np.array_equal(r_out["bootresult"], ro8["bootresult"])
+    dm.free()
+    dm2 = ctx.dist_cellmajor(x, "pearson")  # the memo lives and dies with the matrix
+    dm2.clusterboot(5, samples)
+    assert hits() == h0 + 1
+    dm2.free()
