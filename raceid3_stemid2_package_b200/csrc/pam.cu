@@ -977,6 +977,174 @@ __global__ void k_wdisp_cols(const int *__restrict__ subset, int m, const unsign
     }
 }
 
+// ---- W.k of ALL partitions of a sweep from ONE pass over the matrix: atoms ------------------------------------------
+// The partitions PAM(1..Kmax) of one matrix are strongly related (mostly one cluster split per k), so the common
+// refinement of all of them -- the "atoms": cells with the same label under every k -- has few classes (A ~ Kmax on
+// clustered data).  With the rows sorted by atom, ONE grouped-column-sum pass (k_scan<2>, caps (0, inf)) gives
+// AQ[a][h] = sum_{j in atom a} D[j][h], and every partition's within-cluster sums follow from that small table:
+//     T_q[c] = sum_{h in c} sum_{a subset of c} AQ[a][h]
+// (exact integers, the same numbers k_wk_batch + k_wdisp_cols produce with one 6-partition pass per 6 values of k).
+// The atoms are refined on the device, one partition at a time: key = atom * k + label, dense ranks of the used keys.
+struct AtomState { int A, overflow, pad0, pad1; };
+
+__global__ void k_atom_init(int *atom, int m, AtomState *as)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) atom[p] = 0;
+    if (p == 0) { as->A = 1; as->overflow = 0; }
+}
+
+__global__ void k_atom_mark(const int *__restrict__ atom, const int *__restrict__ lab_pos, int m, int k, int *table,
+                            const AtomState *as)
+{
+    if (as->overflow) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) table[(size_t)atom[p] * k + lab_pos[p]] = 1;
+}
+
+// table[0 .. A*k): 1 = key in use  ->  1-based dense rank of the key (0 stays 0); A := number of keys in use
+__global__ void __launch_bounds__(1024) k_atom_rank(int *table, int k, AtomState *as, int a_cap)
+{
+    if (as->overflow) return;
+    __shared__ int sh[1024];
+    const int n = as->A * k;
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int cnt = 0;
+    for (int i = b; i < e; ++i) cnt += table[i];
+    sh[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // inclusive scan of the per-thread counts
+        int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - cnt;
+    for (int i = b; i < e; ++i)
+        if (table[i]) table[i] = ++run;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tot = sh[1023];
+        if (tot > a_cap) as->overflow = 1;
+        else as->A = tot;
+    }
+}
+
+// atom := rank of its key (the host clears the table before the next partition's marks)
+__global__ void k_atom_relabel(int *atom, const int *__restrict__ lab_pos, int m, int k, const int *__restrict__ table,
+                               const AtomState *as)
+{
+    if (as->overflow) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) atom[p] = table[(size_t)atom[p] * k + lab_pos[p]] - 1;
+}
+
+// counting sort of the owned rows by atom: histogram, exclusive prefix (one block), scatter with the caps (0, inf) that
+// turn k_scan<2> into plain grouped column sums
+__global__ void k_atom_hist(const int *__restrict__ atom, const int *__restrict__ rows_pos, int nls, int *hist)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) atomicAdd(&hist[atom[rows_pos[t]]], 1);
+}
+__global__ void __launch_bounds__(1024) k_atom_prefix(int *hist, int A)
+{
+    __shared__ int sh[1024];
+    const int per = (A + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(A, b + per);
+    int cnt = 0;
+    for (int i = b; i < e; ++i) cnt += hist[i];
+    sh[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - cnt;
+    for (int i = b; i < e; ++i) { int c = hist[i]; hist[i] = run; run += c; }
+}
+__global__ void k_atom_scatter(const int *__restrict__ atom, const int *__restrict__ rows, const int *__restrict__ rows_pos,
+                               int nls, int *cursor, int *s_row, int *s_grp, u32 *s_capP, u32 *s_capQ)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nls) {
+        const int a = atom[rows_pos[t]];
+        const int i = atomicAdd(&cursor[a], 1);
+        s_row[i] = rows[t];
+        s_grp[i] = a;
+        s_capP[i] = 0u;
+        s_capQ[i] = 0xFFFFFFFFu;
+    }
+}
+
+// atomlab[q][a] = label of atom a under partition q (every cell of an atom carries the same one)
+__global__ void k_atom_labels(const int *__restrict__ atom, const int *__restrict__ subset, int m,
+                              const unsigned char *__restrict__ lab_col, size_t lab_pitch, int nq, int A,
+                              unsigned char *__restrict__ atomlab)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        const int a = atom[p];
+        const size_t h = (size_t)subset[p];
+        for (int q = 0; q < nq; ++q) atomlab[(size_t)q * A + a] = lab_col[(size_t)q * lab_pitch + h];
+    }
+}
+
+// T[q][c] += sum_{h in c} sum_{a in c} AQ[a][h]; cnt[q][c] = cells of cluster c.  Thread = one column h and WKA_PB
+// partitions; blockIdx.y walks a chunk of atoms, blockIdx.z a batch of partitions.
+#define WKA_PB 8
+#define WKA_ACH 512
+__global__ void __launch_bounds__(256)
+k_wk_atoms(const int *__restrict__ subset, int m, const unsigned char *__restrict__ lab_col, size_t lab_pitch, int nq,
+           const u64 *__restrict__ AQ, size_t ld, int A, const unsigned char *__restrict__ atomlab, int kmax,
+           u64 *__restrict__ T /* [nq][kmax] */, int *__restrict__ cnt /* [nq][kmax] */)
+{
+    __shared__ unsigned char sh_al[WKA_PB][WKA_ACH];
+    __shared__ u64 sh_T[WKA_PB * 256];
+    __shared__ int sh_C[WKA_PB * 256];
+    const int q0 = blockIdx.z * WKA_PB, nqb = min(WKA_PB, nq - q0);
+    const int a0 = blockIdx.y * WKA_ACH, na = min(WKA_ACH, A - a0);
+    for (int i = threadIdx.x; i < WKA_PB * WKA_ACH; i += blockDim.x) {
+        const int qq = i / WKA_ACH, a = i % WKA_ACH;
+        sh_al[qq][a] = (qq < nqb && a < na) ? atomlab[(size_t)(q0 + qq) * A + a0 + a] : 0xFE;
+    }
+    for (int i = threadIdx.x; i < WKA_PB * 256; i += blockDim.x) { sh_T[i] = 0ull; sh_C[i] = 0; }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) {
+        const size_t h = (size_t)subset[p];
+        u32 l[WKA_PB];
+        u64 acc[WKA_PB];
+#pragma unroll
+        for (int qq = 0; qq < WKA_PB; ++qq) {
+            l[qq] = qq < nqb ? (u32)lab_col[(size_t)(q0 + qq) * lab_pitch + h] : 0xFFu;
+            acc[qq] = 0ull;
+        }
+        const u64 *col = AQ + (size_t)a0 * ld + h;
+        for (int a = 0; a < na; ++a) {
+            const u64 v = col[(size_t)a * ld];
+#pragma unroll
+            for (int qq = 0; qq < WKA_PB; ++qq) acc[qq] += (u32)sh_al[qq][a] == l[qq] ? v : 0ull;
+        }
+#pragma unroll
+        for (int qq = 0; qq < WKA_PB; ++qq)
+            if (qq < nqb) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(&sh_T[qq * 256 + l[qq]]), (unsigned long long)acc[qq]);
+                if (blockIdx.y == 0) atomicAdd(&sh_C[qq * 256 + l[qq]], 1);
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < WKA_PB * 256; i += blockDim.x) {
+        const int qq = i >> 8, c = i & 255;
+        if (qq < nqb && c < kmax) {
+            if (sh_T[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&T[(size_t)(q0 + qq) * kmax + c]), (unsigned long long)sh_T[i]);
+            if (sh_C[i]) atomicAdd(&cnt[(size_t)(q0 + qq) * kmax + c], sh_C[i]);
+        }
+    }
+}
+
 // deterministic sum of n doubles (fixed order) -> out[0]
 __global__ void k_sum_f64(const double *__restrict__ x, int n, double *out)
 {
@@ -1462,7 +1630,7 @@ k_colsum_batch(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chu
 // one CTA per replicate: arg min of SP0 over the replicate's cells, ties to the LARGEST position (cand_better_build)
 __global__ void __launch_bounds__(256)
 k_first_medoid(const u64 *__restrict__ sp0 /* [.][ld] */, size_t ld, const int *__restrict__ cat, const long long *__restrict__ off,
-               const int *__restrict__ rep_of_slot, int2 *__restrict__ first /* by replicate */)
+               const int *__restrict__ rep_of_slot, int2 *__restrict__ first /* by replicate */, int N)
 {
     __shared__ Cand sh[32];
     const int b = rep_of_slot[blockIdx.x];
@@ -1472,12 +1640,31 @@ k_first_medoid(const u64 *__restrict__ sp0 /* [.][ld] */, size_t ld, const int *
     Cand best;
     best.val = ~0ull; best.p = -1; best.mp = 0; best.slot = 0;
     for (int p = threadIdx.x; p < m; p += blockDim.x) {
+        const int h = cells[p];
+        if (h < 0 || h >= N) continue; // (the replicate's own host-side validation reports it)
         Cand x;
-        x.val = sp[cells[p]]; x.p = p; x.mp = 0; x.slot = 0;
+        x.val = sp[h]; x.p = p; x.mp = 0; x.slot = 0;
         if (cand_better_build(x, best)) best = x;
     }
     best = cand_reduce_block<true>(best, sh);
-    if (threadIdx.x == 0) first[b] = make_int2(cells[best.p], best.p);
+    if (threadIdx.x == 0) first[b] = best.p >= 0 ? make_int2(cells[best.p], best.p) : make_int2(0, 0);
+}
+
+// row masks of the batched first-pick passes, built from the samples on the device: bit (b mod CSB) of
+// mask[b / CSB][row] is set iff owned row `row` belongs to replicate b (16-bit masks, OR-ed in as halves of 32-bit words)
+__global__ void k_first_masks(const int *__restrict__ cat, const long long *__restrict__ off, int row0, int nloc, int csb,
+                              unsigned int *__restrict__ mask32)
+{
+    const int b = blockIdx.y;
+    const int *cells = cat + off[b];
+    const int len = (int)(off[b + 1] - off[b]);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < len; p += gridDim.x * blockDim.x) {
+        const int r = cells[p] - row0;
+        if (r >= 0 && r < nloc) {
+            const size_t e = (size_t)(b / csb) * nloc + r;
+            atomicOr(&mask32[e >> 1], (1u << (b % csb)) << ((e & 1) * 16));
+        }
+    }
 }
 
 // cap[c] = D[cell_c][h0] for the compact columns c of a replicate; read as D[min][max] so that a replica that holds only
@@ -2347,6 +2534,23 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
         }
         cudaMemsetAsync(d_lab, 0xFF, (size_t)Kmax * lab_pitch, ctx->stream); // 0xFF = column outside the subset
     }
+    // W.k of all partitions from one pass (atoms, see k_wk_atoms): the common refinement of the partitions is built on the
+    // device while the sweep runs; at most a_cap classes (4 GB of grouped column sums), else the batched passes below
+    const int a_cap = getenv("RID_WK_ATOM_CAP") ? std::max(1, atoi(getenv("RID_WK_ATOM_CAP")))
+                                                : (int)std::min<size_t>(8192, ((size_t)4 << 30) / (w->ld * sizeof(u64)));
+    bool atoms = batched && nshare == 1 && Kmax >= 2 && (a_cap >= 2 * Kmax || getenv("RID_WK_ATOM_CAP")) && !getenv("RID_WK_BATCH");
+    int *d_atom = nullptr, *d_table = nullptr;
+    AtomState *d_as = nullptr;
+    const size_t atom_bytes = (size_t)m * sizeof(int), table_bytes = (size_t)a_cap * Kmax * sizeof(int);
+    if (atoms) {
+        if (rid_tmp_alloc(ctx, &d_atom, atom_bytes) != cudaSuccess || rid_tmp_alloc(ctx, &d_table, table_bytes) != cudaSuccess ||
+            rid_tmp_alloc(ctx, &d_as, sizeof(AtomState)) != cudaSuccess) {
+            cudaGetLastError();
+            atoms = false;
+        } else {
+            LAUNCH(ctx, k_atom_init, nblk(m, 256), 256, 0, d_atom, m, d_as);
+        }
+    }
     // state of the BUILD medoids of the last k this rank handled (see sweep_chain_step)
     const bool chain = !getenv("RID_SWAP_FULL") && !getenv("RID_SWEEP_FULL");
     SweepChain B;
@@ -2402,12 +2606,87 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
         if (batched) {
             LAUNCH(ctx, k_labels_by_column, nblk(m, 256), 256, 0, w->subset, w->lab_pos, m, d_lab + (size_t)ks.size() * lab_pitch);
             ks.push_back(k);
+            if (atoms && k >= 2) { // refine the atoms by this partition
+                cudaMemsetAsync(d_table, 0, (size_t)a_cap * k * sizeof(int), ctx->stream);
+                LAUNCH(ctx, k_atom_mark, nblk(m, 256), 256, 0, d_atom, w->lab_pos, m, k, d_table, d_as);
+                LAUNCH(ctx, k_atom_rank, 1, 1024, 0, d_table, k, d_as, a_cap);
+                LAUNCH(ctx, k_atom_relabel, nblk(m, 256), 256, 0, d_atom, w->lab_pos, m, k, d_table, d_as);
+            }
         } else {
             rc = within_disp(dm, w, k, &W, nullptr);
             logW[k - 1] = log(W);
         }
     }
-    for (size_t q0 = 0; batched && rc == RID_OK && q0 < ks.size(); q0 += WB) {
+    bool wk_done = false;
+    if (atoms && rc == RID_OK && !ks.empty()) {
+        AtomState as;
+        if (cudaMemcpyAsync(&as, d_as, sizeof(as), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RID_ERR_CUDA;
+        const int A = as.A, nq = (int)ks.size();
+        u64 *d_AQ = nullptr, *d_T = nullptr;
+        int *d_cnt = nullptr, *d_hist = nullptr;
+        unsigned char *d_al = nullptr;
+        const size_t aq_bytes = (size_t)A * w->ld * sizeof(u64), t_bytes = (size_t)nq * Kmax * sizeof(u64),
+                     c_bytes = (size_t)nq * Kmax * sizeof(int), h_bytes = (size_t)A * sizeof(int), al_bytes = (size_t)nq * A;
+        if (rc == RID_OK && !as.overflow && A >= 1 &&
+            rid_tmp_alloc(ctx, &d_AQ, aq_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_T, t_bytes) == cudaSuccess &&
+            rid_tmp_alloc(ctx, &d_cnt, c_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_hist, h_bytes) == cudaSuccess &&
+            rid_tmp_alloc(ctx, &d_al, al_bytes) == cudaSuccess) {
+            cudaMemsetAsync(d_AQ, 0, aq_bytes, ctx->stream);
+            cudaMemsetAsync(d_T, 0, t_bytes, ctx->stream);
+            cudaMemsetAsync(d_cnt, 0, c_bytes, ctx->stream);
+            cudaMemsetAsync(d_hist, 0, h_bytes, ctx->stream);
+            if (w->nls) {
+                LAUNCH(ctx, k_atom_hist, nblk(w->nls, 256), 256, 0, d_atom, w->rows_pos, w->nls, d_hist);
+                LAUNCH(ctx, k_atom_prefix, 1, 1024, 0, d_hist, A);
+                LAUNCH(ctx, k_atom_scatter, nblk(w->nls, 256), 256, 0, d_atom, w->rows, w->rows_pos, w->nls, d_hist, w->s_row,
+                       w->s_grp, w->s_capP, w->s_capQ);
+                int strips = (int)((w->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
+                int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
+                int rpc = std::min(std::max((((w->nls + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
+                dim3 grid(strips, std::min((w->nls + rpc - 1) / rpc, want_y * 2));
+                cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_GROUP);
+                auto s8 = k_scan<2, 8>;
+                auto s2 = k_scan<2, 2>;
+                if (dm->bits <= 28)
+                    LAUNCH(ctx, s8, grid, SCAN_THREADS, 0, w->mat, w->ld, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls,
+                           (const int *)nullptr, rpc, (u64 *)nullptr, d_AQ, w->state, 0);
+                else
+                    LAUNCH(ctx, s2, grid, SCAN_THREADS, 0, w->mat, w->ld, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls,
+                           (const int *)nullptr, rpc, (u64 *)nullptr, d_AQ, w->state, 0);
+                rid_prof_end(ctx, pe, RID_PROF_SCAN_GROUP, (double)w->nls * (double)w->m * 4.0, (double)w->nls * (double)w->ld * 4.0);
+            }
+            LAUNCH(ctx, k_atom_labels, nblk(m, 256), 256, 0, d_atom, w->subset, m, d_lab, lab_pitch, nq, A, d_al);
+            dim3 g2(nblk(m, 256), (A + WKA_ACH - 1) / WKA_ACH, (nq + WKA_PB - 1) / WKA_PB);
+            LAUNCH(ctx, k_wk_atoms, g2, 256, 0, w->subset, m, d_lab, lab_pitch, nq, d_AQ, w->ld, A, d_al, Kmax, d_T, d_cnt);
+            if (cudaGetLastError() != cudaSuccess) rc = RID_ERR_CUDA;
+            // every rank summed its own rows: the partial within-cluster sums add up (the counts are complete on every rank)
+            if (rc == RID_OK) rc = rid_allreduce_u64(ctx, d_T, (size_t)nq * Kmax);
+            std::vector<u64> hT((size_t)nq * Kmax);
+            std::vector<int> hC((size_t)nq * Kmax);
+            if (rc == RID_OK && (cudaMemcpyAsync(hT.data(), d_T, t_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                                 cudaMemcpyAsync(hC.data(), d_cnt, c_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                                 cudaStreamSynchronize(ctx->stream) != cudaSuccess)) rc = RID_ERR_CUDA;
+            for (int q = 0; q < nq && rc == RID_OK; ++q) {
+                const int k = ks[q];
+                long double tot = 0.0L;
+                for (int c = 0; c < k; ++c)
+                    if (hC[(size_t)q * Kmax + c] > 0)
+                        tot += (long double)((double)((long double)hT[(size_t)q * Kmax + c] * (long double)dm->step /
+                                                      (long double)hC[(size_t)q * Kmax + c]));
+                logW[k - 1] = log(0.5 * (double)tot);
+            }
+            wk_done = rc == RID_OK;
+            ctx->stat[10] = (double)A;
+        } else {
+            cudaGetLastError();
+            ctx->stat[10] = as.overflow ? -1.0 : 0.0; // more classes than a_cap (or no memory): the batched passes do it
+        }
+        rid_tmp_free(ctx, d_AQ, aq_bytes); rid_tmp_free(ctx, d_T, t_bytes); rid_tmp_free(ctx, d_cnt, c_bytes);
+        rid_tmp_free(ctx, d_hist, h_bytes); rid_tmp_free(ctx, d_al, al_bytes);
+    }
+    rid_tmp_free(ctx, d_atom, atom_bytes); rid_tmp_free(ctx, d_table, table_bytes); rid_tmp_free(ctx, d_as, sizeof(AtomState));
+    for (size_t q0 = 0; batched && !wk_done && rc == RID_OK && q0 < ks.size(); q0 += WB) {
         const int nq = (int)std::min<size_t>(WB, ks.size() - q0);
         cudaMemsetAsync(d_S, 0, (size_t)WB * w->ld * sizeof(u64), ctx->stream);
         if (w->nls) {
@@ -2492,37 +2771,21 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
 // BUILD's first pick of every bootstrap replicate, before any replicate starts: the step-0 column sums of CSB replicates
 // per pass over this rank's rows (k_colsum_batch), summed over the ranks, then the arg min per replicate
 // (k_first_medoid).  Runs on the sharded matrix with the real world size (before any switch to a replica).
-// The row masks of all batches are built on a helper thread while c1 runs (boot_first_masks): with several ranks a pass
-// takes about a millisecond, and building a batch's mask between the passes left the GPU waiting for the host.
+// The row masks of all batches are built from the samples on the device (k_first_masks).
 struct FirstMasks {
-    int err = 0;
-    char msg[96] = {0};
     int nbatch = 0;
-    std::vector<unsigned short> mask; // [nbatch][nloc]
-    std::vector<int> rep;             // [nbatch][CSB] replicate of every slot (padding repeats the batch's last one)
-    std::vector<long long> off;       // [B + 1]
+    std::vector<int> rep;       // [nbatch][CSB] replicate of every slot (padding repeats the batch's last one)
+    std::vector<long long> off; // [B + 1]
 };
-static void boot_first_masks(FirstMasks *M, int N, int row0, int row1, const int *samples, const int *sample_len, int B)
+static void boot_first_tables(FirstMasks *M, const int *sample_len, int B)
 {
-    const int nloc = row1 - row0;
     M->nbatch = (B + CSB - 1) / CSB;
     M->off.assign(B + 1, 0);
     for (int b = 0; b < B; ++b) M->off[b + 1] = M->off[b] + sample_len[b];
-    M->mask.assign((size_t)M->nbatch * std::max(nloc, 1), 0);
     M->rep.assign((size_t)M->nbatch * CSB, 0);
     for (int t = 0; t < M->nbatch; ++t) {
         const int b0 = t * CSB, nb = std::min(CSB, B - b0);
-        unsigned short *hm = M->mask.data() + (size_t)t * std::max(nloc, 1);
         for (int r = 0; r < CSB; ++r) M->rep[(size_t)t * CSB + r] = b0 + std::min(r, nb - 1);
-        for (int r = 0; r < nb; ++r) {
-            const int *sp = samples + M->off[b0 + r];
-            const int len = sample_len[b0 + r];
-            for (int p = 0; p < len; ++p) {
-                const int h = sp[p];
-                if (h < 0 || h >= N) { M->err = RID_ERR_ARG; snprintf(M->msg, sizeof(M->msg), "bootstrap sample index %d out of range", h); return; }
-                if (h >= row0 && h < row1) hm[h - row0] |= (unsigned short)(1u << r);
-            }
-        }
     }
 }
 
@@ -2533,12 +2796,16 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
 {
     rid_ctx *ctx = dm->ctx;
     const int nloc = dm->row1 - dm->row0;
-    if (M.err) { rid_set_error("%s", M.msg); return M.err; }
     // (pageable sources: staged by the time the calls return)
     RID_CUDA(cudaMemcpyAsync(d_cat, samples, (size_t)M.off[B] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(d_off, M.off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(d_rep, M.rep.data(), M.rep.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (nloc) RID_CUDA(cudaMemcpyAsync(d_mask, M.mask.data(), (size_t)M.nbatch * nloc * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+    if (nloc) {
+        const size_t mask_bytes = (((size_t)M.nbatch * nloc * sizeof(unsigned short)) + 3) & ~(size_t)3;
+        RID_CUDA(cudaMemsetAsync(d_mask, 0, mask_bytes, ctx->stream));
+        dim3 gm(std::max(1, std::min(64, nblk(dm->N, 256))), B);
+        LAUNCH(ctx, k_first_masks, gm, 256, 0, d_cat, d_off, dm->row0, nloc, CSB, reinterpret_cast<unsigned int *>(d_mask));
+    }
     int strips = (int)((dm->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
     int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
     int rpc = std::min(std::max((((nloc + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
@@ -2556,7 +2823,7 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
         }
         RID_CUDA(cudaGetLastError());
         RID_TRY(rid_allreduce_u64(ctx, d_sp0, (size_t)CSB * dm->ld));
-        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep + (size_t)t * CSB, d_first);
+        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep + (size_t)t * CSB, d_first, dm->N);
         RID_CUDA(cudaGetLastError());
     }
     return RID_OK;
@@ -2576,14 +2843,12 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     // the copy engines start (or go on) pulling the peers' row blocks while c1 and the first picks run on the shard
     if (ctx->world > 1 && dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")) RID_TRY(rid_replica_start(dm));
     // BUILD's first pick of every replicate comes from a few batched passes over this rank's rows (boot_first_medoids);
-    // only the enqueue-only schedule on a complete view consumes it.  The row masks are built while c1 runs.
+    // only the enqueue-only schedule on a complete view consumes it.
     const bool want_first = B > 0 && k >= 2 && k * k <= K2MAX && !getenv("RID_SWAP_FULL") && !getenv("RID_BOOT_SYNC") &&
                             !getenv("RID_NO_FIRST") &&
                             (ctx->world == 1 || (dm->full && dm->peers_ok && !getenv("RID_NO_REPLICA")));
     FirstMasks fmasks;
-    std::future<void> fmask_fut;
-    if (want_first)
-        fmask_fut = std::async(std::launch::async, boot_first_masks, &fmasks, N, dm->row0, dm->row1, samples, sample_len, B);
+    if (want_first) boot_first_tables(&fmasks, sample_len, B);
     std::vector<int> med_pos(k);
     int c1_swaps = 0;
     int rc = RID_OK;
@@ -2601,7 +2866,6 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
     } else {
         rc = pam_run(dm, nullptr, N, k, med_pos.data(), partition, nullptr, nullptr, &c1_swaps);
     }
-    if (fmask_fut.valid()) fmask_fut.wait();
     if (rc != RID_OK) return rc;
     for (int i = 0; i < 4; ++i)
         if (!ctx->phase_ev[i]) RID_CUDA(cudaEventCreate(&ctx->phase_ev[i]));

@@ -197,7 +197,7 @@ class Context:
 
     def stats(self) -> dict:
         names = ("swaps", "boot_redone", "c1_ms", "first_picks_and_replica_wait_ms", "replicates_ms", "replica_pull_bytes", "boot_ahead",
-                 "replicates_host_enqueue_ms", "replica_pull_ms", "c1_taken_from_sweep")
+                 "replicates_host_enqueue_ms", "replica_pull_ms", "c1_taken_from_sweep", "wk_atoms")
         return {n: load().rid_ctx_stat(self._h, i) for i, n in enumerate(names)}
 
     def trim(self):

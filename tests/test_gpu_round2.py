@@ -521,3 +521,38 @@ def test_clusterboot_takes_c1_from_the_sweep(ctx, oracle, monkeypatch):
     dm2.clusterboot(5, samples)
     assert hits() == h0 + 1
     dm2.free()
+
+
+@pytest.mark.parametrize("metric", ["pearson", "euclidean"])
+def test_sweep_wk_from_atoms_equals_batched_passes(ctx, oracle, metric, monkeypatch):
+    """W.k of all partitions of a sweep from ONE grouped-column-sum pass over the common refinement of the partitions
+    (the atoms), against the 6-partitions-per-pass kernel (RID_WK_BATCH=1) and the oracle: identical logW (the
+    within-cluster sums are exact integers either way).  Full set and a `samp`-style subset (compact copy, positions in
+    arbitrary order); a cap of 4 classes forces the overflow fallback; both fixed-point grids."""
+    from raceid3_stemid2_package_b200.synth import synth_features_numpy
+
+    N, K = 1300, 9
+    if metric == "pearson":
+        x, _ = synth_features_numpy(N, 160, 6, 11, "ring")
+        dm = ctx.dist_cellmajor(x, metric)
+    else:
+        rng = np.random.default_rng(8)
+        P = rng.normal(0, 1, (4, N)) + 3.0 * rng.integers(0, 5, N)
+        dm = ctx.dist(P * 20.0, metric)
+    Dg = dm.as_matrix()
+    sub = np.random.default_rng(2).permutation(N)[:1100].astype(np.int32)
+    for subset in (None, sub):
+        ref = oracle.gap_sweep(Dg, K, subset=subset)
+        lw_atoms = dm.gap_sweep(K, subset=subset)
+        A = ctx.stats()["wk_atoms"]
+        assert A >= K  # the atoms path ran (at least as many classes as the finest partition has clusters)
+        monkeypatch.setenv("RID_WK_BATCH", "1")
+        lw_batch = dm.gap_sweep(K, subset=subset)
+        monkeypatch.delenv("RID_WK_BATCH", raising=False)
+        monkeypatch.setenv("RID_WK_ATOM_CAP", "4")
+        lw_over = dm.gap_sweep(K, subset=subset)
+        assert ctx.stats()["wk_atoms"] == -1  # more classes than the cap: the batched passes did it
+        monkeypatch.delenv("RID_WK_ATOM_CAP", raising=False)
+        assert np.array_equal(lw_atoms, lw_batch) and np.array_equal(lw_atoms, lw_over)
+        assert np.max(np.abs(lw_atoms - ref)) < 1e-12
+    dm.free()
