@@ -1627,6 +1627,102 @@ k_colsum_batch(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chu
             if (acc[b][c]) red_add_u64(out + (size_t)b * ld + col + c, acc[b][c]);
 }
 
+// The same sums on the tensor cores, 16 replicates per pass: SP0 = M x D is a matrix product of the 0/1 membership matrix
+// M [16 replicates x rows] with the matrix itself, and D splits exactly into its four byte planes,
+//     sum_j M[b][j] D[j][h] = sum_d 256^d  sum_j M[b][j] byte_d(D[j][h]),
+// each an u8 x u8 -> s32 product that mma.sync.m16n8k32 evaluates without rounding (255 x rows < 2^31).  A warp owns 32
+// columns: lane (g, t) streams rows 4t..4t+3 and 16+4t..16+4t+3 of every 32-row block at columns 4g..4g+3 (128-bit loads, a
+// warp instruction covers 4 rows x 128 contiguous bytes), transposes 4 rows x 4 bytes per column into the B fragments of
+// the four planes (8 PRMT) and issues 16 MMAs per block; the A fragments (membership bits of the block's rows) are
+// built once per row chunk in shared memory.  The IMAD kernel above needs one multiply-add per element and replicate
+// (FMA-pipe bound at 10 replicates per pass, 4.3 TB/s); this one is HBM bound.
+#define CSM 16
+#define CM_ROWS 512
+__device__ __forceinline__ void mma_u8_16832(int (&c)[4], const uint4 &a, u32 b0, u32 b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ u32 u4c(const uint4 &v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+
+__global__ void __launch_bounds__(128)
+k_colsum_mma(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chunk /* multiple of 32, <= CM_ROWS */,
+             const unsigned short *__restrict__ mask /* [nrows]: bit b = the row belongs to replicate b of the batch */,
+             u64 *__restrict__ out /* [CSM][ld] */)
+{
+    __shared__ unsigned short sh_m[CM_ROWS];
+    __shared__ uint4 sh_a[CM_ROWS / 32][32]; // A fragment of every 32-row block, by lane
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t col0 = (size_t)blockIdx.x * 128 + (size_t)warp * 32; // (ld is a multiple of 128: a CTA is all in or all out)
+    const u32 *base = D + col0 + 4 * g;
+    int acc[4][4][4]; // [column of the lane's uint4][byte plane][C fragment]
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[c][pl][r] = 0;
+    for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < nrows; chunk += gridDim.y) {
+        const int r_begin = chunk * rows_per_chunk;
+        const int nr = min(nrows - r_begin, rows_per_chunk);
+        const int nb32 = (nr + 31) >> 5;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb32 * 32; i += 128) sh_m[i] = i < nr ? mask[r_begin + i] : (unsigned short)0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb32 * 32; i += 128) {
+            const int gg = (i & 31) >> 2, tt = i & 3;
+            const unsigned short *m = sh_m + (i & ~31);
+            u32 a[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { // a0: (replicate gg, rows 4tt..), a1: (gg+8, 4tt..), a2: (gg, 16+4tt..), a3: (gg+8, 16+4tt..)
+                const int rp = gg + ((r & 1) ? 8 : 0), r0 = ((r & 2) ? 16 : 0) + 4 * tt;
+                u32 v = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v |= (((u32)m[r0 + e] >> rp) & 1u) << (8 * e);
+                a[r] = v;
+            }
+            sh_a[i >> 5][i & 31] = make_uint4(a[0], a[1], a[2], a[3]);
+        }
+        __syncthreads();
+        for (int blk = 0; blk < nb32; ++blk) {
+            const int rb = r_begin + blk * 32 + 4 * t;
+            uint4 d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = min(rb + (u < 4 ? u : 12 + u), nrows - 1); // (rows past the end carry mask 0)
+                d[u] = ld_stream(base + (size_t)row * ld);
+            }
+            const uint4 a = sh_a[blk][lane];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                u32 b0[4], b1[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { // rows 4t.. (b0) and 16+4t.. (b1): 4 x 4 byte transpose
+                    const u32 w0 = u4c(d[4 * h], c), w1 = u4c(d[4 * h + 1], c), w2 = u4c(d[4 * h + 2], c), w3 = u4c(d[4 * h + 3], c);
+                    const u32 t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                    const u32 t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                    u32 *b = h ? b1 : b0;
+                    b[0] = __byte_perm(t0, t1, 0x5410); b[1] = __byte_perm(t0, t1, 0x7632);
+                    b[2] = __byte_perm(t2, t3, 0x5410); b[3] = __byte_perm(t2, t3, 0x7632);
+                }
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) mma_u8_16832(acc[c][pl], a, b0[pl], b1[pl]);
+            }
+        }
+    }
+    // C fragment r of lane (g, t): replicate g (+8 if r & 2), MMA column 2t + (r & 1) = the column group whose lanes fed it
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const u64 v = (u64)(u32)acc[c][0][r] + ((u64)(u32)acc[c][1][r] << 8) + ((u64)(u32)acc[c][2][r] << 16) +
+                          ((u64)(u32)acc[c][3][r] << 24);
+            const int rp = g + ((r & 2) ? 8 : 0), n = 2 * t + (r & 1);
+            if (v) red_add_u64(out + (size_t)rp * ld + col0 + 4 * n + c, v);
+        }
+}
+
 // one CTA per replicate: arg min of SP0 over the replicate's cells, ties to the LARGEST position (cand_better_build)
 __global__ void __launch_bounds__(256)
 k_first_medoid(const u64 *__restrict__ sp0 /* [.][ld] */, size_t ld, const int *__restrict__ cat, const long long *__restrict__ off,
@@ -2773,29 +2869,31 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
 // (k_first_medoid).  Runs on the sharded matrix with the real world size (before any switch to a replica).
 // The row masks of all batches are built from the samples on the device (k_first_masks).
 struct FirstMasks {
+    int csb = CSM;              // replicates per pass: CSM on the tensor cores, CSB with the IMAD kernel (RID_COLSUM_IMAD=1)
     int nbatch = 0;
-    std::vector<int> rep;       // [nbatch][CSB] replicate of every slot (padding repeats the batch's last one)
+    std::vector<int> rep;       // [nbatch][csb] replicate of every slot (padding repeats the batch's last one)
     std::vector<long long> off; // [B + 1]
 };
 static void boot_first_tables(FirstMasks *M, const int *sample_len, int B)
 {
-    M->nbatch = (B + CSB - 1) / CSB;
+    const int csb = M->csb = getenv("RID_COLSUM_IMAD") ? CSB : CSM;
+    M->nbatch = (B + csb - 1) / csb;
     M->off.assign(B + 1, 0);
     for (int b = 0; b < B; ++b) M->off[b + 1] = M->off[b] + sample_len[b];
-    M->rep.assign((size_t)M->nbatch * CSB, 0);
+    M->rep.assign((size_t)M->nbatch * csb, 0);
     for (int t = 0; t < M->nbatch; ++t) {
-        const int b0 = t * CSB, nb = std::min(CSB, B - b0);
-        for (int r = 0; r < CSB; ++r) M->rep[(size_t)t * CSB + r] = b0 + std::min(r, nb - 1);
+        const int b0 = t * csb, nb = std::min(csb, B - b0);
+        for (int r = 0; r < csb; ++r) M->rep[(size_t)t * csb + r] = b0 + std::min(r, nb - 1);
     }
 }
 
 // d_first[b] = (cell, position) for every replicate b; d_cat / d_off are the samples on the device.
 static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samples, int B, int2 *d_first, int *d_cat,
-                              long long *d_off, u64 *d_sp0 /* [CSB][ld] */, int *d_rep /* [nbatch][CSB] */,
+                              long long *d_off, u64 *d_sp0 /* [csb][ld] */, int *d_rep /* [nbatch][csb] */,
                               unsigned short *d_mask /* [nbatch][nloc] */)
 {
     rid_ctx *ctx = dm->ctx;
-    const int nloc = dm->row1 - dm->row0;
+    const int nloc = dm->row1 - dm->row0, csb = M.csb;
     // (pageable sources: staged by the time the calls return)
     RID_CUDA(cudaMemcpyAsync(d_cat, samples, (size_t)M.off[B] * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(d_off, M.off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -2804,26 +2902,32 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
         const size_t mask_bytes = (((size_t)M.nbatch * nloc * sizeof(unsigned short)) + 3) & ~(size_t)3;
         RID_CUDA(cudaMemsetAsync(d_mask, 0, mask_bytes, ctx->stream));
         dim3 gm(std::max(1, std::min(64, nblk(dm->N, 256))), B);
-        LAUNCH(ctx, k_first_masks, gm, 256, 0, d_cat, d_off, dm->row0, nloc, CSB, reinterpret_cast<unsigned int *>(d_mask));
+        LAUNCH(ctx, k_first_masks, gm, 256, 0, d_cat, d_off, dm->row0, nloc, csb, reinterpret_cast<unsigned int *>(d_mask));
     }
     int strips = (int)((dm->ld + SCAN_THREADS * 4 - 1) / (SCAN_THREADS * 4));
     int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
     int rpc = std::min(std::max((((nloc + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
     dim3 grid(strips, std::max(1, std::min((nloc + rpc - 1) / rpc, want_y * 2)));
+    // tensor-core kernel: a CTA owns 128 columns and walks row chunks of <= CM_ROWS rows (multiples of 32)
+    const int strips_m = (int)(dm->ld / 128);
+    const int want_ym = std::max(1, (ctx->sm_count * 16 + strips_m - 1) / strips_m);
+    const int rpc_m = std::min(std::max((((nloc + want_ym - 1) / want_ym) + 31) & ~31, 32), CM_ROWS);
+    dim3 grid_m(strips_m, std::max(1, std::min((nloc + rpc_m - 1) / rpc_m, want_ym * 2)));
     for (int t = 0; t < M.nbatch; ++t) {
-        const int nb = std::min(CSB, B - t * CSB);
-        RID_CUDA(cudaMemsetAsync(d_sp0, 0, (size_t)CSB * dm->ld * sizeof(u64), ctx->stream));
+        const int nb = std::min(csb, B - t * csb);
+        RID_CUDA(cudaMemsetAsync(d_sp0, 0, (size_t)csb * dm->ld * sizeof(u64), ctx->stream));
         if (nloc) {
             cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_BUILD);
             auto k8 = k_colsum_batch<8>;
             auto k2 = k_colsum_batch<2>;
-            if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
+            if (csb == CSM) LAUNCH(ctx, k_colsum_mma, grid_m, 128, 0, dm->D, dm->ld, nloc, rpc_m, d_mask + (size_t)t * nloc, d_sp0);
+            else if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
             else LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
             rid_prof_end(ctx, pe, RID_PROF_SCAN_BUILD, (double)nloc * (double)dm->N * 4.0, (double)nloc * (double)dm->ld * 4.0);
         }
         RID_CUDA(cudaGetLastError());
-        RID_TRY(rid_allreduce_u64(ctx, d_sp0, (size_t)CSB * dm->ld));
-        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep + (size_t)t * CSB, d_first, dm->N);
+        RID_TRY(rid_allreduce_u64(ctx, d_sp0, (size_t)csb * dm->ld));
+        LAUNCH(ctx, k_first_medoid, nb, 256, 0, d_sp0, dm->ld, d_cat, d_off, d_rep + (size_t)t * csb, d_first, dm->N);
         RID_CUDA(cudaGetLastError());
     }
     return RID_OK;
@@ -2878,8 +2982,8 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         const long long tot = fmasks.off.empty() ? 0 : fmasks.off[B];
         auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
         const size_t o_first = 0, o_off = o_first + al((size_t)B * sizeof(int2)), o_rep = o_off + al((size_t)(B + 1) * sizeof(long long)),
-                     o_sp0 = o_rep + al((size_t)std::max(fmasks.nbatch, 1) * CSB * sizeof(int)),
-                     o_mask = o_sp0 + al((size_t)CSB * dm->ld * sizeof(u64)),
+                     o_sp0 = o_rep + al((size_t)std::max(fmasks.nbatch, 1) * fmasks.csb * sizeof(int)),
+                     o_mask = o_sp0 + al((size_t)fmasks.csb * dm->ld * sizeof(u64)),
                      o_cat = o_mask + al((size_t)std::max(fmasks.nbatch, 1) * std::max(nloc, 1) * sizeof(unsigned short));
         first_bytes = std::max<size_t>(o_cat + al((size_t)std::max<long long>(tot, 1) * sizeof(int)), (size_t)256 << 10);
         if (rid_pool_alloc(ctx, (void **)&first_buf, first_bytes) != cudaSuccess) { cudaGetLastError(); first_buf = nullptr; }
