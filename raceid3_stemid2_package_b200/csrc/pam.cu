@@ -240,13 +240,16 @@ __global__ void k_fill_u32(u32 *p, u32 v, int n)
     if (i < n) p[i] = v;
 }
 
-__global__ void k_zero(u64 *acc, size_t n_acc, int *hist, int n_hist, const PamState *st, int check_done)
+__global__ void k_zero(u64 *acc, size_t n_acc, int *hist, int n_hist, const PamState *st, int check_done,
+                       int *hist2 = nullptr, int n_hist2 = 0, int *counter = nullptr)
 {
     if (check_done && st->done) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = i; t < n_acc; t += stride) acc[t] = 0ull;
     if (i < (size_t)n_hist) hist[i] = 0;
+    for (size_t t = i; t < (size_t)n_hist2; t += stride) hist2[t] = 0; // (incremental SWAP: pair-key counts, changed-row counter)
+    if (i == 0 && counter) *counter = 0;
 }
 
 __global__ void k_state_init(PamState *st)
@@ -301,7 +304,7 @@ k_scan(const u32 *__restrict__ D, size_t ld, const int *__restrict__ s_row,
        const int *__restrict__ nrows_dev, int rows_per_chunk, u64 *__restrict__ SP, u64 *__restrict__ AQ,
        const PamState *st, int check_done)
 {
-    if (check_done && st->done) return;
+    if (check_done > 0 && st->done) return; // (check_done < 0: A/B switch, static row chunks)
     constexpr bool WITH_P = MODE != 2, WITH_Q = MODE != 0;
     __shared__ int sh_row[SCAN_MAXROWS];
     __shared__ u32 sh_cp[SCAN_MAXROWS];
@@ -309,6 +312,10 @@ k_scan(const u32 *__restrict__ D, size_t ld, const int *__restrict__ s_row,
     __shared__ int sh_g[SCAN_MAXROWS];
 
     const int n = nrows_dev ? *nrows_dev : nrows;
+    // The grid was sized for the host's upper bound of the row count.  When the real count is only known here, spread it
+    // over ALL row chunks of the grid (>= 8 rows each) instead of leaving most CTAs without work: a small incremental
+    // pass then keeps every SM streaming.
+    if (nrows_dev && check_done >= 0) rows_per_chunk = min(rows_per_chunk, max(8, (((n + (int)gridDim.y - 1) / (int)gridDim.y) + 7) & ~7));
     const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const bool active = col < ld;
     const u32 *base = D + col;
@@ -395,29 +402,31 @@ k_scan(const u32 *__restrict__ D, size_t ld, const int *__restrict__ s_row,
 //     SP[h]      += min(d, dn_new) - min(d, dn_old)
 //     AQ[g_old][h] -= min(d, ds_old) - min(d, dn_old)          AQ[g_new][h] += min(d, ds_new) - min(d, dn_new)
 // in wrap-around 64-bit integer arithmetic (exact), so SP / AQ stay equal to what a full pass would give.
-__global__ void k_diff_count(const u32 *__restrict__ nP, const u32 *__restrict__ nQ, const int *__restrict__ nG,
-                             const u32 *__restrict__ oP, const u32 *__restrict__ oQ, const int *__restrict__ oG, int nls,
-                             int k, int *hist2, const PamState *st)
-{
-    if (st->done) return;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nls && (nP[t] != oP[t] || nQ[t] != oQ[t] || nG[t] != oG[t])) atomicAdd(&hist2[oG[t] * k + nG[t]], 1);
-}
-
 __global__ void k_prefix2(int *hist2, int k2, int *total, const PamState *st, u64 *prof_dev, int m, size_t ld)
 {
     if (st->done) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int run = 0;
-        for (int c = 0; c < k2; ++c) {
-            hist2[K2MAX + c] = run;
-            hist2[2 * K2MAX + c] = 0;
-            run += hist2[c];
-        }
-        *total = run;
+    // one warp: exclusive prefix of the k2 <= K2MAX pair-key counts (bases at [K2MAX + c], cursors at [2 K2MAX + c] zeroed)
+    const int lane = threadIdx.x;
+    const int per = (k2 + 31) / 32, b = lane * per, e = min(k2, b + per);
+    int cnt = 0;
+    for (int c = b; c < e; ++c) cnt += hist2[c];
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int run = incl - cnt;
+    for (int c = b; c < e; ++c) {
+        hist2[K2MAX + c] = run;
+        hist2[2 * K2MAX + c] = 0;
+        run += hist2[c];
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) {
+        *total = tot;
         if (prof_dev) { // rows the delta pass is about to rescan
-            atomicAdd((unsigned long long *)prof_dev + 2, (unsigned long long)run * (unsigned long long)m);
-            atomicAdd((unsigned long long *)prof_dev + 3, (unsigned long long)run * (unsigned long long)ld);
+            atomicAdd((unsigned long long *)prof_dev + 2, (unsigned long long)tot * (unsigned long long)m);
+            atomicAdd((unsigned long long *)prof_dev + 3, (unsigned long long)tot * (unsigned long long)ld);
         }
     }
 }
@@ -451,6 +460,8 @@ k_scan_delta(const u32 *__restrict__ D, size_t ld, const int *__restrict__ d_row
     __shared__ int sh_key[SCAN_MAXROWS];
     __shared__ u32 sh_po[SCAN_MAXROWS], sh_qo[SCAN_MAXROWS], sh_pn[SCAN_MAXROWS], sh_qn[SCAN_MAXROWS];
     const int n = *nrows_dev;
+    // (the grid was sized for all owned rows: spread the changed rows over all of its row chunks, see k_scan)
+    rows_per_chunk = min(rows_per_chunk, max(8, (((n + (int)gridDim.y - 1) / (int)gridDim.y) + 7) & ~7));
     const size_t col = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
     const bool active = col < ld;
     const u32 *base = D + col;
@@ -545,9 +556,13 @@ __global__ void k_acc_add(u64 *acc, const u64 *__restrict__ delta, size_t n, con
 
 // nearest / second-nearest medoid of every owned subset row (cstat + the dysma/dysmb refresh of bswap):
 // strict '<' with medoids visited in index (position) order => the lowest-position medoid wins ties.
+// DELTA (incremental SWAP): the previous assignment of every row is kept in o_capP / o_capQ / o_grp and the rows whose
+// (nearest, second nearest) pair changed are counted by their (old group, new group) key in hist2.
+template <bool DELTA>
 __global__ void k_assign(const u32 *__restrict__ D, size_t ld, const int *__restrict__ rows, int nls,
                          const int *__restrict__ med, const int *__restrict__ medpos, int k, u32 *capP, u32 *capQ,
-                         int *grp, int *hist, u64 *td, const PamState *st, int check_done)
+                         int *grp, int *hist, u64 *td, const PamState *st, int check_done,
+                         u32 *o_capP = nullptr, u32 *o_capQ = nullptr, int *o_grp = nullptr, int *hist2 = nullptr)
 {
     if (check_done && st->done) return;
     extern __shared__ int sh[];
@@ -568,6 +583,12 @@ __global__ void k_assign(const u32 *__restrict__ D, size_t ld, const int *__rest
             } else if (d < d2) {
                 d2 = d;
             }
+        }
+        if (DELTA) {
+            const u32 p0 = capP[t], q0 = capQ[t];
+            const int g0 = grp[t];
+            o_capP[t] = p0; o_capQ[t] = q0; o_grp[t] = g0;
+            if (d1 != p0 || d2 != q0 || g != g0) atomicAdd(&hist2[g0 * k + g], 1);
         }
         capP[t] = d1;
         capQ[t] = d2;
@@ -2092,8 +2113,8 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         } else {
             if (s == std::max(k_from, 1)) // the selection kernel leaves AQ0 zeroed for the next step
                 RID_CUDA(cudaMemsetAsync(AQ0, 0, w->ld * sizeof(u64), ctx->stream));
-            RID_TRY((launch_scan<2>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, w->chg_count, 0,
-                                    RID_PROF_SCAN_BUILD)));
+            RID_TRY((launch_scan<2>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, w->chg_count,
+                                    getenv("RID_SCAN_STATIC") ? -1 : 0, RID_PROF_SCAN_BUILD)));
             RID_TRY(rid_allreduce_u64(ctx, AQ0, w->ld));
         }
         // picks the next medoid; for s > 0 it first applies SP -= AQ0 (and clears AQ0 and the changed-row counter)
@@ -2149,8 +2170,9 @@ static int pam_assign(rid_dmat *dm, PamWs *w, int k, int check_done, u64 *acc = 
         LAUNCH(ctx, k_zero, blocks, 256, 0, acc, n, w->hist, 3 * w->kcap, w->state, check_done);
     }
     if (w->nls)
-        LAUNCH(ctx, k_assign, nblk(w->nls, 128), 128, 2 * k * sizeof(int), w->mat, w->ld, w->rows, w->nls,
-               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, acc, w->state, check_done);
+        LAUNCH(ctx, k_assign<false>, nblk(w->nls, 128), 128, 2 * k * sizeof(int), w->mat, w->ld, w->rows, w->nls,
+               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, acc, w->state, check_done, (u32 *)nullptr,
+               (u32 *)nullptr, (int *)nullptr, (int *)nullptr);
     RID_CUDA(cudaGetLastError());
     return RID_OK;
 }
@@ -2173,17 +2195,18 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
 {
     rid_ctx *ctx = dm->ctx;
     const size_t nacc = 4 + (size_t)(1 + k) * w->ld;
-    if (w->nls) {
-        RID_CUDA(cudaMemcpyAsync(w->o_capP, w->capP, (size_t)w->nls * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-        RID_CUDA(cudaMemcpyAsync(w->o_capQ, w->capQ, (size_t)w->nls * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-        RID_CUDA(cudaMemcpyAsync(w->o_grp, w->grp, (size_t)w->nls * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    // one iteration = 7 launches (all early-exit once the local optimum is reached): zero acc2 / key counts; new
+    // assignment (keeps the old one, counts the changed rows by key, TD -> acc2[0]); prefix; scatter; the delta pass; add; select
+    {
+        int blocks = (int)std::min<size_t>((nacc + 255) / 256, (size_t)ctx->sm_count * 8);
+        blocks = std::max(blocks, nblk(3 * w->kcap, 256));
+        LAUNCH(ctx, k_zero, blocks, 256, 0, w->acc2, nacc, w->hist, 3 * w->kcap, w->state, 1, w->hist2, k * k, w->chg_count);
     }
-    RID_TRY(pam_assign(dm, w, k, 1, w->acc2)); // zeroes acc2, new caps / groups, TD -> acc2[0]
-    RID_CUDA(cudaMemsetAsync(w->hist2, 0, (size_t)k * k * sizeof(int), ctx->stream));
-    RID_CUDA(cudaMemsetAsync(w->chg_count, 0, sizeof(int), ctx->stream));
+    if (w->nls)
+        LAUNCH(ctx, k_assign<true>, nblk(w->nls, 128), 128, 2 * k * sizeof(int), w->mat, w->ld, w->rows, w->nls,
+               w->med, w->medpos, k, w->capP, w->capQ, w->grp, w->hist, w->acc2, w->state, 1, w->o_capP, w->o_capQ, w->o_grp,
+               w->hist2);
     if (w->nls) {
-        LAUNCH(ctx, k_diff_count, nblk(w->nls, 256), 256, 0, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ, w->o_grp,
-               w->nls, k, w->hist2, w->state);
         LAUNCH(ctx, k_prefix2, 1, 32, 0, w->hist2, k * k, w->chg_count, w->state,
                ((ctx->prof_on >> RID_PROF_SCAN_DELTA) & 1) ? ctx->prof_dev : (u64 *)nullptr, w->m, w->ld);
         LAUNCH(ctx, k_diff_scatter, nblk(w->nls, 256), 256, 0, w->rows, w->capP, w->capQ, w->grp, w->o_capP, w->o_capQ,
