@@ -1665,62 +1665,85 @@ __device__ __forceinline__ void mma_u8_16832(int (&c)[4], const uint4 &a, u32 b0
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ u32 u4c(const uint4 &v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+__device__ __forceinline__ uint2 ld_stream2(const u32 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 
+// MB = 1: 16 replicates per pass, a lane streams 4 columns (128-bit loads), a CTA of 4 warps owns 128 columns.
+// MB = 2: 32 replicates per pass (two A fragments share every B fragment), a lane streams 2 columns (64-bit loads: the
+//         same 64 accumulator registers), a CTA owns 64 columns -- half the passes over the matrix for 50 replicates.
+template <int MB>
 __global__ void __launch_bounds__(128)
 k_colsum_mma(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chunk /* multiple of 32, <= CM_ROWS */,
-             const unsigned short *__restrict__ mask /* [nrows]: bit b = the row belongs to replicate b of the batch */,
-             u64 *__restrict__ out /* [CSM][ld] */)
+             const void *__restrict__ mask_v /* [nrows] u16 (MB = 1) / u32 (MB = 2): bit b = the row belongs to replicate b */,
+             u64 *__restrict__ out /* [16 MB][ld] */)
 {
-    __shared__ unsigned short sh_m[CM_ROWS];
-    __shared__ uint4 sh_a[CM_ROWS / 32][32]; // A fragment of every 32-row block, by lane
+    constexpr int NC = 4 / MB; // columns per lane
+    __shared__ u32 sh_m[CM_ROWS];
+    __shared__ uint4 sh_a[CM_ROWS / 32][MB][32]; // A fragments of every 32-row block, by lane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const size_t col0 = (size_t)blockIdx.x * 128 + (size_t)warp * 32; // (ld is a multiple of 128: a CTA is all in or all out)
-    const u32 *base = D + col0 + 4 * g;
-    int acc[4][4][4]; // [column of the lane's uint4][byte plane][C fragment]
+    const size_t col0 = (size_t)blockIdx.x * (32 * NC) + (size_t)warp * (8 * NC); // (ld is a multiple of 128)
+    const u32 *base = D + col0 + NC * g;
+    int acc[MB][NC][4][4]; // [replicate block][column of the lane][byte plane][C fragment]
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[c][pl][r] = 0;
+            for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[mb][c][pl][r] = 0;
     for (int chunk = blockIdx.y; (long long)chunk * rows_per_chunk < nrows; chunk += gridDim.y) {
         const int r_begin = chunk * rows_per_chunk;
         const int nr = min(nrows - r_begin, rows_per_chunk);
         const int nb32 = (nr + 31) >> 5;
         __syncthreads();
-        for (int i = threadIdx.x; i < nb32 * 32; i += 128) sh_m[i] = i < nr ? mask[r_begin + i] : (unsigned short)0;
+        for (int i = threadIdx.x; i < nb32 * 32; i += 128)
+            sh_m[i] = i >= nr ? 0u : (MB == 1 ? (u32)reinterpret_cast<const unsigned short *>(mask_v)[r_begin + i]
+                                              : reinterpret_cast<const u32 *>(mask_v)[r_begin + i]);
         __syncthreads();
-        for (int i = threadIdx.x; i < nb32 * 32; i += 128) {
-            const int gg = (i & 31) >> 2, tt = i & 3;
-            const unsigned short *m = sh_m + (i & ~31);
+        for (int i = threadIdx.x; i < nb32 * 32 * MB; i += 128) {
+            const int mb = i / (nb32 * 32), j = i - mb * (nb32 * 32);
+            const int gg = (j & 31) >> 2, tt = j & 3;
+            const u32 *m = sh_m + (j & ~31);
             u32 a[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) { // a0: (replicate gg, rows 4tt..), a1: (gg+8, 4tt..), a2: (gg, 16+4tt..), a3: (gg+8, 16+4tt..)
-                const int rp = gg + ((r & 1) ? 8 : 0), r0 = ((r & 2) ? 16 : 0) + 4 * tt;
+                const int rp = 16 * mb + gg + ((r & 1) ? 8 : 0), r0 = ((r & 2) ? 16 : 0) + 4 * tt;
                 u32 v = 0;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v |= (((u32)m[r0 + e] >> rp) & 1u) << (8 * e);
+                for (int e = 0; e < 4; ++e) v |= ((m[r0 + e] >> rp) & 1u) << (8 * e);
                 a[r] = v;
             }
-            sh_a[i >> 5][i & 31] = make_uint4(a[0], a[1], a[2], a[3]);
+            sh_a[j >> 5][mb][j & 31] = make_uint4(a[0], a[1], a[2], a[3]);
         }
         __syncthreads();
         for (int blk = 0; blk < nb32; ++blk) {
             const int rb = r_begin + blk * 32 + 4 * t;
-            uint4 d[8];
+            u32 d[8][NC];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int row = min(rb + (u < 4 ? u : 12 + u), nrows - 1); // (rows past the end carry mask 0)
-                d[u] = ld_stream(base + (size_t)row * ld);
+                if (MB == 1) {
+                    const uint4 v = ld_stream(base + (size_t)row * ld);
+                    d[u][0] = v.x; d[u][1 % NC] = v.y; d[u][2 % NC] = v.z; d[u][3 % NC] = v.w;
+                } else {
+                    const uint2 v = ld_stream2(base + (size_t)row * ld);
+                    d[u][0] = v.x; d[u][1 % NC] = v.y;
+                }
             }
-            const uint4 a = sh_a[blk][lane];
+            uint4 a[MB];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int mb = 0; mb < MB; ++mb) a[mb] = sh_a[blk][mb][lane];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
                 u32 b0[4], b1[4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) { // rows 4t.. (b0) and 16+4t.. (b1): 4 x 4 byte transpose
-                    const u32 w0 = u4c(d[4 * h], c), w1 = u4c(d[4 * h + 1], c), w2 = u4c(d[4 * h + 2], c), w3 = u4c(d[4 * h + 3], c);
+                    const u32 w0 = d[4 * h][c], w1 = d[4 * h + 1][c], w2 = d[4 * h + 2][c], w3 = d[4 * h + 3][c];
                     const u32 t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
                     const u32 t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
                     u32 *b = h ? b1 : b0;
@@ -1728,20 +1751,24 @@ k_colsum_mma(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chunk
                     b[2] = __byte_perm(t2, t3, 0x5410); b[3] = __byte_perm(t2, t3, 0x7632);
                 }
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl) mma_u8_16832(acc[c][pl], a, b0[pl], b1[pl]);
+                for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) mma_u8_16832(acc[mb][c][pl], a[mb], b0[pl], b1[pl]);
             }
         }
     }
     // C fragment r of lane (g, t): replicate g (+8 if r & 2), MMA column 2t + (r & 1) = the column group whose lanes fed it
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const u64 v = (u64)(u32)acc[c][0][r] + ((u64)(u32)acc[c][1][r] << 8) + ((u64)(u32)acc[c][2][r] << 16) +
-                          ((u64)(u32)acc[c][3][r] << 24);
-            const int rp = g + ((r & 2) ? 8 : 0), n = 2 * t + (r & 1);
-            if (v) red_add_u64(out + (size_t)rp * ld + col0 + 4 * n + c, v);
-        }
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const u64 v = (u64)(u32)acc[mb][c][0][r] + ((u64)(u32)acc[mb][c][1][r] << 8) + ((u64)(u32)acc[mb][c][2][r] << 16) +
+                              ((u64)(u32)acc[mb][c][3][r] << 24);
+                const int rp = 16 * mb + g + ((r & 2) ? 8 : 0), n = 2 * t + (r & 1);
+                if (v) red_add_u64(out + (size_t)rp * ld + col0 + NC * n + c, v);
+            }
 }
 
 // one CTA per replicate: arg min of SP0 over the replicate's cells, ties to the LARGEST position (cand_better_build)
@@ -1772,6 +1799,7 @@ k_first_medoid(const u64 *__restrict__ sp0 /* [.][ld] */, size_t ld, const int *
 __global__ void k_first_masks(const int *__restrict__ cat, const long long *__restrict__ off, int row0, int nloc, int csb,
                               unsigned int *__restrict__ mask32)
 {
+    // (csb > 16: one 32-bit mask per row)
     const int b = blockIdx.y;
     const int *cells = cat + off[b];
     const int len = (int)(off[b + 1] - off[b]);
@@ -1779,7 +1807,8 @@ __global__ void k_first_masks(const int *__restrict__ cat, const long long *__re
         const int r = cells[p] - row0;
         if (r >= 0 && r < nloc) {
             const size_t e = (size_t)(b / csb) * nloc + r;
-            atomicOr(&mask32[e >> 1], (1u << (b % csb)) << ((e & 1) * 16));
+            if (csb > 16) atomicOr(&mask32[e], 1u << (b % csb));
+            else atomicOr(&mask32[e >> 1], (1u << (b % csb)) << ((e & 1) * 16));
         }
     }
 }
@@ -2866,6 +2895,10 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
         RID_TRY(replica_begin(dm, &R));
         if (R.active) RID_TRY(replica_need_whole(R.full));
     }
+    // RID_REPLICA_EARLY=1: the copy engines start pulling the peers' row blocks now, under the (cooperative) sweep
+    if (!R.active && getenv("RID_REPLICA_EARLY") && atoi(getenv("RID_REPLICA_EARLY")) && ctx->world > 1 && dm->full && dm->peers_ok &&
+        !getenv("RID_NO_REPLICA"))
+        RID_TRY(rid_replica_start(dm));
     replica_local(&R, true);
     int rc = gap_sweep_on(R.active ? R.full : dm, subset, m, Kmax, logW, R.active ? R.saved_world : 1,
                           R.active ? R.saved_rank : 0);
@@ -2892,14 +2925,14 @@ extern "C" int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, d
 // (k_first_medoid).  Runs on the sharded matrix with the real world size (before any switch to a replica).
 // The row masks of all batches are built from the samples on the device (k_first_masks).
 struct FirstMasks {
-    int csb = CSM;              // replicates per pass: CSM on the tensor cores, CSB with the IMAD kernel (RID_COLSUM_IMAD=1)
+    int csb = 2 * CSM;          // replicates per pass: 32 (or 16: RID_COLSUM_MB=1) on the tensor cores, CSB with the IMAD kernel (RID_COLSUM_IMAD=1)
     int nbatch = 0;
     std::vector<int> rep;       // [nbatch][csb] replicate of every slot (padding repeats the batch's last one)
     std::vector<long long> off; // [B + 1]
 };
 static void boot_first_tables(FirstMasks *M, const int *sample_len, int B)
 {
-    const int csb = M->csb = getenv("RID_COLSUM_IMAD") ? CSB : CSM;
+    const int csb = M->csb = getenv("RID_COLSUM_IMAD") ? CSB : ((getenv("RID_COLSUM_MB") && atoi(getenv("RID_COLSUM_MB")) == 1) ? CSM : 2 * CSM);
     M->nbatch = (B + csb - 1) / csb;
     M->off.assign(B + 1, 0);
     for (int b = 0; b < B; ++b) M->off[b + 1] = M->off[b] + sample_len[b];
@@ -2922,7 +2955,7 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
     RID_CUDA(cudaMemcpyAsync(d_off, M.off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(d_rep, M.rep.data(), M.rep.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (nloc) {
-        const size_t mask_bytes = (((size_t)M.nbatch * nloc * sizeof(unsigned short)) + 3) & ~(size_t)3;
+        const size_t mask_bytes = csb > 16 ? (size_t)M.nbatch * nloc * sizeof(u32) : ((((size_t)M.nbatch * nloc * sizeof(unsigned short)) + 3) & ~(size_t)3);
         RID_CUDA(cudaMemsetAsync(d_mask, 0, mask_bytes, ctx->stream));
         dim3 gm(std::max(1, std::min(64, nblk(dm->N, 256))), B);
         LAUNCH(ctx, k_first_masks, gm, 256, 0, d_cat, d_off, dm->row0, nloc, csb, reinterpret_cast<unsigned int *>(d_mask));
@@ -2931,8 +2964,9 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
     int want_y = std::max(1, (ctx->sm_count * 16 + strips - 1) / strips);
     int rpc = std::min(std::max((((nloc + want_y - 1) / want_y) + 7) & ~7, 8), SCAN_MAXROWS);
     dim3 grid(strips, std::max(1, std::min((nloc + rpc - 1) / rpc, want_y * 2)));
-    // tensor-core kernel: a CTA owns 128 columns and walks row chunks of <= CM_ROWS rows (multiples of 32)
-    const int strips_m = (int)(dm->ld / 128);
+    // tensor-core kernel: a CTA owns 128 (16 replicates per pass) or 64 (32 per pass) columns and walks row chunks of
+    // <= CM_ROWS rows (multiples of 32)
+    const int strips_m = (int)(dm->ld / (csb > 16 ? 64 : 128));
     const int want_ym = std::max(1, (ctx->sm_count * 16 + strips_m - 1) / strips_m);
     const int rpc_m = std::min(std::max((((nloc + want_ym - 1) / want_ym) + 31) & ~31, 32), CM_ROWS);
     dim3 grid_m(strips_m, std::max(1, std::min((nloc + rpc_m - 1) / rpc_m, want_ym * 2)));
@@ -2943,7 +2977,11 @@ static int boot_first_medoids(rid_dmat *dm, const FirstMasks &M, const int *samp
             cudaEvent_t pe = rid_prof_begin(ctx, RID_PROF_SCAN_BUILD);
             auto k8 = k_colsum_batch<8>;
             auto k2 = k_colsum_batch<2>;
-            if (csb == CSM) LAUNCH(ctx, k_colsum_mma, grid_m, 128, 0, dm->D, dm->ld, nloc, rpc_m, d_mask + (size_t)t * nloc, d_sp0);
+            if (csb == 2 * CSM)
+                LAUNCH(ctx, k_colsum_mma<2>, grid_m, 128, 0, dm->D, dm->ld, nloc, rpc_m,
+                       (const void *)(reinterpret_cast<const u32 *>(d_mask) + (size_t)t * nloc), d_sp0);
+            else if (csb == CSM)
+                LAUNCH(ctx, k_colsum_mma<1>, grid_m, 128, 0, dm->D, dm->ld, nloc, rpc_m, (const void *)(d_mask + (size_t)t * nloc), d_sp0);
             else if (dm->bits <= 28) LAUNCH(ctx, k8, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
             else LAUNCH(ctx, k2, grid, SCAN_THREADS, 0, dm->D, dm->ld, nloc, rpc, d_mask + (size_t)t * nloc, d_sp0);
             rid_prof_end(ctx, pe, RID_PROF_SCAN_BUILD, (double)nloc * (double)dm->N * 4.0, (double)nloc * (double)dm->ld * 4.0);
@@ -3007,7 +3045,7 @@ extern "C" int rid_clusterboot(rid_dmat *dm, int k, const int *samples, const in
         const size_t o_first = 0, o_off = o_first + al((size_t)B * sizeof(int2)), o_rep = o_off + al((size_t)(B + 1) * sizeof(long long)),
                      o_sp0 = o_rep + al((size_t)std::max(fmasks.nbatch, 1) * fmasks.csb * sizeof(int)),
                      o_mask = o_sp0 + al((size_t)fmasks.csb * dm->ld * sizeof(u64)),
-                     o_cat = o_mask + al((size_t)std::max(fmasks.nbatch, 1) * std::max(nloc, 1) * sizeof(unsigned short));
+                     o_cat = o_mask + al((size_t)std::max(fmasks.nbatch, 1) * std::max(nloc, 1) * sizeof(u32));
         first_bytes = std::max<size_t>(o_cat + al((size_t)std::max<long long>(tot, 1) * sizeof(int)), (size_t)256 << 10);
         if (rid_pool_alloc(ctx, (void **)&first_buf, first_bytes) != cudaSuccess) { cudaGetLastError(); first_buf = nullptr; }
         int all_ok = 0;

@@ -14,7 +14,7 @@ dm = ctx.dist((x.data_ptr(), G, N), "pearson")
 dm.gap_sweep(K)
 ref = None
 variants = [("warm", {}), ("default", {}),
-            ("ahead20", {"RID_BOOT_AHEAD": "20"}), ("default", {}), ("static", {"RID_SCAN_STATIC": "1"}), ("default", {}), ("static", {"RID_SCAN_STATIC": "1"})] + \
+            ("mb1", {"RID_COLSUM_MB": "1"}), ("default", {}), ("mb1", {"RID_COLSUM_MB": "1"}), ("imad", {"RID_COLSUM_IMAD": "1"})] + \
            [(a, b) for a, b in (os.environ.get("AB_EXTRA") and eval(os.environ["AB_EXTRA"]) or [])]
 for name, env in variants:
     for k_, v_ in env.items(): os.environ[k_] = v_

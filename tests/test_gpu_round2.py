@@ -414,12 +414,12 @@ def test_clusterboot_first_pick_batched_and_fused(ctx, oracle, metric, monkeypat
     """rid_clusterboot takes BUILD's step-0 column sums of all replicates in batched passes over the resident matrix
     (10 replicates per pass), so every replicate's first medoid is known before its compaction, which then accumulates
     the second step's sums directly (no full rescan for that step).  Identical to the oracle and to the plain flow
-    (RID_NO_FIRST=1); 20 replicates = two batches; resamples large enough for the compact symmetric copy; the euclidean
+    (RID_NO_FIRST=1); 36 replicates = two batches (or more); resamples large enough for the compact symmetric copy; the euclidean
     case runs on the 31-bit grid (all four byte planes of the tensor-core column sums in use)."""
     from raceid3_stemid2_package_b200.scseq import bootstrap_samples
     from raceid3_stemid2_package_b200.synth import synth_features_numpy
 
-    N, B, k = 1500, 20, 6
+    N, B, k = 1500, 36, 6
     if metric == "pearson":
         x, _ = synth_features_numpy(N, 180, k, 33)
         x[1200] = x[3]  # duplicated cells: tied column sums
@@ -433,9 +433,10 @@ def test_clusterboot_first_pick_batched_and_fused(ctx, oracle, metric, monkeypat
     samples = bootstrap_samples(N, B, 17000)
     assert min(len(s) for s in samples) ** 2 * 4 >= 1 << 20
     ro = oracle.clusterboot(Dg, k, samples)
-    # default: the column sums of 16 replicates per pass on the tensor cores (k_colsum_mma: u8 byte planes, exact);
-    # RID_COLSUM_IMAD=1: the 10-per-pass multiply-add kernel; RID_NO_FIRST=1: no batched first picks at all
-    for env in (None, "RID_COLSUM_IMAD", "RID_NO_FIRST"):
+    # default: the column sums of 32 replicates per pass on the tensor cores (k_colsum_mma<2>: u8 byte planes, exact);
+    # RID_COLSUM_MB=1: 16 per pass; RID_COLSUM_IMAD=1: the 10-per-pass multiply-add kernel; RID_NO_FIRST=1: no batched
+    # first picks at all
+    for env in (None, "RID_COLSUM_MB", "RID_COLSUM_IMAD", "RID_NO_FIRST"):
         if env:
             monkeypatch.setenv(env, "1")
         r = dm.clusterboot(k, samples)
