@@ -566,7 +566,7 @@ def main():
         sc_ = {f: sum(prof[k][f] for k in ("scan_swap", "scan_build", "scan_group")) for f in ("launches", "ms", "work", "traffic")}
         if sc_["launches"] and sc_["ms"] > 0:
             ach = sc_["work"] / (sc_["ms"] * 1e-3) / 1e9
-            roofs.append({"bound": "hbm", "kernel": "k_scan<MODE> / k_wk_batch (PAM streaming pass: BUILD steps, SWAP scan, grouped column sums)",
+            roofs.append({"bound": "hbm", "kernel": "k_scan<MODE> / k_colsum_mma (PAM streaming passes: BUILD steps incl. the batched first picks, SWAP scan, grouped column sums of the sweep's W.k)",
                           "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                           "traffic": traffic_of("k_scan", sc_["work"] / sc_["launches"]), "peak_source": hbm_src,
                           "read_only_stream_gbs_measured_here": read_peak, "launches": sc_["launches"],

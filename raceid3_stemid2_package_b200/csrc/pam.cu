@@ -1721,39 +1721,49 @@ k_colsum_mma(const u32 *__restrict__ D, size_t ld, int nrows, int rows_per_chunk
             sh_a[j >> 5][mb][j & 31] = make_uint4(a[0], a[1], a[2], a[3]);
         }
         __syncthreads();
-        for (int blk = 0; blk < nb32; ++blk) {
-            const int rb = r_begin + blk * 32 + 4 * t;
-            u32 d[8][NC];
+        // MB = 2 streams 64-bit words: two 32-row blocks are loaded before the first MMA so that as many bytes are in flight
+        // per lane as with the 128-bit loads of MB = 1
+        constexpr int NBLK = MB;
+        for (int blk0 = 0; blk0 < nb32; blk0 += NBLK) {
+            u32 d[NBLK][8][NC];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int row = min(rb + (u < 4 ? u : 12 + u), nrows - 1); // (rows past the end carry mask 0)
-                if (MB == 1) {
-                    const uint4 v = ld_stream(base + (size_t)row * ld);
-                    d[u][0] = v.x; d[u][1 % NC] = v.y; d[u][2 % NC] = v.z; d[u][3 % NC] = v.w;
-                } else {
-                    const uint2 v = ld_stream2(base + (size_t)row * ld);
-                    d[u][0] = v.x; d[u][1 % NC] = v.y;
+            for (int bb = 0; bb < NBLK; ++bb) {
+                const int rb = r_begin + (blk0 + bb) * 32 + 4 * t;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int row = min(rb + (u < 4 ? u : 12 + u), nrows - 1); // (rows past the end carry mask 0)
+                    if (MB == 1) {
+                        const uint4 v = ld_stream(base + (size_t)row * ld);
+                        d[bb][u][0] = v.x; d[bb][u][1 % NC] = v.y; d[bb][u][2 % NC] = v.z; d[bb][u][3 % NC] = v.w;
+                    } else {
+                        const uint2 v = ld_stream2(base + (size_t)row * ld);
+                        d[bb][u][0] = v.x; d[bb][u][1 % NC] = v.y;
+                    }
                 }
             }
-            uint4 a[MB];
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) a[mb] = sh_a[blk][mb][lane];
+            for (int bb = 0; bb < NBLK; ++bb) {
+                if (blk0 + bb >= nb32) break; // (its loads were clamped to valid rows)
+                uint4 a[MB];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                u32 b0[4], b1[4];
+                for (int mb = 0; mb < MB; ++mb) a[mb] = sh_a[blk0 + bb][mb][lane];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) { // rows 4t.. (b0) and 16+4t.. (b1): 4 x 4 byte transpose
-                    const u32 w0 = d[4 * h][c], w1 = d[4 * h + 1][c], w2 = d[4 * h + 2][c], w3 = d[4 * h + 3][c];
-                    const u32 t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
-                    const u32 t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
-                    u32 *b = h ? b1 : b0;
-                    b[0] = __byte_perm(t0, t1, 0x5410); b[1] = __byte_perm(t0, t1, 0x7632);
-                    b[2] = __byte_perm(t2, t3, 0x5410); b[3] = __byte_perm(t2, t3, 0x7632);
+                for (int c = 0; c < NC; ++c) {
+                    u32 b0[4], b1[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { // rows 4t.. (b0) and 16+4t.. (b1): 4 x 4 byte transpose
+                        const u32 w0 = d[bb][4 * h][c], w1 = d[bb][4 * h + 1][c], w2 = d[bb][4 * h + 2][c], w3 = d[bb][4 * h + 3][c];
+                        const u32 t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                        const u32 t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                        u32 *b = h ? b1 : b0;
+                        b[0] = __byte_perm(t0, t1, 0x5410); b[1] = __byte_perm(t0, t1, 0x7632);
+                        b[2] = __byte_perm(t2, t3, 0x5410); b[3] = __byte_perm(t2, t3, 0x7632);
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl) mma_u8_16832(acc[mb][c][pl], a[mb], b0[pl], b1[pl]);
                 }
-#pragma unroll
-                for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) mma_u8_16832(acc[mb][c][pl], a[mb], b0[pl], b1[pl]);
             }
         }
     }

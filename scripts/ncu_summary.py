@@ -101,5 +101,56 @@ def ratios(path, out):
     print(json.dumps(res, indent=1))
 
 
+RAW_KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def rawcsv(path, out):
+    """The wide CSV of `ncu -i x.ncu-rep --page raw --csv` (made on the GPU box when the report itself is too large to bring
+    back) -> the metrics the roofline argument needs, per captured launch; launches under 0.05 ms are left out."""
+    rows = list(csv.reader(open(path, errors="replace")))
+    hdr, units = rows[0], rows[1]
+    ik = hdr.index("Kernel Name")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+    tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}
+    seen = defaultdict(int)
+    with open(out, "w") as f:
+        f.write(f"# selected metrics from {path} (ncu --set full --clock-control none --kernel-name-base demangled)\n")
+        for r in rows[2:]:
+            if len(r) <= ik:
+                continue
+            name = re.sub(r"\(.*", "", r[ik]).strip()
+            it = hdr.index("gpu__time_duration.sum")
+            try:
+                ms = float(r[it].replace(",", "")) * tscale.get(units[it], 1e-6)
+            except ValueError:
+                ms = 0.0
+            seen[name] += 1
+            if ms < 0.05:
+                continue
+            f.write(f"== {name}  (launch #{seen[name]})\n")
+            tot = 0.0
+            for k in RAW_KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"   {k:100s} {r[i]:>14s} {units[i]}\n")
+                    if k.startswith("dram__bytes"):
+                        try:
+                            tot += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+                        except ValueError:
+                            pass
+            if ms > 0 and tot > 0:
+                f.write(f"   {'-> DRAM bytes / duration':100s} {tot / 1e9 / ms:14.2f} TB/s (GB per ms)\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep, "ratios": ratios}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "rep": rep, "ratios": ratios, "rawcsv": rawcsv}[sys.argv[1]](sys.argv[2], sys.argv[3])
