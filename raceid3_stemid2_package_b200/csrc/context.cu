@@ -449,7 +449,8 @@ static int ensure_scratch(rid_ctx *ctx)
 {
     if (!ctx->scratch) {
         RID_CUDA(cudaMalloc(&ctx->scratch, 4096));
-        RID_CUDA(cudaMemset(ctx->scratch, 0, 4096));
+        // (on the library's stream: it is not ordered against the legacy default stream)
+        RID_CUDA(cudaMemsetAsync(ctx->scratch, 0, 4096, ctx->stream));
     }
     return RID_OK;
 }
