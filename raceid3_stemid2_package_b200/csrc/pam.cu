@@ -26,7 +26,7 @@
 #include "common.cuh"
 
 // ----------------------------------------------------------------------------------------------------------
-#define K2MAX 4096   // incremental SWAP keys rows by (old group, new group): k*k <= K2MAX, i.e. k <= 64
+#define K2MAX 16384  // incremental SWAP keys rows by (old group, new group): k*k <= K2MAX, i.e. k <= 128
 
 struct PamState {
     u64 td;       // total deviation at the last SWAP decision (fixed point)
@@ -2701,13 +2701,15 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     AtomState *d_as = nullptr;
     const size_t atom_bytes = (size_t)m * sizeof(int), table_bytes = (size_t)a_cap * Kmax * sizeof(int);
     if (atoms) {
+        int mine = 1, all = 0;
         if (rid_tmp_alloc(ctx, &d_atom, atom_bytes) != cudaSuccess || rid_tmp_alloc(ctx, &d_table, table_bytes) != cudaSuccess ||
             rid_tmp_alloc(ctx, &d_as, sizeof(AtomState)) != cudaSuccess) {
             cudaGetLastError();
-            atoms = false;
-        } else {
-            LAUNCH(ctx, k_atom_init, nblk(m, 256), 256, 0, d_atom, m, d_as);
+            mine = 0;
         }
+        RID_TRY(rid_agree_all(ctx, mine, &all)); // (the two W.k routes use different collectives: every rank takes the same one)
+        atoms = all != 0;
+        if (atoms) LAUNCH(ctx, k_atom_init, nblk(m, 256), 256, 0, d_atom, m, d_as);
     }
     // state of the BUILD medoids of the last k this rank handled (see sweep_chain_step)
     const bool chain = !getenv("RID_SWAP_FULL") && !getenv("RID_SWEEP_FULL");
@@ -2786,10 +2788,13 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
         unsigned char *d_al = nullptr;
         const size_t aq_bytes = (size_t)A * w->ld * sizeof(u64), t_bytes = (size_t)nq * Kmax * sizeof(u64),
                      c_bytes = (size_t)nq * Kmax * sizeof(int), h_bytes = (size_t)A * sizeof(int), al_bytes = (size_t)nq * A;
-        if (rc == RID_OK && !as.overflow && A >= 1 &&
-            rid_tmp_alloc(ctx, &d_AQ, aq_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_T, t_bytes) == cudaSuccess &&
-            rid_tmp_alloc(ctx, &d_cnt, c_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_hist, h_bytes) == cudaSuccess &&
-            rid_tmp_alloc(ctx, &d_al, al_bytes) == cudaSuccess) {
+        int mine = rc == RID_OK && !as.overflow && A >= 1 &&
+                   rid_tmp_alloc(ctx, &d_AQ, aq_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_T, t_bytes) == cudaSuccess &&
+                   rid_tmp_alloc(ctx, &d_cnt, c_bytes) == cudaSuccess && rid_tmp_alloc(ctx, &d_hist, h_bytes) == cudaSuccess &&
+                   rid_tmp_alloc(ctx, &d_al, al_bytes) == cudaSuccess;
+        int all = 0;
+        if (rc == RID_OK) rc = rid_agree_all(ctx, mine, &all);
+        if (rc == RID_OK && all) {
             cudaMemsetAsync(d_AQ, 0, aq_bytes, ctx->stream);
             cudaMemsetAsync(d_T, 0, t_bytes, ctx->stream);
             cudaMemsetAsync(d_cnt, 0, c_bytes, ctx->stream);

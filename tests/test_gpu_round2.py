@@ -560,3 +560,35 @@ def test_sweep_wk_from_atoms_equals_batched_passes(ctx, oracle, metric, monkeypa
         assert np.array_equal(lw_atoms, lw_batch) and np.array_equal(lw_atoms, lw_over)
         assert np.max(np.abs(lw_atoms - ref)) < 1e-12
     dm.free()
+
+
+def test_many_clusters_keep_the_incremental_paths(ctx, oracle, monkeypatch):
+    """k = 70 and k = 100 (> 64: round 1 fell back to full rescans there): incremental SWAP keyed by (old, new) group
+    pairs (k^2 <= 16 384 keys) and the enqueue-only bootstrap against the oracle on data without cluster structure (SWAP
+    iterates); the chained sweep with the atoms pass against the plain one (full scans, batched W.k) up to K.max = 72."""
+    from raceid3_stemid2_package_b200.scseq import bootstrap_samples
+
+    rng = np.random.default_rng(21)
+    N = 1000
+    x = rng.gamma(2.0, 1.0, (N, 40)) + 0.1
+    dm = ctx.dist_cellmajor(x, "pearson")
+    Dg = dm.as_matrix()
+    r = dm.pam(70)
+    o = oracle.pam(Dg, 70)
+    assert np.array_equal(r["id_med"], o["id_med"]) and np.array_equal(r["clustering"], o["clustering"])
+    assert r["n_swaps"] == o["n_swaps"] and o["n_swaps"] >= 3
+    sub = rng.permutation(N)[:600].astype(np.int32)
+    r = dm.pam(100, subset=sub)
+    o = oracle.pam(Dg[np.ix_(sub, sub)], 100)
+    assert np.array_equal(r["id_med"], o["id_med"]) and np.array_equal(r["clustering"], o["clustering"])
+    assert r["n_swaps"] == o["n_swaps"]
+    samples = bootstrap_samples(N, 2, 17000)
+    r = dm.clusterboot(70, samples)
+    o = oracle.clusterboot(Dg, 70, samples)
+    assert np.array_equal(r["partition"], o["partition"]) and np.array_equal(r["bootresult"], o["bootresult"])
+    lw = dm.gap_sweep(72)
+    for v in ("RID_SWEEP_FULL", "RID_SWAP_FULL", "RID_WK_BATCH"):
+        monkeypatch.setenv(v, "1")
+    lw_plain = dm.gap_sweep(72)
+    assert np.array_equal(lw, lw_plain)
+    dm.free()
