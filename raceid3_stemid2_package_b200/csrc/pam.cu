@@ -693,8 +693,9 @@ template <bool BUILD>
 __global__ void __launch_bounds__(256)
 k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
          u64 *acc, size_t ld, int k, int *med, int *medpos, unsigned char *is_med,
-         Cand *blockbest, PamState *st, int check_done, u64 *sp_sub, int *zero_cnt, u64 *prof_dev)
+         Cand *blockbest, PamState *st, int check_done, u64 *sp_sub, int *zero_cnt, u64 *prof_dev, int *order_out = nullptr)
 {
+    // order_out (BUILD, k-sweep): only report the pick -- order_out[k] = its column -- and leave the medoid tables alone
     // sp_sub (incremental BUILD): SP[h] -= sp_sub[h] and sp_sub[h] = 0 on the way (every subset column is visited once);
     // zero_cnt: a counter the next kernel fills again
     if (check_done && st->done) return;
@@ -759,7 +760,9 @@ k_select(const int *__restrict__ subset, int m, const unsigned char *is_med_c,
             *zero_cnt = 0;
         }
         u64 td = acc[0];
-        if (BUILD) {
+        if (BUILD && order_out) {
+            order_out[k] = subset[c.p];
+        } else if (BUILD) {
             int h = subset[c.p];
             int s = st->nmed;
             med[s] = h;
@@ -2159,7 +2162,7 @@ static int pam_build(rid_dmat *dm, PamWs *w, int k_from, int k_to)
         // picks the next medoid; for s > 0 it first applies SP -= AQ0 (and clears AQ0 and the changed-row counter)
         LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, s, w->med, w->medpos,
                w->is_med, w->blockbest, w->state, 0, (s > 0 && !(have_first && s == 1)) ? AQ0 : (u64 *)nullptr, w->chg_count,
-               ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr);
+               ((ctx->prof_on >> RID_PROF_SCAN_BUILD) & 1) ? ctx->prof_dev : (u64 *)nullptr, (int *)nullptr);
         if (lazy && s == 1) // SP is exact for the caps before this pick: the gains it implies bound every later gain
             LAUNCH(ctx, k_lazy_init, 1, 1024, 0, SP, w->capP, w->m, w->lz_ub, w->lz_stamp, w->lz_chg, w->lz_thr);
         if (w->nls)
@@ -2279,7 +2282,7 @@ static int pam_swap_delta_iteration(rid_dmat *dm, PamWs *w, int k, int *n_delta,
     if (do_select) {
         auto sel_swap = k_select<false>;
         LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-               w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
+               w->is_med, w->blockbest, w->state, 1, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr, (int *)nullptr);
     }
     RID_CUDA(cudaGetLastError());
     return RID_OK;
@@ -2317,7 +2320,7 @@ static int pam_swap_enqueue(rid_dmat *dm, PamWs *w, int k, int ahead, int *n_del
     RID_TRY((launch_scan<1>(dm, w, w->s_row, w->s_capP, w->s_capQ, w->s_grp, w->nls, nullptr, 0, RID_PROF_SCAN_SWAP)));
     auto sel_swap = k_select<false>;
     LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr, (int *)nullptr);
     RID_CUDA(cudaGetLastError());
     for (int i = 0; i < ahead; ++i) RID_TRY(pam_swap_delta_iteration(dm, w, k, n_delta));
     return RID_OK;
@@ -2356,7 +2359,7 @@ static int pam_swap(rid_dmat *dm, PamWs *w, int k, PamState *h_state, bool resum
                 RID_TRY(rid_allreduce_u64(ctx, w->acc, 4 + (size_t)(1 + k) * w->ld));
                 auto sel_swap = k_select<false>;
                 LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k,
-                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
+                       w->med, w->medpos, w->is_med, w->blockbest, w->state, chk, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr, (int *)nullptr);
                 RID_CUDA(cudaGetLastError());
             }
             // every later iteration only rescans the rows whose (nearest, second nearest) pair changed
@@ -2611,7 +2614,7 @@ struct SweepChain {
 // SWAP(k) of the sweep starts from the first k BUILD picks.  Their accumulators and assignment are kept from the previous
 // k of this rank and moved to the new medoid set by ONE delta pass over the rows whose (nearest, second nearest) pair
 // changes when the extra medoids are added, instead of a full scan per k.  Medoids must already be installed.
-static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamState *hs)
+static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamState *hs, int *next_pick = nullptr)
 {
     rid_ctx *ctx = dm->ctx;
     const size_t nl = (size_t)std::max(w->nls, 1);
@@ -2635,9 +2638,16 @@ static int sweep_chain_step(rid_dmat *dm, PamWs *w, int k, SweepChain &B, PamSta
     RID_CUDA(cudaMemcpyAsync(B.grp, w->grp, nl * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     RID_CUDA(cudaMemcpyAsync(B.acc, w->acc, nacc * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
     B.chain_k = k;
+    if (next_pick) {
+        // SP of the first k BUILD picks is exactly what BUILD's next step selects from (gain(h) = TD - SP[h]): the chain
+        // makes BUILD's own incremental passes redundant.  next_pick[k] = column of pick k + 1 (medoid tables untouched).
+        auto sel_build = k_select<true>;
+        LAUNCH(ctx, sel_build, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
+               w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr, next_pick);
+    }
     auto sel_swap = k_select<false>;
     LAUNCH(ctx, sel_swap, nblk(w->m, 256), 256, 0, w->subset, w->m, w->is_med, w->acc, w->ld, k, w->med, w->medpos,
-           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr);
+           w->is_med, w->blockbest, w->state, 0, (u64 *)nullptr, (int *)nullptr, (u64 *)nullptr, (int *)nullptr);
     RID_CUDA(cudaGetLastError());
     return pam_swap(dm, w, k, hs, true);
 }
@@ -2666,13 +2676,31 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
     RID_TRY(ws_get(dm, Kmax, &w));
     RID_TRY(pam_set_subset(dm, w, subset, m, true));
     RID_TRY(pam_begin(dm, w));
-    RID_TRY(pam_build(dm, w, 0, Kmax));
-    std::vector<int> order(Kmax);
-    RID_CUDA(cudaMemcpyAsync(order.data(), w->med, (size_t)Kmax * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    RID_CUDA(cudaStreamSynchronize(ctx->stream));
+    // state of the BUILD medoids of the last k this rank handled (see sweep_chain_step)
+    const bool chain = !getenv("RID_SWAP_FULL") && !getenv("RID_SWEEP_FULL");
+    SweepChain B;
+    char *b_buf = nullptr;
+    const size_t b_nl = (size_t)std::max(w->nls, 1);
+    const size_t b_nacc = 4 + (size_t)(1 + Kmax) * w->ld;
+    const size_t b_bytes = std::max<size_t>(((b_nacc * sizeof(u64) + 255) & ~(size_t)255) + 3 * ((b_nl * 4 + 255) & ~(size_t)255),
+                                            (size_t)256 << 10);
+    {
+        int mine = chain && rid_pool_alloc(ctx, (void **)&b_buf, b_bytes) == cudaSuccess, all = 0;
+        if (!mine) { cudaGetLastError(); b_buf = nullptr; }
+        RID_TRY(rid_agree_all(ctx, mine, &all)); // (chained and plain SWAP(k) use different collectives)
+        if (!all && b_buf) { rid_pool_free(ctx, b_buf, b_bytes); b_buf = nullptr; }
+        if (b_buf) {
+            char *p = b_buf;
+            carve(p, B.acc, b_nacc); carve(p, B.capP, b_nl); carve(p, B.capQ, b_nl); carve(p, B.grp, b_nl);
+        }
+    }
+    // With the chain, BUILD only makes its first two picks here: pick k + 1 is selected from the chain's sums of the
+    // first k picks (sweep_chain_step), which are the sums BUILD's own incremental pass would produce.
+    const bool interleave = b_buf && nshare == 1 && Kmax >= 3 && Kmax * Kmax <= K2MAX && !getenv("RID_SWEEP_BUILD_FIRST");
+    RID_TRY(pam_build(dm, w, 0, interleave ? 2 : Kmax));
     int *d_order = nullptr;
     RID_CUDA(rid_tmp_alloc(ctx, &d_order, (size_t)Kmax * sizeof(int)));
-    RID_CUDA(cudaMemcpyAsync(d_order, order.data(), (size_t)Kmax * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    RID_CUDA(cudaMemcpyAsync(d_order, w->med, (size_t)(interleave ? 2 : Kmax) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     int rc = RID_OK;
     // Labels of every k this rank owns are kept by column (bytes); W.k is then evaluated for WB values of k per pass
     // over the matrix instead of one pass per k.
@@ -2711,21 +2739,6 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
         atoms = all != 0;
         if (atoms) LAUNCH(ctx, k_atom_init, nblk(m, 256), 256, 0, d_atom, m, d_as);
     }
-    // state of the BUILD medoids of the last k this rank handled (see sweep_chain_step)
-    const bool chain = !getenv("RID_SWAP_FULL") && !getenv("RID_SWEEP_FULL");
-    SweepChain B;
-    char *b_buf = nullptr;
-    const size_t b_nl = (size_t)std::max(w->nls, 1);
-    const size_t b_nacc = 4 + (size_t)(1 + Kmax) * w->ld;
-    const size_t b_bytes = std::max<size_t>(((b_nacc * sizeof(u64) + 255) & ~(size_t)255) + 3 * ((b_nl * 4 + 255) & ~(size_t)255),
-                                            (size_t)256 << 10);
-    if (chain && rid_pool_alloc(ctx, (void **)&b_buf, b_bytes) == cudaSuccess) {
-        char *p = b_buf;
-        carve(p, B.acc, b_nacc); carve(p, B.capP, b_nl); carve(p, B.capQ, b_nl); carve(p, B.grp, b_nl);
-    } else {
-        cudaGetLastError();
-        b_buf = nullptr;
-    }
     for (int k = 1; k <= Kmax && rc == RID_OK; ++k) {
         logW[k - 1] = 0.0;
         if ((k - 1) % nshare != myshare) continue; // another rank's k
@@ -2743,7 +2756,7 @@ static int gap_sweep_on(rid_dmat *dm, const int *subset, int m, int Kmax, double
                 B.chain_k = 0;
                 rc = pam_swap(dm, w, k, &hs);
             } else {
-                rc = sweep_chain_step(dm, w, k, B, &hs);
+                rc = sweep_chain_step(dm, w, k, B, &hs, (interleave && k < Kmax) ? d_order : (int *)nullptr);
             }
             std::vector<int> slot, h_medpos(k);
             const bool memo = rc == RID_OK && subset == nullptr && nshare == 1 && !dm->parent && !getenv("RID_NO_MEMO");

@@ -19,6 +19,9 @@ for rep in range(2):
     s0 = ctx.swaps
     ctx.profile(True); lw = dm.gap_sweep(K); show(f"sweep   swaps {ctx.swaps - s0:4d}"); ctx.profile(False)
     t0 = time.perf_counter(); lw = dm.gap_sweep(K); print(f"sweep unprofiled dev {ctx.last_ms:.1f} wall {(time.perf_counter()-t0)*1e3:.1f}")
+    os.environ["RID_SWEEP_BUILD_FIRST"] = "1"
+    t0 = time.perf_counter(); lw2 = dm.gap_sweep(K); print(f"sweep BUILD-first unprofiled dev {ctx.last_ms:.1f} wall {(time.perf_counter()-t0)*1e3:.1f}", np.array_equal(lw, lw2))
+    os.environ.pop("RID_SWEEP_BUILD_FIRST")
     s0 = ctx.swaps
     ctx.profile(True); r = dm.clusterboot(K, samples); show(f"boot    swaps {ctx.swaps - s0:4d}"); ctx.profile(False)
     r = dm.clusterboot(K, samples); print(f"boot unprofiled dev {ctx.last_ms:.1f}", ctx.stats())

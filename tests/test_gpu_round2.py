@@ -557,6 +557,11 @@ def test_sweep_wk_from_atoms_equals_batched_passes(ctx, oracle, metric, monkeypa
         lw_over = dm.gap_sweep(K, subset=subset)
         assert ctx.stats()["wk_atoms"] == -1  # more classes than the cap: the batched passes did it
         monkeypatch.delenv("RID_WK_ATOM_CAP", raising=False)
+        # BUILD's picks 3..K come from the chain's sums by default; RID_SWEEP_BUILD_FIRST=1: BUILD(K.max) up front
+        monkeypatch.setenv("RID_SWEEP_BUILD_FIRST", "1")
+        lw_first = dm.gap_sweep(K, subset=subset)
+        monkeypatch.delenv("RID_SWEEP_BUILD_FIRST", raising=False)
+        assert np.array_equal(lw_atoms, lw_first)
         assert np.array_equal(lw_atoms, lw_batch) and np.array_equal(lw_atoms, lw_over)
         assert np.max(np.abs(lw_atoms - ref)) < 1e-12
     dm.free()
