@@ -71,7 +71,8 @@ long long rid_ctx_swaps(const rid_ctx *ctx);
  * 2-4 milliseconds of the last rid_clusterboot spent in c1 / in the batched first picks + waiting for the replica
  * pulls / in the replicates, 5 bytes the last replica pull moved over NVLink, 6 look-ahead iterations enqueued per
  * replicate, 7 host milliseconds spent inside the enqueue calls of the replicates, 8 milliseconds the last replica pull
- * took on the copy stream. */
+ * took on the copy stream, 9 rid_clusterboot calls that took c1 from the sweep, 10 classes of the common refinement of
+ * the last sweep's partitions (the "atoms" its W.k pass grouped the rows by; -1: too many, batched passes ran). */
 double rid_ctx_stat(const rid_ctx *ctx, int which);
 /* Give the cached device buffers back to the driver (collective when world > 1: call it on every rank). */
 int rid_ctx_trim(rid_ctx *ctx);
@@ -128,6 +129,9 @@ int rid_pam(rid_dmat *dm, const int *subset, int m, int k, int *medoids, int *la
             double *avg_sil, int *n_swaps);
 
 /* ---- clusGapExt(..., FUNcluster=pam, random=FALSE, diss=TRUE) k-loop, R/RaceID_utils.R:58-61 ----------- */
+/* logW[Kmax].  With subset == NULL the PAM(k) results of k = 2..Kmax stay with the (immutable) matrix: clustexp follows
+ * the sweep with fpc::clusterboot, whose first step is the same pam(as.dist(D), cln) call (R/RaceID_utils.R:113,132), and
+ * rid_clusterboot takes c1 from there instead of repeating it (identical by construction; RID_NO_MEMO=1 disables). */
 int rid_gap_sweep(rid_dmat *dm, const int *subset, int m, int Kmax, double *logW);
 
 /* ---- fpc::clusterboot(..., clustermethod=pamkdCBI, k) as called at R/RaceID_utils.R:132-133 ------------ */
