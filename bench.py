@@ -740,7 +740,10 @@ def main():
                 "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "s8 x s8 -> s32 tensor cores, exact (distance; f64 DMMA for euclidean) + u32/u64 fixed point (PAM)", "data": "synthetic",
                 "config": {"workload": workload_name(a), "seed": a.seed, "parallelism": f"row-block shard x{world}",
-                           "l2": "inputs (distance matrix %.1f GB) larger than L2" % (N * N * 4 / 1e9)},
+                           "l2": "inputs (distance matrix %.1f GB) larger than L2" % (N * N * 4 / 1e9),
+                           "c1": ("clusterboot's c1 = pam(D, cln) is the sweep's PAM(cln) of the SAME step (identical call on the same "
+                                  "matrix, computed once inside the timed region; RID_NO_MEMO=1 repeats it: +30 ms at cfg4)"
+                                  if a.sat and a.cln <= a.clustnr else "computed by rid_clusterboot")},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "result_digest": digest, "n_swaps": res["n_swaps_per_step"], "parity_spot": spot,
                 "dist_tflops": (detail.get("gram_i8") or detail.get("gram") or {}).get("tflops_algorithmic_2N2G"),
